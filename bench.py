@@ -1,0 +1,305 @@
+#!/usr/bin/env python
+"""bench.py — PM particle-steps/s of the B200-native force loop (BASELINE.json metric).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl reference]
+
+A "step" is one pass of the hot path over the resident particle set: zero mesh -> CIC paint ->
+R2C FFT -> fused Green's x gradient pass -> 3x C2R FFT -> fused read3 + kick + drift
+(jaxpm/ode.py:100-117 around jaxpm/pm.py:12-58).  Workload: SIZE^3 particles on a SIZE^3 mesh
+(default 512^3, the size the metric is quoted on), Planck15 Gaussian ICs (L = SIZE Mpc/h), 1LPT at
+a = 0.1, then W untimed + K timed drift-kick steps towards a = 1 (relative/displacement mode, the
+mode of the reference's published runs).
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
+(oracle/, NumPy/SciPy; JAX is not installable here) on a bounded sub-box of the same workload.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "pm_particle_steps_per_sec"
+UNIT = "particle-steps/s"
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index=0, period=0.1):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake",
+            }
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+                time.sleep(self.period)
+        except Exception as e:  # NVML missing: report it, do not fake numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU arm: the oracle (NumPy/SciPy restatement of the reference) on a bounded sample
+# ---------------------------------------------------------------------------------------
+def cpu_step_rate(n_sample, steps, warmup=0):
+    """Time `steps` drift-kick steps of an n_sample^3 sub-box with the oracle.  Returns
+    (particle-steps/s, seconds per step, threads)."""
+    import numpy as np
+    from oracle import cosmology as OC
+    from oracle import ode as OO
+    shape = (n_sample,) * 3
+    rng = np.random.default_rng(0)
+    grid = np.stack(np.meshgrid(*[np.arange(n_sample)] * 3, indexing="ij"), -1).astype(np.float32)
+    disp = (0.5 * rng.standard_normal(grid.shape)).astype(np.float32)
+    vel = (0.01 * rng.standard_normal(grid.shape)).astype(np.float32)
+    cosmo = OC.Planck15()
+    OC.growth_tables(cosmo)
+    drift, kick = OO.symplectic_ode(shape, cosmo, paint_absolute_pos=False)
+    if warmup:
+        disp, vel = OO.semi_implicit_euler(drift, kick, disp, vel, 0.1, 0.1 + 0.01 * warmup, warmup)
+    t0 = time.perf_counter()
+    OO.semi_implicit_euler(drift, kick, disp, vel, 0.2, 0.2 + 0.01 * steps, steps)
+    dt = time.perf_counter() - t0
+    return n_sample**3 * steps / dt, dt / steps, os.cpu_count()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_s = 128 if (args.steps + args.warmup) <= 12 else 64
+    rate, sps, cores = cpu_step_rate(n_s, args.steps, args.warmup)
+    sample = (f"{args.steps} drift-kick steps of a {n_s}^3-particle / {n_s}^3-mesh sub-box of the "
+              f"{args.size}^3 workload (same cell size), oracle NumPy/SciPy port, scipy.fft workers=all")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.size}^3 particles on {args.size}^3 mesh, PM drift-kick steps "
+                               f"(timed on a {n_s}^3 sub-box)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------
+def time_kernel(fn, iters=5, warm=2):
+    import torch
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e-3 / iters
+
+
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    from jaxpm_b200 import _lib, ops
+    from jaxpm_b200.cosmology import Planck15, linear_matter_power
+    from jaxpm_b200.ode import kick_drift_coefficients
+    from jaxpm_b200.pm import linear_field, lpt
+
+    if world > 1:
+        from bench_multi import run_multi  # sharded path (jaxpm_b200/halo.py, pfft.py)
+        return run_multi(args, world, rank, dev)
+
+    N = args.size
+    shape = (N, N, N)
+    npart = N**3
+    cosmo = Planck15()
+    box = (float(N),) * 3
+    K, W = args.steps, args.warmup
+
+    # ---- workload set-up (untimed): ICs -> 1LPT at a=0.1 -> displacement + momentum ------------
+    ic = linear_field(shape, box, lambda k: linear_matter_power(cosmo, k), seed=0, device=dev)
+    dx, p, _ = lpt(cosmo, ic, a=0.1, order=1)
+    del ic
+    disp, vel = dx.contiguous(), p.contiguous()
+    plan = ops.get_plan(shape, dev)
+    d, k = kick_drift_coefficients(cosmo, 0.1, 1.0, K + W, "symplectic")
+    ops.axpby(1.0, disp, d[0], vel, out=disp)
+    torch.cuda.empty_cache()
+
+    def step(n):
+        ops.pm_step_(plan, disp, vel, k[n], d[n + 1] if n + 1 < K + W else 0.0, True)
+
+    for n in range(W):
+        step(n)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for n in range(W, W + K):
+        step(n)
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    value = npart * K / t_dev
+
+    # ---- per-kernel durations (CUDA events, live, on the evolved particle set) -----------------
+    peak, peak_kind = _peaks()
+    mesh = torch.zeros(shape, dtype=torch.float32, device=dev)
+    f3 = torch.empty((3, *shape), dtype=torch.float32, device=dev)
+    spec = torch.empty(plan.spec_shape, dtype=torch.complex64, device=dev)
+    spec3 = torch.empty((3, *plan.spec_shape), dtype=torch.complex64, device=dev)
+    scratch_p, scratch_v = disp.clone(), vel.clone()
+
+    def k_paint():
+        mesh.zero_()
+        ops.cic_paint_dx_(mesh, disp)
+
+    t_zero = time_kernel(lambda: mesh.zero_())
+    t_paint = time_kernel(k_paint) - t_zero
+    ops.call("jpm_fft3d_r2c", plan.handle, ops.stream(), ops.ptr(mesh), ops.ptr(spec))
+    t_r2c = time_kernel(lambda: ops.call("jpm_fft3d_r2c", plan.handle, ops.stream(), ops.ptr(mesh), ops.ptr(spec)))
+    t_ksp = time_kernel(lambda: ops.call("jpm_greens_grad_c64", plan.handle, ops.stream(), ops.ptr(spec),
+                                         ops.ptr(spec3), 1.0 / npart, 0.0, None, 0, 0.0))
+    t_c2r = time_kernel(lambda: ops.call("jpm_ifft3d_c2r", plan.handle, ops.stream(), ops.ptr(spec3), ops.ptr(f3), 3))
+    t_read = time_kernel(lambda: ops.read3_kick_drift_(f3, scratch_p, scratch_v, 0.0, 0.0, True))
+    nc = npart
+    kernels = {
+        "cic_paint_dx": {"s": t_paint, "alg_bytes": 12 * npart + 4 * nc},
+        "mesh_memset": {"s": t_zero, "alg_bytes": 4 * nc},
+        "fft_r2c(cuFFT)": {"s": t_r2c, "alg_bytes": 8 * nc},
+        "greens_grad": {"s": t_ksp, "alg_bytes": 16 * nc},
+        "ifft_c2r_x3(cuFFT)": {"s": t_c2r, "alg_bytes": 24 * nc},
+        "read3_kick_drift": {"s": t_read, "alg_bytes": 48 * npart + 12 * nc},
+    }
+    for v in kernels.values():
+        v["GBps"] = v["alg_bytes"] / v["s"] / 1e9
+        v["frac"] = v["GBps"] / peak
+    own = {n: v for n, v in kernels.items() if "cuFFT" not in n and n != "mesh_memset"}
+    dom_name = max(own, key=lambda n: own[n]["s"])
+    dom = own[dom_name]
+    step_alg_bytes = 60 * npart + 64 * nc
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                "step_achieved": step_alg_bytes * K / t_dev / 1e9,
+                "step_frac": step_alg_bytes * K / t_dev / 1e9 / peak,
+                "kernels": {n: {"ms": round(v["s"] * 1e3, 4), "GBps": round(v["GBps"], 1),
+                                "frac": round(v["frac"], 4)} for n, v in kernels.items()}}
+    del mesh, f3, spec, spec3, scratch_p, scratch_v
+    torch.cuda.empty_cache()
+
+    # ---- end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step) -
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    ph = torch.empty(disp.shape, dtype=torch.float32).pin_memory()
+    vh = torch.empty(vel.shape, dtype=torch.float32).pin_memory()
+    ph.copy_(disp)
+    vh.copy_(vel)
+    ops.pm_step_host_(plan, ph, vh, disp, vel, 0.0, 0.0, True)  # warm
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for n in range(e2e_steps):
+        ops.pm_step_host_(plan, ph, vh, disp, vel, 1e-6, 1e-6, True)
+    torch.cuda.synchronize()
+    t_e2e = time.perf_counter() - t0
+    bytes_state = 2 * npart * 12
+    e2e = {"value": npart * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
+           "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
+           "entry": "jpm_pm_step_host_f32 (pinned host pos/vel in, pos/vel out)"}
+
+    # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------------
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        rate, sps, cores = cpu_step_rate(128, 1)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": "1 drift-kick step of a 128^3 sub-box (same cell size), oracle NumPy/SciPy port "
+                         f"of the reference, {sps:.1f} s"}
+
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then PM drift-kick steps "
+                                   f"to a=1 (relative mode), Planck15, L={N} Mpc/h",
+                       "l2": "inputs larger than L2 (particle state 3.2 GB, mesh 0.5 GB at 512^3)",
+                       "parallelism": "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+            "clocks": clocks,
+        }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "b200":
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,231 @@
+/*
+ * jaxpm_b200 — C ABI of the B200-native particle-mesh force loop.
+ *
+ * This is the drop-in boundary.  The reference (JaxPM) has no
+ * FFI of its own: its operator API is the Python functions cited next to each
+ * entry point below; an XLA FFI handler (jaxpm_b200/csrc/xla_ffi.cc) or the
+ * ctypes host layer (jaxpm_b200/_lib.py) binds exactly these symbols.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative jpm_status; the message
+ *     is available from jpm_last_error_string() (thread-local);
+ *   - `stream` is a cudaStream_t passed as void*; kernels are only enqueued on
+ *     it, nothing synchronises or allocates (CUDA-graph / XLA safe), except the
+ *     *_create / *_destroy / *_host entry points, which say so;
+ *   - all pointers are DEVICE pointers unless the name ends in `_host`;
+ *   - the caller owns every buffer; outputs are pre-allocated; in-place
+ *     behaviour is documented per function;
+ *   - meshes are row-major [nx][ny][nz] float32 (z fastest); particle arrays are
+ *     [np][3] float32 in CELL units; spectra are cuFFT R2C half-spectra
+ *     [nx][ny][nz/2+1] complex64 (interleaved re,im).
+ */
+#ifndef JAXPM_B200_H_
+#define JAXPM_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+  JPM_OK = 0,
+  JPM_ERR_INVALID = -1, /* bad argument */
+  JPM_ERR_CUDA = -2,    /* CUDA runtime error */
+  JPM_ERR_CUFFT = -3,   /* cuFFT error */
+  JPM_ERR_NOGPU = -4    /* no usable sm_100 device */
+} jpm_status;
+
+#define JPM_ABI_VERSION 1
+
+int32_t jpm_abi_version(void);
+const char* jpm_last_error_string(void);
+/* Name, SM count and compute capability of the current device (host call). */
+int32_t jpm_device_info(char* name, int32_t name_len, int32_t* sm_count, int32_t* cc_major,
+                        int32_t* cc_minor);
+
+/* ------------------------------------------------------------------------
+ * K1  CIC paint (scatter-add)
+ * ---------------------------------------------------------------------- */
+
+/* jaxpm/painting.py:15-45 `_cic_paint_impl` (wrapper `cic_paint` :48-75).
+ * mesh[(floor(x)+c) mod N] += w * prod_d (1-|x_d-(floor(x_d)+c_d)|), 8 corners.
+ * ACCUMULATES into `mesh` (callers pass zeros, pm.py:28-30).  `weight` is a
+ * per-particle array [np] or NULL (then `weight_scalar` is used).
+ * (pgx,pgy,pgz) is the particle-grid shape used only to form cache-friendly
+ * bricks (pgx*pgy*pgz == np; pass (1,1,np) for an unstructured list). */
+int32_t jpm_cic_paint_f32(void* stream, float* mesh, const float* positions, const float* weight,
+                          float weight_scalar, int64_t np, int32_t nx, int32_t ny, int32_t nz,
+                          int32_t pgx, int32_t pgy, int32_t pgz);
+
+/* jaxpm/painting.py:161-189 `_cic_paint_dx_impl` + jaxpm/painting_utils.py:28-96
+ * `enmesh` (relative mode).  Particle (i,j,k) of the local [nx][ny][nz] grid sits
+ * at (i+hx, j+hy, k) + disp in a mesh of shape [nx+2hx][ny+2hy][nz]; the float
+ * mod / floor-div / rint wrap rule of enmesh is reproduced bit-for-bit,
+ * including the dropped out-of-range index.  ACCUMULATES into `mesh`. */
+int32_t jpm_cic_paint_dx_f32(void* stream, float* mesh, const float* disp, const float* weight,
+                             float weight_scalar, int32_t nx, int32_t ny, int32_t nz, int32_t hx,
+                             int32_t hy);
+
+/* Debug/parity helper: the int32 flat cell index (ix*ny+iy)*nz+iz of the
+ * (0,0,0) corner of every particle, -1 where the reference drops it.
+ * mode 0 = absolute rule (painting.py:35-37), 1 = relative rule (painting_utils.py:53-65)
+ * with mesh shape [nx][ny][nz], halo offsets (hx,hy) and particle grid (nx-2hx,ny-2hy,nz). */
+int32_t jpm_cic_cell_index_i32(void* stream, int32_t* out, const float* pos_or_disp, int64_t np,
+                               int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy,
+                               int32_t mode);
+
+/* ------------------------------------------------------------------------
+ * K5  CIC read (gather) and the fused read3 + kick + drift
+ * ---------------------------------------------------------------------- */
+
+/* jaxpm/painting.py:78-106 `_cic_read_impl` (wrapper `cic_read` :109-128). out[np]. */
+int32_t jpm_cic_read_f32(void* stream, float* out, const float* mesh, const float* positions,
+                         int64_t np, int32_t nx, int32_t ny, int32_t nz);
+
+/* jaxpm/painting.py:218-236 `_cic_read_dx_impl`.  `mesh` is the padded, halo-filled
+ * local mesh [nx+2hx][ny+2hy][nz]; out[nx][ny][nz]. */
+int32_t jpm_cic_read_dx_f32(void* stream, float* out, const float* mesh, const float* disp,
+                            int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy);
+
+/* The three reads + jnp.stack of jaxpm/pm.py:54-56 in one pass: out[np][3] =
+ * scale * (read(fx), read(fy), read(fz)).  relative != 0 selects the
+ * painting_utils rule with halo offsets (then np = nx*ny*nz of the particle grid
+ * and the meshes are [nx+2hx][ny+2hy][nz]). */
+int32_t jpm_cic_read3_f32(void* stream, float* out, const float* fx, const float* fy,
+                          const float* fz, const float* pos_or_disp, float scale, int64_t np,
+                          int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy,
+                          int32_t relative);
+
+/* read3 fused with the ODE update (jaxpm/ode.py:100-117 kick, :91-98 drift; the
+ * FastPM variants :19-58 only change the two scalars):
+ *     F       = (read(fx), read(fy), read(fz)) at pos_in
+ *     vel_out = vel_prev + kick_coef  * F          (kick_coef = dt*1.5*Om/(a^2 E) ...)
+ *     pos_out = pos_prev + drift_coef * vel_drift  (vel_drift = vel_out if use_new_vel
+ *                                                   else vel_in)
+ * Kick-drift (symplectic): pos_prev=pos_in, vel_prev=vel_in, use_new_vel=1, all in place.
+ * Leapfrog-midpoint (diffrax): pos_prev/vel_prev = state n-1, use_new_vel=0, vel_in = v_n.
+ * Output pointers may alias the *_prev pointers.  forces_out (nullable) receives F. */
+int32_t jpm_cic_read3_kick_drift_f32(void* stream, float* pos_out, float* vel_out,
+                                     float* forces_out, const float* fx, const float* fy,
+                                     const float* fz, const float* pos_in, const float* vel_in,
+                                     const float* pos_prev, const float* vel_prev,
+                                     float kick_coef, float drift_coef, int32_t use_new_vel,
+                                     int64_t np, int32_t nx, int32_t ny, int32_t nz, int32_t hx,
+                                     int32_t hy, int32_t relative);
+
+/* ------------------------------------------------------------------------
+ * K6  adjoints (what jax.grad of paint/read transposes to)
+ * ---------------------------------------------------------------------- */
+
+/* value[np] = read(mesh, pos) and grad[np][3] = s_p * d value / d pos with
+ * d(1-|t|)/dt = -sign(t), sign(0)=0 (JAX's abs' convention).  Either output may be NULL.
+ * s_p = grad_scale_scalar * (grad_scale ? grad_scale[p] : 1) folds the cotangent / weight in.
+ * Used for: read VJP wrt positions (cot * grad), paint VJP wrt positions
+ * (weight * grad of read(cotangent mesh)), paint VJP wrt weights (value).
+ * relative as in jpm_cic_read3_f32. */
+int32_t jpm_cic_readgrad_f32(void* stream, float* value, float* grad, const float* mesh,
+                             const float* pos_or_disp, const float* grad_scale,
+                             float grad_scale_scalar, int64_t np, int32_t nx, int32_t ny,
+                             int32_t nz, int32_t hx, int32_t hy, int32_t relative);
+
+/* ------------------------------------------------------------------------
+ * K2/K3/K4  FFT plan and the fused k-space pass
+ * ---------------------------------------------------------------------- */
+
+typedef struct jpm_plan jpm_plan; /* opaque; one stream at a time per plan */
+
+/* Host call; allocates cuFFT plans + work areas + the per-axis tables of
+ * jaxpm/kernels.py:10-23 `fftk` (w_d = 2*pi*fftfreq(N_d)), :62-66
+ * `gradient_kernel` order 1 (a_d = (8 sin w - sin 2w)/6) built in float64 on the host. */
+int32_t jpm_plan_create(jpm_plan** plan, int32_t nx, int32_t ny, int32_t nz);
+int32_t jpm_plan_destroy(jpm_plan* plan);
+
+/* jaxpm/distributed.py:37-38 `fft3d` on a real field: unnormalised forward R2C.
+ * in: real [nx][ny][nz]; out: complex64 [nx][ny][nz/2+1]. */
+int32_t jpm_fft3d_r2c(jpm_plan* plan, void* stream, const float* in, void* out);
+/* jaxpm/distributed.py:41-42 `ifft3d` (`.real` of the inverse) for `batch` Hermitian
+ * half-spectra stored contiguously; UNNORMALISED (callers fold 1/Nc into the
+ * k-space pass). The input spectra are destroyed (cuFFT C2R). batch in {1,3}. */
+int32_t jpm_ifft3d_c2r(jpm_plan* plan, void* stream, void* in, float* out, int32_t batch);
+
+/* Fused k-space pass of jaxpm/pm.py:49-56: for d in 0..2
+ *     out_d = -(i a_d) * ( -1/k^2 [k=0 -> 0] ) * exp(-k^2 r_split^2) * filter(|k|) * delta_k * norm
+ * i.e. jaxpm/kernels.py:69-92 `invlaplace_kernel`, :95-115 `longrange_kernel`, :41-66
+ * `gradient_kernel`, and the optional radial filter slot of jaxpm/ode.py:194-196 /
+ * jaxpm/kernels.py:139-165 (table `filter_tab[n_tab]`, linear in |k| on [0, filter_kmax];
+ * NULL = none).  out: 3 contiguous half-spectra.  norm is typically 1/(nx*ny*nz). */
+int32_t jpm_greens_grad_c64(jpm_plan* plan, void* stream, const void* delta_k, void* out3,
+                            float norm, float r_split, const float* filter_tab, int32_t n_tab,
+                            float filter_kmax);
+
+/* Transpose (VJP) of jpm_greens_grad_c64: out = sum_d (-i a_d)(1/k^2) G filter * in_d * norm, the
+ * k-space half of the adjoint of jaxpm/pm.py:49-56 (in3: 3 contiguous half-spectra). */
+int32_t jpm_greens_div_c64(jpm_plan* plan, void* stream, const void* in3, void* out, float norm,
+                           float r_split, const float* filter_tab, int32_t n_tab,
+                           float filter_kmax);
+
+/* 2LPT shear spectra of jaxpm/pm.py:95-109: out6 = (-a_i a_j)(-1/k^2) delta_k * norm for
+ * (i,j) in (00,11,22,01,02,12) — `gradient_kernel(i)*gradient_kernel(j)*pot_k`. */
+int32_t jpm_lpt2_shear_c64(jpm_plan* plan, void* stream, const void* delta_k, void* out6,
+                           float norm);
+/* delta2 = s00*s11 + s22*(s00+s11) - s01^2 - s02^2 - s12^2 (pm.py:92-109 accumulated form). */
+int32_t jpm_lpt2_source_f32(void* stream, float* delta2, const float* shear6, int64_t ncell);
+
+/* Generic k-space multiply used by linear_field (pm.py:134-143): out = in * tab(|k| scaled)
+ * where kphys^2 = sum_d (w_d * kscale_d)^2 and the table is linear in log10(kphys) on
+ * [log10_kmin, log10_kmax] (values are sqrt(P(k) * Nc / V)); k=0 -> tab value at kmin. */
+int32_t jpm_kfilter_logtab_c64(jpm_plan* plan, void* stream, const void* in, void* out,
+                               const float* tab, int32_t n_tab, float log10_kmin,
+                               float log10_kmax, float kscale_x, float kscale_y, float kscale_z,
+                               float norm);
+
+/* ------------------------------------------------------------------------
+ * composed hot path
+ * ---------------------------------------------------------------------- */
+
+/* jaxpm/pm.py:12-58 `pm_forces` given a painted density: real `density` [nx][ny][nz] ->
+ * three force meshes (fx,fy,fz contiguous, each [nx][ny][nz]).  Uses plan scratch. */
+int32_t jpm_density_to_force_meshes(jpm_plan* plan, void* stream, const float* density,
+                                    float* force3, float r_split, const float* filter_tab,
+                                    int32_t n_tab, float filter_kmax);
+
+/* One full PM step on resident particles (single GPU, absolute or relative positions):
+ * memset mesh -> paint -> R2C -> greens-grad -> 3x C2R -> read3+kick+drift (kick-drift
+ * form, in place on pos/vel).  jaxpm/ode.py:100-117 + :91-98 around jaxpm/pm.py:12-58. */
+int32_t jpm_pm_step_f32(jpm_plan* plan, void* stream, float* pos, float* vel, float kick_coef,
+                        float drift_coef, int32_t relative);
+
+/* Same step through HOST buffers (pinned or pageable): H2D pos/vel, step, D2H pos/vel.
+ * Synchronises `stream`.  This is the end-to-end entry a host-side caller binds. */
+int32_t jpm_pm_step_host_f32(jpm_plan* plan, void* stream, float* pos_host, float* vel_host,
+                             float* pos_dev, float* vel_dev, float kick_coef, float drift_coef,
+                             int32_t relative);
+
+/* Number of kernels of THIS library launched since process start (for bench accounting). */
+int64_t jpm_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * small elementwise helpers (keep host-side glue off third-party ops)
+ * ---------------------------------------------------------------------- */
+/* out = a*x + b*y (y may be NULL -> a*x); out may alias x or y. */
+int32_t jpm_axpby_f32(void* stream, float* out, float a, const float* x, float b, const float* y,
+                      int64_t n);
+/* out[i][3] = (float)grid(i)[d] + disp[i][d]: absolute positions from a relative state. */
+int32_t jpm_grid_plus_disp_f32(void* stream, float* out, const float* disp, int32_t nx,
+                               int32_t ny, int32_t nz, int32_t ox, int32_t oy);
+
+/* ------------------------------------------------------------------------
+ * multi-GPU building blocks (jaxpm/distributed.py:45-113; one process per GPU)
+ * ---------------------------------------------------------------------- */
+/* Copy / add a [x0:x1) x [y0:y1) x nz sub-box between a strided mesh and a packed buffer. */
+int32_t jpm_pack_box_f32(void* stream, float* packed, const float* mesh, int32_t ny, int32_t nz,
+                         int32_t x0, int32_t x1, int32_t y0, int32_t y1);
+int32_t jpm_unpack_box_f32(void* stream, float* mesh, const float* packed, int32_t ny, int32_t nz,
+                           int32_t x0, int32_t x1, int32_t y0, int32_t y1, int32_t accumulate);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JAXPM_B200_H_ */

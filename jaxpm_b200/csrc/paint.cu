@@ -1,0 +1,125 @@
+// K1 — CIC paint (scatter-add), absolute and relative rules.
+//   reference: jaxpm/painting.py:15-45 (_cic_paint_impl), :161-189 (_cic_paint_dx_impl),
+//              jaxpm/painting_utils.py:28-112 (enmesh + _scatter_chunk)
+#include "common.cuh"
+
+namespace jpm {
+
+// ---------------------------------------------------------------------------------
+// Direct path: one particle per thread, 8 REDG.E.ADD.F32 into the global mesh.  Correct
+// for any particle order; used for small meshes and as the fallback of the tiled path.
+// ---------------------------------------------------------------------------------
+template <bool REL>
+__global__ void __launch_bounds__(256)
+paint_direct_kernel(float* __restrict__ mesh, const float* __restrict__ pos,
+                    const float* __restrict__ weight, float wscalar, long long np, int nx, int ny,
+                    int nz, int pnx, int pny, int pnz, int hx, int hy) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+    const float px = ld_stream(pos + 3 * p + 0);
+    const float py = ld_stream(pos + 3 * p + 1);
+    const float pz = ld_stream(pos + 3 * p + 2);
+    int bi = 0, bj = 0, bk = 0;
+    if (REL) {
+      bk = (int)(p % pnz);
+      const long long t = p / pnz;
+      bj = (int)(t % pny) + hy;
+      bi = (int)(t / pny) + hx;
+    }
+    const Cic1 cx = cic_1d<REL, false>(bi, px, nx);
+    const Cic1 cy = cic_1d<REL, false>(bj, py, ny);
+    const Cic1 cz = cic_1d<REL, false>(bk, pz, nz);
+    const float w = weight ? weight[p] : wscalar;
+    const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
+    const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
+          // reference order: (kx*ky)*kz, then * weight (painting.py:29-33)
+          const float k = w * ((wx[a] * wy[b]) * wz[c]);
+          atomicAdd(mesh + ((long long)ix[a] * ny + iy[b]) * nz + iz[c], k);
+        }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+cell_index_kernel(int* __restrict__ out, const float* __restrict__ pos, long long np, int nx, int ny,
+                  int nz, int hx, int hy, int rel) {
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= np) return;
+  const float px = pos[3 * p], py = pos[3 * p + 1], pz = pos[3 * p + 2];
+  int i, j, k;
+  if (rel) {
+    const int pnz = nz, pny = ny - 2 * hy;
+    const int bk = (int)(p % pnz);
+    const long long t = p / pnz;
+    const int bj = (int)(t % pny) + hy, bi = (int)(t / pny) + hx;
+    i = cic_rel<false>(bi, px, nx).i0;
+    j = cic_rel<false>(bj, py, ny).i0;
+    k = cic_rel<false>(bk, pz, nz).i0;
+  } else {
+    i = cic_abs<false>(px, nx).i0;
+    j = cic_abs<false>(py, ny).i0;
+    k = cic_abs<false>(pz, nz).i0;
+  }
+  out[p] = (i < 0 || j < 0 || k < 0) ? -1 : (i * ny + j) * nz + k;
+}
+
+template <bool REL>
+static int32_t launch_paint(cudaStream_t s, float* mesh, const float* pos, const float* weight,
+                            float wscalar, long long np, int nx, int ny, int nz, int pnx, int pny,
+                            int pnz, int hx, int hy) {
+  if (np == 0) return JPM_OK;
+  const int threads = 256;
+  long long blocks = (np + threads - 1) / threads;
+  const long long cap = (long long)kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  paint_direct_kernel<REL><<<(int)blocks, threads, 0, s>>>(mesh, pos, weight, wscalar, np, nx, ny,
+                                                           nz, pnx, pny, pnz, hx, hy);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+}  // namespace jpm
+
+using namespace jpm;
+
+extern "C" int32_t jpm_cic_paint_f32(void* stream, float* mesh, const float* positions,
+                                     const float* weight, float weight_scalar, int64_t np,
+                                     int32_t nx, int32_t ny, int32_t nz, int32_t pgx, int32_t pgy,
+                                     int32_t pgz) {
+  JPM_CHECK_ARG(mesh && (positions || np == 0), "null mesh/positions");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && np >= 0, "bad mesh shape / np");
+  JPM_CHECK_ARG((int64_t)nx * ny * nz < (1ll << 31), "mesh too large for int32 cell ids");
+  JPM_CHECK_ARG((int64_t)pgx * pgy * pgz == np, "particle grid does not match np");
+  return launch_paint<false>((cudaStream_t)stream, mesh, positions, weight, weight_scalar, np, nx,
+                             ny, nz, pgx, pgy, pgz, 0, 0);
+}
+
+extern "C" int32_t jpm_cic_paint_dx_f32(void* stream, float* mesh, const float* disp,
+                                        const float* weight, float weight_scalar, int32_t nx,
+                                        int32_t ny, int32_t nz, int32_t hx, int32_t hy) {
+  JPM_CHECK_ARG(mesh && disp, "null mesh/disp");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && hx >= 0 && hy >= 0, "bad shape / halo");
+  const int mx = nx + 2 * hx, my = ny + 2 * hy;
+  JPM_CHECK_ARG((int64_t)mx * my * nz < (1ll << 31), "mesh too large for int32 cell ids");
+  return launch_paint<true>((cudaStream_t)stream, mesh, disp, weight, weight_scalar,
+                            (long long)nx * ny * nz, mx, my, nz, nx, ny, nz, hx, hy);
+}
+
+extern "C" int32_t jpm_cic_cell_index_i32(void* stream, int32_t* out, const float* pos_or_disp,
+                                          int64_t np, int32_t nx, int32_t ny, int32_t nz,
+                                          int32_t hx, int32_t hy, int32_t mode) {
+  JPM_CHECK_ARG(out && pos_or_disp && np >= 0, "null pointer");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0, "bad mesh shape");
+  if (mode) JPM_CHECK_ARG((int64_t)(nx - 2 * hx) * (ny - 2 * hy) * nz == np, "np != particle grid");
+  if (np == 0) return JPM_OK;
+  cell_index_kernel<<<div_up(np, 256), 256, 0, (cudaStream_t)stream>>>(out, pos_or_disp, np, nx, ny,
+                                                                       nz, hx, hy, mode);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}

@@ -1,0 +1,346 @@
+// K2/K3/K4 — FFT plan (cuFFT R2C / batched C2R), the fused k-space pass, and the
+// composed force / step entry points.
+//   reference: jaxpm/distributed.py:37-42 (fft3d/ifft3d), jaxpm/kernels.py:10-23,41-115,139-165,
+//              jaxpm/pm.py:12-58 (pm_forces), :88-124 (2LPT source), jaxpm/ode.py:91-117
+#include <cufft.h>
+
+#include <cmath>
+#include <vector>
+
+#include "common.cuh"
+
+struct jpm_plan {
+  int nx, ny, nz, nzh;
+  long long ncell, nspec;
+  cufftHandle r2c = 0, c2r1 = 0, c2r3 = 0;
+  void* work = nullptr;
+  size_t work_bytes = 0;
+  // per-axis tables (device): w_d (rad/cell, fp32) and a_d = (8 sin w - sin 2w)/6
+  float *wx = nullptr, *wy = nullptr, *wz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
+  // scratch owned by the plan, used by the composed entry points
+  float* density = nullptr;   // [ncell]
+  float2* spec = nullptr;     // [nspec]
+  float2* spec3 = nullptr;    // [3*nspec]
+  float* force3 = nullptr;    // [3*ncell]
+};
+
+namespace jpm {
+
+#define JPM_CUFFT(call)                                                          \
+  do {                                                                           \
+    cufftResult r__ = (call);                                                    \
+    if (r__ != CUFFT_SUCCESS) {                                                  \
+      jpm::set_error("%s failed: cufft error %d (%s:%d)", #call, (int)r__, __FILE__, __LINE__); \
+      return JPM_ERR_CUFFT;                                                      \
+    }                                                                            \
+  } while (0)
+
+// ---------------------------------------------------------------------------------
+// K3: delta_k -> NOUT spectra, one HBM pass (read 8 B, write NOUT*8 B per mode).
+// KIND 0: force spectra  out_d = i a_d delta / k^2 * G * norm       (3 outputs)
+// KIND 1: shear spectra  out_ij = a_i a_j delta / k^2 * norm        (6 outputs: 00 11 22 01 02 12)
+// KIND 2: transpose of KIND 0 (its VJP): out = sum_d (-i a_d) in_d / k^2 * G * norm   (3 inputs, 1 output)
+// Threads run along z (fastest axis) so loads/stores of the interleaved complex rows coalesce.
+// ---------------------------------------------------------------------------------
+template <int KIND>
+__global__ void __launch_bounds__(256)
+kspace_kernel(const float2* __restrict__ dk, float2* __restrict__ out, const float* __restrict__ wx,
+              const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
+              const float* __restrict__ ay, const float* __restrict__ az, int nx, int ny, int nzh,
+              long long nspec, float norm, float r_split2, const float* __restrict__ ftab, int ntab,
+              float fscale) {
+  const long long nrows = (long long)nx * ny;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int ix = (int)(row / ny), iy = (int)(row % ny);
+    const float kx = wx[ix], ky = wy[iy];
+    const float kxy2 = kx * kx + ky * ky;  // ((0 + kx^2) + ky^2), kernels.py:87
+    const float a0 = ax[ix], a1 = ay[iy];
+    for (int iz = threadIdx.x; iz < nzh; iz += blockDim.x) {
+      const float kz = wz[iz];
+      const float kk = kxy2 + kz * kz;
+      float g = (kk == 0.f) ? 0.f : (1.0f / kk);  // -invlaplace = 1/k^2, 0 at k=0
+      g *= norm;
+      if (KIND != 1) {
+        if (r_split2 != 0.f) g *= expf(-kk * r_split2);
+        if (ftab) {
+          const float t = sqrtf(kk) * fscale;
+          const int i = min((int)t, ntab - 2);
+          const float fr = fminf(t - (float)i, 1.0f);
+          g *= ftab[i] + fr * (ftab[i + 1] - ftab[i]);
+        }
+      }
+      const long long o = row * nzh + iz;
+      const float a2 = az[iz];
+      if (KIND == 2) {
+        const float2 d0 = __ldcs(dk + o), d1 = __ldcs(dk + nspec + o), d2 = __ldcs(dk + 2 * nspec + o);
+        const float g0 = a0 * g, g1 = a1 * g, g2 = a2 * g;
+        // (-i a g)(re + i im) = (a g im, -a g re)
+        __stcs(out + o, make_float2(g0 * d0.y + g1 * d1.y + g2 * d2.y,
+                                    -(g0 * d0.x + g1 * d1.x + g2 * d2.x)));
+        continue;
+      }
+      const float2 d = __ldcs(dk + o);
+      if (KIND == 0) {
+        // -(i a) * (-1/k^2) * delta = i a g delta : (re,im) -> (-a g im, a g re)
+        const float g0 = a0 * g, g1 = a1 * g, g2 = a2 * g;
+        __stcs(out + o, make_float2(-g0 * d.y, g0 * d.x));
+        __stcs(out + nspec + o, make_float2(-g1 * d.y, g1 * d.x));
+        __stcs(out + 2 * nspec + o, make_float2(-g2 * d.y, g2 * d.x));
+      } else {
+        // (i a_i)(i a_j) * (-1/k^2) * delta = a_i a_j g delta
+        const float m[6] = {a0 * a0 * g, a1 * a1 * g, a2 * a2 * g, a0 * a1 * g, a0 * a2 * g, a1 * a2 * g};
+#pragma unroll
+        for (int q = 0; q < 6; ++q) __stcs(out + q * nspec + o, make_float2(m[q] * d.x, m[q] * d.y));
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+kfilter_logtab_kernel(const float2* __restrict__ in, float2* __restrict__ out,
+                      const float* __restrict__ wx, const float* __restrict__ wy,
+                      const float* __restrict__ wz, int nx, int ny, int nzh, const float* __restrict__ tab,
+                      int ntab, float lkmin, float lkmax, float sx, float sy, float sz, float norm) {
+  const long long nrows = (long long)nx * ny;
+  const float inv = (float)(ntab - 1) / (lkmax - lkmin);
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const int ix = (int)(row / ny), iy = (int)(row % ny);
+    const float kx = wx[ix] * sx, ky = wy[iy] * sy;
+    const float kxy2 = kx * kx + ky * ky;
+    for (int iz = threadIdx.x; iz < nzh; iz += blockDim.x) {
+      const float kz = wz[iz] * sz;
+      const float kk = kxy2 + kz * kz;
+      float t = (kk > 0.f) ? (0.5f * log10f(kk) - lkmin) * inv : 0.f;
+      t = fminf(fmaxf(t, 0.f), (float)(ntab - 1));
+      const int i = min((int)t, ntab - 2);
+      const float fr = t - (float)i;
+      const float m = (tab[i] + fr * (tab[i + 1] - tab[i])) * norm;
+      const long long o = row * nzh + iz;
+      const float2 d = in[o];
+      out[o] = make_float2(m * d.x, m * d.y);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+lpt2_source_kernel(float* __restrict__ d2, const float* __restrict__ s, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float s00 = s[i], s11 = s[n + i], s22 = s[2 * n + i];
+    const float s01 = s[3 * n + i], s02 = s[4 * n + i], s12 = s[5 * n + i];
+    // pm.py:92-109: delta2 = s11*s00 + s22*(s00+s11) - s01^2 - s02^2 - s12^2
+    float v = s11 * s00;
+    v -= s01 * s01;
+    v -= s02 * s02;
+    v += s22 * (s00 + s11);
+    v -= s12 * s12;
+    d2[i] = v;
+  }
+}
+
+static void build_tables(int n, int nh, std::vector<float>& w, std::vector<float>& a) {
+  // fftk: w = 2*pi*fftfreq(n) (kernels.py:10-23, [ext] jaxdecomp.fftfreq3d), stored fp32;
+  // gradient_kernel order 1 (kernels.py:62-66) evaluated in fp64 at the fp32 frequency.
+  w.resize(nh);
+  a.resize(nh);
+  for (int i = 0; i < nh; ++i) {
+    const int f = (i < (n + 1) / 2) ? i : i - n;
+    const float wf = (float)(2.0 * M_PI * (double)f / (double)n);
+    w[i] = wf;
+    const double wd = (double)wf;
+    a[i] = (float)((8.0 * std::sin(wd) - std::sin(2.0 * wd)) / 6.0);
+    // the reference takes .real of a C2C inverse (distributed.py:41-42): the self-conjugate
+    // Nyquist mode of an odd kernel contributes nothing.  a(pi) is 0 up to rounding; make it exact
+    // so that the C2R transform sees a Hermitian spectrum.
+    if (n % 2 == 0 && i == n / 2) a[i] = 0.f;
+  }
+}
+
+static int32_t upload(float** dst, const std::vector<float>& v) {
+  JPM_CUDA(cudaMalloc(dst, v.size() * sizeof(float)));
+  JPM_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return JPM_OK;
+}
+
+static int kspace_grid(const jpm_plan* p) {
+  const long long rows = (long long)p->nx * p->ny;
+  const long long cap = (long long)kNumSMs * 8;
+  return (int)(rows < cap ? rows : cap);
+}
+
+}  // namespace jpm
+
+using namespace jpm;
+
+extern "C" int32_t jpm_plan_create(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz) {
+  JPM_CHECK_ARG(out, "null plan pointer");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0, "bad mesh shape");
+  JPM_CHECK_ARG((int64_t)nx * ny * nz < (1ll << 31), "mesh too large for int32 cell ids");
+  jpm_plan* p = new jpm_plan();
+  p->nx = nx; p->ny = ny; p->nz = nz; p->nzh = nz / 2 + 1;
+  p->ncell = (long long)nx * ny * nz;
+  p->nspec = (long long)nx * ny * p->nzh;
+  int n[3] = {nx, ny, nz};
+  size_t ws[3] = {0, 0, 0};
+  cufftHandle* hs[3] = {&p->r2c, &p->c2r1, &p->c2r3};
+  const cufftType types[3] = {CUFFT_R2C, CUFFT_C2R, CUFFT_C2R};
+  const int batches[3] = {1, 1, 3};
+  for (int i = 0; i < 3; ++i) {
+    JPM_CUFFT(cufftCreate(hs[i]));
+    JPM_CUFFT(cufftSetAutoAllocation(*hs[i], 0));
+    const long long idist = (types[i] == CUFFT_R2C) ? p->ncell : p->nspec;
+    const long long odist = (types[i] == CUFFT_R2C) ? p->nspec : p->ncell;
+    JPM_CUFFT(cufftMakePlanMany(*hs[i], 3, n, nullptr, 1, (int)idist, nullptr, 1, (int)odist, types[i],
+                                batches[i], &ws[i]));
+    if (ws[i] > p->work_bytes) p->work_bytes = ws[i];
+  }
+  if (p->work_bytes) JPM_CUDA(cudaMalloc(&p->work, p->work_bytes));
+  for (int i = 0; i < 3; ++i) JPM_CUFFT(cufftSetWorkArea(*hs[i], p->work));
+  std::vector<float> w, a;
+  int32_t rc;
+  build_tables(nx, nx, w, a);
+  if ((rc = upload(&p->wx, w)) || (rc = upload(&p->ax, a))) return rc;
+  build_tables(ny, ny, w, a);
+  if ((rc = upload(&p->wy, w)) || (rc = upload(&p->ay, a))) return rc;
+  build_tables(nz, p->nzh, w, a);
+  if ((rc = upload(&p->wz, w)) || (rc = upload(&p->az, a))) return rc;
+  JPM_CUDA(cudaMalloc(&p->density, p->ncell * sizeof(float)));
+  JPM_CUDA(cudaMalloc(&p->spec, p->nspec * sizeof(float2)));
+  JPM_CUDA(cudaMalloc(&p->spec3, 3 * p->nspec * sizeof(float2)));
+  JPM_CUDA(cudaMalloc(&p->force3, 3 * p->ncell * sizeof(float)));
+  *out = p;
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_plan_destroy(jpm_plan* p) {
+  if (!p) return JPM_OK;
+  if (p->r2c) cufftDestroy(p->r2c);
+  if (p->c2r1) cufftDestroy(p->c2r1);
+  if (p->c2r3) cufftDestroy(p->c2r3);
+  void* bufs[] = {p->work, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->density, p->spec, p->spec3, p->force3};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  delete p;
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_fft3d_r2c(jpm_plan* p, void* stream, const float* in, void* out) {
+  JPM_CHECK_ARG(p && in && out, "null pointer");
+  JPM_CUFFT(cufftSetStream(p->r2c, (cudaStream_t)stream));
+  JPM_CUFFT(cufftExecR2C(p->r2c, const_cast<float*>(in), (cufftComplex*)out));
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_ifft3d_c2r(jpm_plan* p, void* stream, void* in, float* out, int32_t batch) {
+  JPM_CHECK_ARG(p && in && out, "null pointer");
+  JPM_CHECK_ARG(batch == 1 || batch == 3, "batch must be 1 or 3");
+  cufftHandle h = (batch == 3) ? p->c2r3 : p->c2r1;
+  JPM_CUFFT(cufftSetStream(h, (cudaStream_t)stream));
+  JPM_CUFFT(cufftExecC2R(h, (cufftComplex*)in, out));
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_greens_grad_c64(jpm_plan* p, void* stream, const void* delta_k, void* out3,
+                                       float norm, float r_split, const float* filter_tab,
+                                       int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(p && delta_k && out3, "null pointer");
+  JPM_CHECK_ARG(!filter_tab || (n_tab >= 2 && filter_kmax > 0.f), "bad filter table");
+  const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
+  kspace_kernel<0><<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)delta_k, (float2*)out3, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->nx, p->ny,
+      p->nzh, p->nspec, norm, r_split * r_split, filter_tab, n_tab, fscale);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_greens_div_c64(jpm_plan* p, void* stream, const void* in3, void* out,
+                                      float norm, float r_split, const float* filter_tab,
+                                      int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(p && in3 && out, "null pointer");
+  JPM_CHECK_ARG(!filter_tab || (n_tab >= 2 && filter_kmax > 0.f), "bad filter table");
+  const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
+  kspace_kernel<2><<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)in3, (float2*)out, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->nx, p->ny,
+      p->nzh, p->nspec, norm, r_split * r_split, filter_tab, n_tab, fscale);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_lpt2_shear_c64(jpm_plan* p, void* stream, const void* delta_k, void* out6,
+                                      float norm) {
+  JPM_CHECK_ARG(p && delta_k && out6, "null pointer");
+  kspace_kernel<1><<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)delta_k, (float2*)out6, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->nx, p->ny,
+      p->nzh, p->nspec, norm, 0.f, nullptr, 0, 0.f);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_lpt2_source_f32(void* stream, float* delta2, const float* shear6, int64_t ncell) {
+  JPM_CHECK_ARG(delta2 && shear6 && ncell >= 0, "null pointer");
+  if (ncell == 0) return JPM_OK;
+  long long blocks = (ncell + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  lpt2_source_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(delta2, shear6, ncell);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_kfilter_logtab_c64(jpm_plan* p, void* stream, const void* in, void* out,
+                                          const float* tab, int32_t n_tab, float log10_kmin,
+                                          float log10_kmax, float kscale_x, float kscale_y,
+                                          float kscale_z, float norm) {
+  JPM_CHECK_ARG(p && in && out && tab && n_tab >= 2 && log10_kmax > log10_kmin, "bad arguments");
+  kfilter_logtab_kernel<<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)in, (float2*)out, p->wx, p->wy, p->wz, p->nx, p->ny, p->nzh, tab, n_tab,
+      log10_kmin, log10_kmax, kscale_x, kscale_y, kscale_z, norm);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_density_to_force_meshes(jpm_plan* p, void* stream, const float* density,
+                                               float* force3, float r_split, const float* filter_tab,
+                                               int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(p && density && force3, "null pointer");
+  int32_t rc;
+  if ((rc = jpm_fft3d_r2c(p, stream, density, p->spec))) return rc;
+  if ((rc = jpm_greens_grad_c64(p, stream, p->spec, p->spec3, 1.0f / (float)p->ncell, r_split,
+                                filter_tab, n_tab, filter_kmax)))
+    return rc;
+  return jpm_ifft3d_c2r(p, stream, p->spec3, force3, 3);
+}
+
+extern "C" int32_t jpm_pm_step_f32(jpm_plan* p, void* stream, float* pos, float* vel, float kick_coef,
+                                   float drift_coef, int32_t relative) {
+  JPM_CHECK_ARG(p && pos && vel, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  int32_t rc;
+  JPM_CUDA(cudaMemsetAsync(p->density, 0, p->ncell * sizeof(float), s));
+  if (relative)
+    rc = jpm_cic_paint_dx_f32(stream, p->density, pos, nullptr, 1.0f, p->nx, p->ny, p->nz, 0, 0);
+  else
+    rc = jpm_cic_paint_f32(stream, p->density, pos, nullptr, 1.0f, p->ncell, p->nx, p->ny, p->nz,
+                           p->nx, p->ny, p->nz);
+  if (rc) return rc;
+  if ((rc = jpm_density_to_force_meshes(p, stream, p->density, p->force3, 0.f, nullptr, 0, 0.f)))
+    return rc;
+  return jpm_cic_read3_kick_drift_f32(stream, pos, vel, nullptr, p->force3, p->force3 + p->ncell,
+                                      p->force3 + 2 * p->ncell, pos, vel, pos, vel, kick_coef,
+                                      drift_coef, 1, p->ncell, p->nx, p->ny, p->nz, 0, 0, relative);
+}
+
+extern "C" int32_t jpm_pm_step_host_f32(jpm_plan* p, void* stream, float* pos_host, float* vel_host,
+                                        float* pos_dev, float* vel_dev, float kick_coef,
+                                        float drift_coef, int32_t relative) {
+  JPM_CHECK_ARG(p && pos_host && vel_host && pos_dev && vel_dev, "null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t bytes = (size_t)p->ncell * 3 * sizeof(float);
+  JPM_CUDA(cudaMemcpyAsync(pos_dev, pos_host, bytes, cudaMemcpyHostToDevice, s));
+  JPM_CUDA(cudaMemcpyAsync(vel_dev, vel_host, bytes, cudaMemcpyHostToDevice, s));
+  int32_t rc = jpm_pm_step_f32(p, stream, pos_dev, vel_dev, kick_coef, drift_coef, relative);
+  if (rc) return rc;
+  JPM_CUDA(cudaMemcpyAsync(pos_host, pos_dev, bytes, cudaMemcpyDeviceToHost, s));
+  JPM_CUDA(cudaMemcpyAsync(vel_host, vel_dev, bytes, cudaMemcpyDeviceToHost, s));
+  JPM_CUDA(cudaStreamSynchronize(s));
+  return JPM_OK;
+}

@@ -1,0 +1,254 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Tolerances: cell indices bit-exact; fields 1e-5 relative
+(fp32, max|a-b|/max|b|); power spectrum 1e-4."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import displaced, lagrangian_grid, rel_err
+from oracle import cosmology as OC
+from oracle import kernels as OK
+from oracle import ode as OO
+from oracle import painting as OP
+from oracle import pm as OPM
+from oracle import utils as OU
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-5
+SHAPES = [(16, 16, 16), (32, 32, 64), (24, 40, 18)]
+
+
+def T(x, dev):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("sigma", [0.0, 0.4, 3.0])
+def test_cell_indices_bit_exact(cuda, shape, sigma):
+    from jaxpm_b200 import ops
+    grid, disp = displaced(shape, sigma)
+    pos = grid + disp
+    # absolute rule, incl. negative / beyond-box coordinates
+    pos[0, 0, 0] = (-0.25, -1e-7, shape[2] + 2.5)
+    idx, _ = OP.cic_indices_weights(pos, shape)
+    flat = (idx[:, 0, 0] * shape[1] + idx[:, 0, 1]) * shape[2] + idx[:, 0, 2]
+    got = ops.cell_index(T(pos, cuda), shape).cpu().numpy()
+    np.testing.assert_array_equal(got, flat)
+    # relative rule (float mod), incl. the dropped-index edge case
+    disp[1, 1, 1, 0] = -1.0 - 1e-7
+    disp[0, 0, 0] = (-1e-7, 0.3, -0.2)
+    ridx, _ = OP.enmesh_rel(OP._pmid(shape, 0, 0), disp.reshape(-1, 3), shape)
+    c0 = ridx[:, 0]
+    ok = np.all((c0 >= 0) & (c0 < np.asarray(shape)), axis=-1)
+    rflat = np.where(ok, (c0[:, 0] * shape[1] + c0[:, 1]) * shape[2] + c0[:, 2], -1)
+    got = ops.cell_index(T(disp, cuda), shape, relative=True).cpu().numpy()
+    np.testing.assert_array_equal(got, rflat)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("sigma", [0.0, 0.5, 2.0, 8.0])
+def test_cic_paint_read_absolute(cuda, shape, sigma):
+    from jaxpm_b200.painting import cic_paint, cic_read
+    grid, disp = displaced(shape, sigma)
+    pos = grid + disp
+    rng = np.random.default_rng(2)
+    w = rng.uniform(0.5, 1.5, shape).astype(np.float32)
+    for weight, wt in ((1.0, 1.0), (w, T(w, cuda))):
+        ref = OP.cic_paint(np.zeros(shape, np.float32), pos, weight)
+        got = cic_paint(torch.zeros(shape, device=cuda), T(pos, cuda), wt).cpu().numpy()
+        assert rel_err(got, ref) < FIELD_TOL
+    assert abs(got.sum(dtype=np.float64) - w.sum(dtype=np.float64)) < 1e-4 * w.sum()
+    mesh = rng.standard_normal(shape).astype(np.float32)
+    ref = OP.cic_read(mesh, pos)
+    got = cic_read(T(mesh, cuda), T(pos, cuda)).cpu().numpy()
+    assert got.shape == shape
+    assert rel_err(got, ref) < FIELD_TOL
+
+
+def test_cic_paint_accumulates_and_unstructured(cuda):
+    from jaxpm_b200.painting import cic_paint, cic_read
+    shape = (16, 16, 16)
+    rng = np.random.default_rng(4)
+    pos = rng.uniform(-5, 25, (1000, 3)).astype(np.float32)      # np != ncell, outside the box
+    base = rng.standard_normal(shape).astype(np.float32)
+    ref = OP.cic_paint(base, pos, 2.5)
+    got = cic_paint(T(base, cuda), T(pos, cuda), 2.5).cpu().numpy()
+    assert rel_err(got, ref) < FIELD_TOL
+    assert rel_err(cic_read(T(base, cuda), T(pos, cuda)).cpu().numpy(), OP.cic_read(base, pos)) < FIELD_TOL
+    # empty input
+    assert cic_read(T(base, cuda), torch.zeros((0, 3), device=cuda)).shape == (0,)
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+@pytest.mark.parametrize("sigma", [0.0, 0.5, 4.0])
+def test_cic_paint_read_relative(cuda, shape, sigma):
+    from jaxpm_b200.painting import cic_paint_dx, cic_read_dx
+    _, disp = displaced(shape, sigma)
+    disp[0, 0, 0] = (-1e-7, 0.3, -0.2)   # dropped-corner edge case must match too
+    ref = OP.cic_paint_dx(disp)
+    got = cic_paint_dx(T(disp, cuda)).cpu().numpy()
+    assert rel_err(got, ref) < FIELD_TOL
+    w = np.random.default_rng(2).uniform(0.5, 1.5, shape).astype(np.float32)
+    assert rel_err(cic_paint_dx(T(disp, cuda), weight=T(w, cuda)).cpu().numpy(),
+                   OP.cic_paint_dx(disp, w)) < FIELD_TOL
+    mesh = np.random.default_rng(3).standard_normal(shape).astype(np.float32)
+    assert rel_err(cic_read_dx(T(mesh, cuda), T(disp, cuda)).cpu().numpy(),
+                   OP.cic_read_dx(mesh, disp)) < FIELD_TOL
+    with pytest.raises(ValueError):
+        cic_paint_dx(T(disp, cuda), weight=torch.ones(3, 3, 3, device=cuda))
+
+
+@pytest.mark.parametrize("halo", [(4, 0), (0, 6), (4, 6)])
+def test_padded_relative_kernels(cuda, halo):
+    """The per-shard kernels of the distributed path: padded local mesh, offsets (hx, hy)."""
+    from jaxpm_b200 import ops
+    shape = (8, 12, 16)
+    _, disp = displaced(shape, 1.5)
+    ref = OP.cic_paint_dx_padded(disp, 1.0, halo)
+    mesh = torch.zeros(ref.shape, device=cuda)
+    ops.cic_paint_dx_(mesh, T(disp, cuda), 1.0, halo)
+    assert rel_err(mesh.cpu().numpy(), ref) < FIELD_TOL
+    pm = np.random.default_rng(1).standard_normal(ref.shape).astype(np.float32)
+    got = ops.cic_read_dx(T(pm, cuda), T(disp, cuda), halo).cpu().numpy()
+    assert rel_err(got, OP.cic_read_dx_padded(pm, disp, halo)) < FIELD_TOL
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 32, 64), (12, 20, 18)])
+def test_fft_and_kspace(cuda, shape):
+    from jaxpm_b200 import ops
+    from jaxpm_b200.distributed import fft3d, ifft3d
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal(shape).astype(np.float32)
+    xk = fft3d(T(x, cuda))
+    ref = OK.fft3d(x.astype(np.float64))[..., :shape[2] // 2 + 1]
+    assert rel_err(np.abs(xk.cpu().numpy() - ref), np.abs(ref)) < FIELD_TOL
+    assert rel_err(ifft3d(xk).cpu().numpy(), x) < FIELD_TOL
+    # fused Green's x gradient pass vs the unfused reference chain (pm.py:49-56)
+    plan = ops.get_plan(shape, cuda)
+    f3 = ops.force_meshes_from_density(T(x, cuda), plan).cpu().numpy()
+    dk = OK.fft3d(x.astype(np.float64))
+    kvec = OK.fftk(dk)
+    pot = dk * OK.invlaplace_kernel(kvec)
+    for d in range(3):
+        ref = OK.ifft3d(-OK.gradient_kernel(kvec, d) * pot)
+        assert rel_err(f3[d], ref) < FIELD_TOL
+
+
+@pytest.mark.parametrize("absolute", [True, False])
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 32, 64)])
+def test_pm_forces(cuda, shape, absolute):
+    from jaxpm_b200.pm import pm_forces
+    grid, disp = displaced(shape, 1.0)
+    x = grid + disp if absolute else disp
+    ref = OPM.pm_forces(x, mesh_shape=shape, paint_absolute_pos=absolute)
+    got = pm_forces(T(x, cuda), mesh_shape=shape, paint_absolute_pos=absolute).cpu().numpy()
+    assert got.shape == (*shape, 3)
+    assert rel_err(got, ref) < FIELD_TOL
+    # optional long-range split and radial filter slot (PGD)
+    from jaxpm_b200.kernels import pgd_filter_table
+    ref = OPM.pm_forces(x, mesh_shape=shape, paint_absolute_pos=absolute, r_split=1.3,
+                        kfilter=OK.PGD_kernel(OK.fftk(shape), 0.4, 2.5))
+    got = pm_forces(T(x, cuda), mesh_shape=shape, paint_absolute_pos=absolute, r_split=1.3,
+                    filter_tab=pgd_filter_table(0.4, 2.5, 1 << 16)).cpu().numpy()
+    assert rel_err(got, ref) < 1e-4   # table-interpolated filter
+
+
+def _ic(shape, box):
+    from jaxpm_b200.cosmology import Planck15, linear_matter_power
+    from helpers import gaussian_ic
+    c = Planck15()
+    return gaussian_ic(shape, box, lambda k: linear_matter_power(c, k))
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("absolute", [True, False])
+@pytest.mark.parametrize("cfg", [((32, 32, 32), (256., 256., 256.)), ((32, 32, 64), (256., 256., 512.))])
+def test_lpt(cuda, cfg, absolute, order):
+    """Mirrors tests/test_against_fpm.py::test_lpt_absolute/relative (32^3 and 32x32x64)."""
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.painting import cic_paint, cic_paint_dx
+    from jaxpm_b200.pm import lpt
+    shape, box = cfg
+    ic = _ic(shape, box)
+    grid = lagrangian_grid(shape)
+    ocos = OC.Planck15()
+    ref = OPM.lpt(ocos, ic, particles=grid if absolute else None, a=0.1, order=order)
+    got = lpt(Planck15(), T(ic, cuda), particles=T(grid, cuda) if absolute else None, a=0.1, order=order)
+    for g, r in zip(got, ref):
+        assert rel_err(g.cpu().numpy(), r) < FIELD_TOL
+    if absolute:
+        field = cic_paint(torch.zeros(shape, device=cuda), T(grid, cuda) + got[0]).cpu().numpy()
+        rfield = OP.cic_paint(np.zeros(shape, np.float32), grid + ref[0])
+    else:
+        field = cic_paint_dx(got[0]).cpu().numpy()
+        rfield = OP.cic_paint_dx(ref[0])
+    np.testing.assert_allclose(field, rfield, rtol=1e-4, atol=1e-3)   # the reference's own tolerances
+    _, ps = OU.power_spectrum(field, box_shape=box)
+    _, rps = OU.power_spectrum(rfield, box_shape=box)
+    assert OU.MSRE(ps, rps) < 1e-8 and np.abs(ps / rps - 1).max() < 1e-4
+
+
+@pytest.mark.parametrize("absolute", [True, False])
+def test_nbody_config1(cuda, absolute):
+    """configs[0]: 64^3 / 64^3, 256 Mpc/h, Planck15, 1LPT at a=0.1 then 10 PM steps to a=1."""
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.ode import nbody_kick_drift
+    from jaxpm_b200.painting import cic_paint, cic_paint_dx
+    from jaxpm_b200.pm import lpt
+    shape, box = (64, 64, 64), (256.,) * 3
+    ic = _ic(shape, box)
+    grid = lagrangian_grid(shape)
+    cosmo, ocos = Planck15(), OC.Planck15()
+    dx, p, _ = OPM.lpt(ocos, ic, particles=grid if absolute else None, a=0.1, order=1)
+    drift, kick = OO.symplectic_ode(shape, ocos, paint_absolute_pos=absolute)
+    rpos, rvel = OO.semi_implicit_euler(drift, kick, grid + dx if absolute else dx, p, 0.1, 1.0, 10)
+    gdx, gp, _ = lpt(cosmo, T(ic, cuda), particles=T(grid, cuda) if absolute else None, a=0.1, order=1)
+    start = (T(grid, cuda) + gdx) if absolute else gdx
+    pos, vel = nbody_kick_drift(cosmo, start.clone(), gp.clone(), 0.1, 1.0, 10, mesh_shape=shape,
+                                paint_absolute_pos=absolute)
+    if absolute:
+        field = cic_paint(torch.zeros(shape, device=cuda), pos).cpu().numpy()
+        rfield = OP.cic_paint(np.zeros(shape, np.float32), rpos)
+    else:
+        field = cic_paint_dx(pos).cpu().numpy()
+        rfield = OP.cic_paint_dx(rpos)
+    # chaotic amplification of fp32 rounding over 10 steps: positions agree to ~1e-4 cells
+    assert np.abs(pos.cpu().numpy() - rpos).max() < 5e-3
+    _, ps = OU.power_spectrum(field, box_shape=box)
+    _, rps = OU.power_spectrum(rfield, box_shape=box)
+    assert np.abs(ps / rps - 1).max() < 1e-4
+
+
+def test_leapfrog_midpoint_and_rhs(cuda):
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.ode import make_diffrax_ode, make_ode_fn, nbody_leapfrog_midpoint
+    shape = (16, 16, 16)
+    grid, disp = displaced(shape, 0.5)
+    vel = (0.02 * np.random.default_rng(7).standard_normal(disp.shape)).astype(np.float32)
+    cosmo, ocos = Planck15(), OC.Planck15()
+    dpos, dvel = make_ode_fn(shape)((T(grid + disp, cuda), T(vel, cuda)), 0.3, cosmo)
+    rdpos, rdvel = OO.make_ode_fn(shape)((grid + disp, vel), 0.3, ocos)
+    assert rel_err(dpos.cpu().numpy(), rdpos) < FIELD_TOL and rel_err(dvel.cpu().numpy(), rdvel) < FIELD_TOL
+    y = make_diffrax_ode(shape, paint_absolute_pos=False)(0.3, torch.stack([T(disp, cuda), T(vel, cuda)]), cosmo)
+    ry = OO.make_diffrax_ode(shape, paint_absolute_pos=False)(0.3, np.stack([disp, vel]), ocos)
+    assert rel_err(y.cpu().numpy(), ry) < FIELD_TOL
+    p, v = nbody_leapfrog_midpoint(cosmo, T(disp, cuda), T(vel, cuda), 0.1, 0.2, 5, paint_absolute_pos=False)
+    ry = OO.leapfrog_midpoint(OO.make_diffrax_ode(shape, paint_absolute_pos=False), np.stack([disp, vel]),
+                              0.1, 0.2, 5, ocos)
+    assert rel_err(p.cpu().numpy(), ry[0]) < 1e-4 and rel_err(v.cpu().numpy(), ry[1]) < 1e-4
+
+
+def test_host_step_entry_matches_device_step(cuda):
+    from jaxpm_b200 import ops
+    shape = (32, 32, 32)
+    grid, disp = displaced(shape, 0.8)
+    vel = (0.02 * np.random.default_rng(7).standard_normal(disp.shape)).astype(np.float32)
+    plan = ops.get_plan(shape, cuda)
+    pos_d, vel_d = T(grid + disp, cuda), T(vel, cuda)
+    ops.pm_step_(plan, pos_d, vel_d, 0.01, 0.02, False)
+    ph = torch.as_tensor(grid + disp).pin_memory()
+    vh = torch.as_tensor(vel).pin_memory()
+    ops.pm_step_host_(plan, ph, vh, torch.empty_like(pos_d), torch.empty_like(vel_d), 0.01, 0.02, False)
+    torch.cuda.synchronize()
+    assert rel_err(ph.numpy(), pos_d.cpu().numpy()) < 1e-6 and rel_err(vh.numpy(), vel_d.cpu().numpy()) < 1e-5
