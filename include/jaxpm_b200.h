@@ -203,6 +203,36 @@ int32_t jpm_pm_step_host_f32(jpm_plan* plan, void* stream, float* pos_host, floa
                              float* pos_dev, float* vel_dev, float kick_coef, float drift_coef,
                              int32_t relative);
 
+/* ------------------------------------------------------------------------
+ * tile-sorted resident particle state (the fast path for many steps)
+ * ---------------------------------------------------------------------- */
+typedef struct jpm_sim jpm_sim; /* opaque; owns a tile-sorted copy of (pos, vel) */
+
+/* Host call.  Mesh [nx][ny][nz]; particles form a [pnx][pny][pnz] grid (ids in that order).
+ * relative != 0: state holds displacements and nx = pnx+2hx, ny = pny+2hy, nz = pnz
+ * (jaxpm/painting.py:161-189); else absolute positions (jaxpm/painting.py:15-45).
+ * tile in {8,16,32} cells, margin = cells a particle may move per step before the slow
+ * (global-memory) fallback is used.  `plan` (nullable) enables jpm_sim_step. */
+int32_t jpm_sim_create(jpm_sim** sim, jpm_plan* plan, int32_t nx, int32_t ny, int32_t nz,
+                       int32_t pnx, int32_t pny, int32_t pnz, int32_t hx, int32_t hy,
+                       int32_t relative, int32_t tile, int32_t margin);
+int32_t jpm_sim_destroy(jpm_sim* sim);
+/* Build the sorted state from user-order arrays pos[np][3], vel[np][3] / write it back. */
+int32_t jpm_sim_load(jpm_sim* sim, void* stream, const float* pos, const float* vel);
+int32_t jpm_sim_store(jpm_sim* sim, void* stream, float* pos, float* vel);
+/* mesh += paint(state) (same arithmetic as jpm_cic_paint[_dx]_f32, weight 1); also records the
+ * tile occupancy that the following jpm_sim_read_kick_drift uses to re-sort. */
+int32_t jpm_sim_paint(jpm_sim* sim, void* stream, float* mesh);
+/* vel += kick*F(pos); pos += drift*vel for every particle (jaxpm/ode.py:91-117), F gathered from
+ * the three force meshes through shared-memory boxes; writes the next tile ordering. */
+int32_t jpm_sim_read_kick_drift(jpm_sim* sim, void* stream, const float* fx, const float* fy,
+                                const float* fz, float kick_coef, float drift_coef);
+/* One PM step on the resident state: memset, paint, R2C, greens-grad, 3x C2R, read+kick+drift. */
+int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_coef);
+/* out2_host[0..1] = particles that took the global-memory fallback in paint / read so far
+ * (synchronises the stream). */
+int32_t jpm_sim_stats_host(jpm_sim* sim, void* stream, int64_t* out2_host);
+
 /* Number of kernels of THIS library launched since process start (for bench accounting). */
 int64_t jpm_kernel_launch_count(void);
 

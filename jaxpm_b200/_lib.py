@@ -41,6 +41,14 @@ SIGNATURES = {
     "jpm_density_to_force_meshes": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_pm_step_f32": ([vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_pm_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32, i32], i32),
+    "jpm_sim_create": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
+    "jpm_sim_destroy": ([vp], i32),
+    "jpm_sim_load": ([vp, vp, vp, vp], i32),
+    "jpm_sim_store": ([vp, vp, vp, vp], i32),
+    "jpm_sim_paint": ([vp, vp, vp], i32),
+    "jpm_sim_read_kick_drift": ([vp, vp, vp, vp, vp, f32, f32], i32),
+    "jpm_sim_step": ([vp, vp, f32, f32], i32),
+    "jpm_sim_stats_host": ([vp, vp, C.POINTER(i64)], i32),
     "jpm_kernel_launch_count": ([], i64),
     "jpm_axpby_f32": ([vp, vp, f32, vp, f32, vp, i64], i32),
     "jpm_grid_plus_disp_f32": ([vp, vp, vp, i32, i32, i32, i32, i32], i32),

@@ -138,6 +138,11 @@ lpt2_source_kernel(float* __restrict__ d2, const float* __restrict__ s, long lon
   }
 }
 
+float* plan_density(jpm_plan* p) { return p->density; }
+float* plan_force3(jpm_plan* p) { return p->force3; }
+long long plan_ncell(jpm_plan* p) { return p->ncell; }
+void plan_dims(jpm_plan* p, int* nx, int* ny, int* nz) { *nx = p->nx; *ny = p->ny; *nz = p->nz; }
+
 static void build_tables(int n, int nh, std::vector<float>& w, std::vector<float>& a) {
   // fftk: w = 2*pi*fftfreq(n) (kernels.py:10-23, [ext] jaxdecomp.fftfreq3d), stored fp32;
   // gradient_kernel order 1 (kernels.py:62-66) evaluated in fp64 at the fp32 frequency.

@@ -156,7 +156,7 @@ using namespace jpm;
 extern "C" int32_t jpm_cic_read_f32(void* stream, float* out, const float* mesh,
                                     const float* positions, int64_t np, int32_t nx, int32_t ny,
                                     int32_t nz) {
-  JPM_CHECK_ARG(out && mesh && positions && np >= 0, "null pointer");
+  JPM_CHECK_ARG(np >= 0 && mesh && (np == 0 || (out && positions)), "null pointer");
   JPM_CHECK_MESH(nx, ny, nz);
   return launch_read<1, 0>((cudaStream_t)stream, false, out, nullptr, nullptr, mesh, nullptr,
                            nullptr, positions, nullptr, nullptr, nullptr, 1.0f, 0.f, 0.f, 0, np, nx,

@@ -137,12 +137,15 @@ def kick_drift_coefficients(cosmo, a0, a1, nsteps, scheme="symplectic"):
 
 
 def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_absolute_pos=True,
-                     scheme="symplectic", halo_size=0, sharding=None, callback=None):
+                     scheme="symplectic", halo_size=0, sharding=None, callback=None, resident=True,
+                     tile=None, margin=2):
     """Run `nsteps` drift-kick steps in place on (pos, vel) and return them.
 
     The first drift is a plain axpy; every following force evaluation is one fused
     paint -> FFT -> k-space -> 3x iFFT -> read3+kick+drift chain, with the drift of the NEXT
-    step folded into the same kernel that applies the kick."""
+    step folded into the same kernel that applies the kick.  `resident=True` keeps the particles
+    in the tile-sorted device state of jaxpm_b200/csrc/sim.cu between steps (fast for scattered,
+    late-time distributions); `resident=False` runs the order-preserving kernels every step."""
     pos, vel = as_f32(pos), as_f32(vel)
     relative = not paint_absolute_pos
     mesh_shape = tuple(pos.shape[:3]) if (mesh_shape is None or relative) else tuple(mesh_shape)
@@ -151,12 +154,24 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
     if not _single(sharding):
         from . import halo
         return halo.nbody_kick_drift(pos, vel, d, k, mesh_shape, halo_size, sharding, callback)
-    plan = ops.get_plan(mesh_shape, pos.device)
+    if not resident:
+        plan = ops.get_plan(mesh_shape, pos.device)
+        for n in range(nsteps):
+            dn = d[n + 1] if n + 1 < nsteps else 0.0
+            ops.pm_step_(plan, pos, vel, k[n], dn, relative)
+            if callback is not None:
+                callback(n, pos, vel)
+        return pos, vel
+    # resident tile-sorted state: load once, K fused steps, store back in the caller's order
+    sim = ops.Sim(mesh_shape, pos.shape[:3] if pos.dim() == 4 else (1, 1, pos.numel() // 3), relative,
+                  pos.device, tile=tile, margin=margin)
+    sim.load(pos, vel)
     for n in range(nsteps):
-        dn = d[n + 1] if n + 1 < nsteps else 0.0
-        ops.pm_step_(plan, pos, vel, k[n], dn, relative)
+        sim.step(k[n], d[n + 1] if n + 1 < nsteps else 0.0)
         if callback is not None:
+            sim.store(pos, vel)
             callback(n, pos, vel)
+    sim.store(pos, vel)
     return pos, vel
 
 

@@ -274,3 +274,52 @@ def unpack_box_(mesh, packed, x0, x1, y0, y1, accumulate=False):
     call("jpm_unpack_box_f32", stream(), ptr(mesh, torch.float32), ptr(packed, torch.float32), ny, nz,
          x0, x1, y0, y1, int(accumulate))
     return mesh
+
+
+class Sim:
+    """Tile-sorted resident particle state (jpm_sim): load once, step many times, store back."""
+
+    def __init__(self, mesh_shape, particle_shape, relative, device, halo=(0, 0), tile=None, margin=2,
+                 with_plan=True):
+        self.mesh_shape = tuple(int(s) for s in mesh_shape)
+        self.pshape = tuple(int(s) for s in particle_shape)
+        self.relative, self.device, self.halo = bool(relative), device, halo
+        if tile is None:
+            tile = 16 if min(self.mesh_shape) >= 64 else 8
+        self.tile, self.margin = tile, margin
+        self.plan = get_plan(self.mesh_shape, device) if with_plan else None
+        h = C.c_void_p()
+        with torch.cuda.device(device):
+            call("jpm_sim_create", C.byref(h), self.plan.handle if self.plan else None, *self.mesh_shape,
+                 *self.pshape, halo[0], halo[1], int(self.relative), tile, margin)
+        self.handle = h
+
+    def __del__(self):
+        try:
+            if self.handle:
+                _lib.load().jpm_sim_destroy(self.handle)
+        except Exception:
+            pass
+
+    def load(self, pos, vel):
+        call("jpm_sim_load", self.handle, stream(), ptr(pos, torch.float32), ptr(vel, torch.float32))
+
+    def store(self, pos, vel):
+        call("jpm_sim_store", self.handle, stream(), ptr(pos, torch.float32), ptr(vel, torch.float32))
+
+    def paint_(self, mesh):
+        assert tuple(mesh.shape) == self.mesh_shape
+        call("jpm_sim_paint", self.handle, stream(), ptr(mesh, torch.float32))
+        return mesh
+
+    def read_kick_drift(self, force3, kick, drift):
+        call("jpm_sim_read_kick_drift", self.handle, stream(), ptr(force3[0]), ptr(force3[1]),
+             ptr(force3[2]), float(kick), float(drift))
+
+    def step(self, kick, drift):
+        call("jpm_sim_step", self.handle, stream(), float(kick), float(drift))
+
+    def fallback_counts(self):
+        out = (C.c_int64 * 2)()
+        call("jpm_sim_stats_host", self.handle, stream(), out)
+        return int(out[0]), int(out[1])

@@ -122,7 +122,7 @@ def test_fft_and_kspace(cuda, shape):
     x = rng.standard_normal(shape).astype(np.float32)
     xk = fft3d(T(x, cuda))
     ref = OK.fft3d(x.astype(np.float64))[..., :shape[2] // 2 + 1]
-    assert rel_err(np.abs(xk.cpu().numpy() - ref), np.abs(ref)) < FIELD_TOL
+    assert np.abs(xk.cpu().numpy() - ref).max() / np.abs(ref).max() < FIELD_TOL
     assert rel_err(ifft3d(xk).cpu().numpy(), x) < FIELD_TOL
     # fused Green's x gradient pass vs the unfused reference chain (pm.py:49-56)
     plan = ops.get_plan(shape, cuda)
@@ -252,3 +252,49 @@ def test_host_step_entry_matches_device_step(cuda):
     ops.pm_step_host_(plan, ph, vh, torch.empty_like(pos_d), torch.empty_like(vel_d), 0.01, 0.02, False)
     torch.cuda.synchronize()
     assert rel_err(ph.numpy(), pos_d.cpu().numpy()) < 1e-6 and rel_err(vh.numpy(), vel_d.cpu().numpy()) < 1e-5
+
+
+# ---- tile-sorted resident state (jaxpm_b200/csrc/sim.cu) ---------------------------------------
+@pytest.mark.parametrize("relative", [False, True])
+@pytest.mark.parametrize("shape,tile,margin,sigma", [((32, 32, 32), 8, 2, 0.5), ((32, 32, 64), 16, 2, 3.0),
+                                                      ((24, 40, 18), 8, 1, 6.0), ((64, 64, 64), 16, 2, 1.0)])
+def test_sim_load_paint_store(cuda, shape, tile, margin, sigma, relative):
+    from jaxpm_b200 import ops
+    grid, disp = displaced(shape, sigma)
+    if relative:
+        disp[0, 0, 0] = (-1e-7, 0.3, -0.2)
+    x = disp if relative else grid + disp
+    vel = np.random.default_rng(9).standard_normal(x.shape).astype(np.float32)
+    sim = ops.Sim(shape, shape, relative, cuda, tile=tile, margin=margin)
+    sim.load(T(x, cuda), T(vel, cuda))
+    # bit-exact round trip through the sorted state
+    xo, vo = torch.empty(x.shape, device=cuda), torch.empty(x.shape, device=cuda)
+    sim.store(xo, vo)
+    np.testing.assert_array_equal(xo.cpu().numpy(), x)
+    np.testing.assert_array_equal(vo.cpu().numpy(), vel)
+    # paint from the sorted state == oracle paint
+    mesh = sim.paint_(torch.zeros(shape, device=cuda)).cpu().numpy()
+    ref = OP.cic_paint_dx(x) if relative else OP.cic_paint(np.zeros(shape, np.float32), x)
+    assert rel_err(mesh, ref) < FIELD_TOL
+    assert sim.fallback_counts()[0] == 0      # freshly sorted: everything inside its box
+
+
+@pytest.mark.parametrize("relative", [False, True])
+def test_sim_step_matches_order_preserving_path(cuda, relative):
+    """K resident steps == K order-preserving steps == oracle, including particles that leave
+    their box (margin 0 forces the global-memory fallback)."""
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.ode import nbody_kick_drift
+    shape = (32, 32, 32)
+    grid, disp = displaced(shape, 1.0)
+    x = disp if relative else grid + disp
+    vel = (0.3 * np.random.default_rng(9).standard_normal(x.shape)).astype(np.float32)
+    cosmo, ocos = Planck15(), OC.Planck15()
+    drift, kick = OO.symplectic_ode(shape, ocos, paint_absolute_pos=not relative)
+    rp, rv = OO.semi_implicit_euler(drift, kick, x, vel, 0.5, 0.8, 3)
+    for kw in (dict(resident=False), dict(resident=True, tile=8, margin=2), dict(resident=True, tile=8, margin=0),
+               dict(resident=True, tile=16, margin=1)):
+        p, v = nbody_kick_drift(cosmo, T(x, cuda), T(vel, cuda), 0.5, 0.8, 3, mesh_shape=shape,
+                                paint_absolute_pos=not relative, **kw)
+        assert np.abs(p.cpu().numpy() - rp).max() < 2e-4, kw
+        assert rel_err(v.cpu().numpy(), rv) < 1e-4, kw
