@@ -64,24 +64,34 @@ __device__ __forceinline__ int wrap_local(int i, int o, int n) {
   return a;
 }
 
+__device__ __forceinline__ int wrap_global(int a, int n) {  // a in [-n, 2n)
+  if (a < 0) a += n;
+  else if (a >= n) a -= n;
+  return (a >= 0 && a < n) ? a : pymod(a, n);
+}
+
+// relative mode keeps the Lagrangian site packed as (i << 20 | j << 10 | k) in pos.w, so the hot
+// kernels decode it with shifts; absolute mode keeps the plain particle id there.
+__device__ __forceinline__ int pack_ijk(int i, int j, int k) { return (i << 20) | (j << 10) | k; }
+
 template <bool REL>
-__device__ __forceinline__ void sim_stencil(const SimGeom& g, float x, float y, float z, int id,
+__device__ __forceinline__ void sim_stencil(const SimGeom& g, float x, float y, float z, int w,
                                             Cic1& cx, Cic1& cy, Cic1& cz) {
   int bi = 0, bj = 0, bk = 0;
   if (REL) {
-    bk = id % g.pnz;
-    const int t = id / g.pnz;
-    bj = t % g.pny + g.hy;
-    bi = t / g.pny + g.hx;
+    bk = w & 1023;
+    bj = ((w >> 10) & 1023) + g.hy;
+    bi = (w >> 20) + g.hx;
   }
   cx = cic_1d<REL, false>(bi, x, g.nx);
   cy = cic_1d<REL, false>(bj, y, g.ny);
   cz = cic_1d<REL, false>(bk, z, g.nz);
 }
 
+template <int TS>
 __device__ __forceinline__ int tile_of(const SimGeom& g, int i0, int j0, int k0) {
   i0 = max(i0, 0); j0 = max(j0, 0); k0 = max(k0, 0);  // dropped corner (-1) -> tile of cell 0
-  return ((i0 >> g.tshift) * g.nty + (j0 >> g.tshift)) * g.ntz + (k0 >> g.tshift);
+  return ((i0 >> TS) * g.nty + (j0 >> TS)) * g.ntz + (k0 >> TS);
 }
 
 // Warp-aggregated "add n to counter[key]" (RET=false) or slot claim (RET=true: returns this lane's
@@ -102,51 +112,63 @@ __device__ __forceinline__ int warp_claim(int* counter, int key, bool valid) {
 }
 
 // ---- build / re-sort from user arrays -------------------------------------------------------
-template <bool REL>
+template <bool REL, int TS>
 __global__ void __launch_bounds__(256)
 sim_count_kernel(SimGeom g, const float* __restrict__ pos, long long np, int* __restrict__ count) {
-  const long long base = (long long)blockIdx.x * blockDim.x;
-  const long long p = base + threadIdx.x;
+  const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = p < np;
   int tt = 0;
   if (valid) {
+    int w = (int)p;
+    if (REL) {
+      const int k = (int)(p % g.pnz);
+      const long long t = p / g.pnz;
+      w = pack_ijk((int)(t / g.pny), (int)(t % g.pny), k);
+    }
     Cic1 cx, cy, cz;
-    sim_stencil<REL>(g, pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], (int)p, cx, cy, cz);
-    tt = tile_of(g, cx.i0, cy.i0, cz.i0);
+    sim_stencil<REL>(g, pos[3 * p], pos[3 * p + 1], pos[3 * p + 2], w, cx, cy, cz);
+    tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
   }
   warp_claim<false>(count, tt, valid);
 }
 
-template <bool REL>
+template <bool REL, int TS>
 __global__ void __launch_bounds__(256)
 sim_fill_kernel(SimGeom g, const float* __restrict__ pos, const float* __restrict__ vel, long long np,
                 int* __restrict__ cursor, float4* __restrict__ spos, float* __restrict__ svel) {
   const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool valid = p < np;
-  int tt = 0;
+  int tt = 0, w = (int)p;
   float x = 0, y = 0, z = 0;
   if (valid) {
     x = pos[3 * p]; y = pos[3 * p + 1]; z = pos[3 * p + 2];
+    if (REL) {
+      const int k = (int)(p % g.pnz);
+      const long long t = p / g.pnz;
+      w = pack_ijk((int)(t / g.pny), (int)(t % g.pny), k);
+    }
     Cic1 cx, cy, cz;
-    sim_stencil<REL>(g, x, y, z, (int)p, cx, cy, cz);
-    tt = tile_of(g, cx.i0, cy.i0, cz.i0);
+    sim_stencil<REL>(g, x, y, z, w, cx, cy, cz);
+    tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
   }
   const int slot = warp_claim<true>(cursor, tt, valid);
   if (valid) {
-    spos[slot] = make_float4(x, y, z, __int_as_float((int)p));
+    spos[slot] = make_float4(x, y, z, __int_as_float(w));
     svel[slot] = vel[3 * p];
     svel[np + slot] = vel[3 * p + 1];
     svel[2 * np + slot] = vel[3 * p + 2];
   }
 }
 
+template <bool REL>
 __global__ void __launch_bounds__(256)
-sim_store_kernel(const float4* __restrict__ spos, const float* __restrict__ svel, long long np,
+sim_store_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restrict__ svel, long long np,
                  float* __restrict__ pos, float* __restrict__ vel) {
   const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= np) return;
   const float4 p = spos[q];
-  const long long id = __float_as_int(p.w);
+  const int w = __float_as_int(p.w);
+  const long long id = REL ? ((long long)(w >> 20) * g.pny + ((w >> 10) & 1023)) * g.pnz + (w & 1023) : w;
   if (pos) { pos[3 * id] = p.x; pos[3 * id + 1] = p.y; pos[3 * id + 2] = p.z; }
   if (vel) { vel[3 * id] = svel[q]; vel[3 * id + 1] = svel[np + q]; vel[3 * id + 2] = svel[2 * np + q]; }
 }
@@ -179,91 +201,140 @@ sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restric
   if (tid == 1023) start[nt] = part[1023];
 }
 
+__device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
+  asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
+}
+
+// Per-lane view of the 8 corners, selectable at run time so that each lane can walk the corners
+// in a different order (lane-rotated): particles that share a cell then update 8 DIFFERENT
+// addresses at any instant and the shared-memory CAS loops rarely retry.
+struct Corners {
+  int ix[2], iy[2], iz[2];     // wrapped global cell indices (-1 = dropped)
+  int lx[2], ly[2], lz[2];     // box-local coordinates
+  float wx[2], wy[2], wz[2];
+  bool inside;
+};
+
+template <int B>
+__device__ __forceinline__ void make_corners(const SimGeom& g, const Cic1& cx, const Cic1& cy,
+                                             const Cic1& cz, int ox, int oy, int oz, Corners& c) {
+  c.ix[0] = cx.i0; c.ix[1] = cx.i1; c.iy[0] = cy.i0; c.iy[1] = cy.i1; c.iz[0] = cz.i0; c.iz[1] = cz.i1;
+  c.wx[0] = cx.w0; c.wx[1] = cx.w1; c.wy[0] = cy.w0; c.wy[1] = cy.w1; c.wz[0] = cz.w0; c.wz[1] = cz.w1;
+  c.inside = true;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    c.lx[a] = wrap_local(max(c.ix[a], 0), ox, g.nx);
+    c.ly[a] = wrap_local(max(c.iy[a], 0), oy, g.ny);
+    c.lz[a] = wrap_local(max(c.iz[a], 0), oz, g.nz);
+    c.inside = c.inside && c.lx[a] < B && c.ly[a] < B && c.lz[a] < B;
+  }
+}
+
 // ---- paint -------------------------------------------------------------------------------------
-template <bool REL>
-__global__ void __launch_bounds__(256)
+// One CTA per tile.  Box = (T+2M+1)^3 cells, rows padded to an even length BZ so that the flush
+// can use 8-byte vector reductions (REDG.E.ADD.F32x2).
+template <bool REL, int TS, int M>
+__global__ void __launch_bounds__(256, 4)
 sim_paint_kernel(SimGeom g, const float4* __restrict__ spos, const int* __restrict__ start,
                  float* __restrict__ mesh, int* __restrict__ count, unsigned long long* __restrict__ stats) {
+  constexpr int T = 1 << TS, B = T + 2 * M + 1, BZ = (B + 1) & ~1, NBOX = B * B * BZ;
   extern __shared__ float box[];
+  __shared__ int scnt[27];
   const int t = blockIdx.x;
-  const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-  const int ox = (tx << g.tshift) - g.m, oy = (ty << g.tshift) - g.m, oz = (tz << g.tshift) - g.m;
-  const int nbox = g.BX * g.BY * g.BZ;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
-  for (int i = threadIdx.x; i < nbox; i += blockDim.x) box[i] = 0.f;
+  const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
+  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
+  for (int i = threadIdx.x; i < NBOX; i += blockDim.x) box[i] = 0.f;
+  if (threadIdx.x < 27) scnt[threadIdx.x] = 0;
   __syncthreads();
-  for (int qb = beg; qb < end; qb += blockDim.x) {
-    const int q = qb + threadIdx.x;
-    const bool valid = q < end;
-    int tt = 0;
-    if (valid) {
-      const float4 p = __ldcs(spos + q);
-      Cic1 cx, cy, cz;
-      sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-      tt = tile_of(g, cx.i0, cy.i0, cz.i0);
-      const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
-      const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
-      int lx[2], ly[2], lz[2];
-      bool inside = true;
+  const int rot = threadIdx.x & 7;
+  for (int q = beg + threadIdx.x; q < end; q += blockDim.x) {
+    const float4 p = __ldcs(spos + q);
+    Cic1 cx, cy, cz;
+    sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+    Corners c;
+    make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
+    if (c.inside) {
 #pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        lx[a] = wrap_local(max(ix[a], 0), ox, g.nx);
-        ly[a] = wrap_local(max(iy[a], 0), oy, g.ny);
-        lz[a] = wrap_local(max(iz[a], 0), oz, g.nz);
-        inside = inside && lx[a] < g.BX && ly[a] < g.BY && lz[a] < g.BZ;
+      for (int j = 0; j < 8; ++j) {
+        const int cc = (j + rot) & 7;   // run-time corner: select with predicates, not array indexing
+        const bool a = cc & 1, b = cc & 2, d = cc & 4;
+        if (REL && ((a ? c.ix[1] : c.ix[0]) < 0 || (b ? c.iy[1] : c.iy[0]) < 0 || (d ? c.iz[1] : c.iz[0]) < 0))
+          continue;
+        // reference order (kx*ky)*kz, weight 1
+        const float k = ((a ? c.wx[1] : c.wx[0]) * (b ? c.wy[1] : c.wy[0])) * (d ? c.wz[1] : c.wz[0]);
+        atomicAdd(box + ((a ? c.lx[1] : c.lx[0]) * B + (b ? c.ly[1] : c.ly[0])) * BZ + (d ? c.lz[1] : c.lz[0]), k);
       }
+    } else {
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
-            const float k = (wx[a] * wy[b]) * wz[c];
-            if (inside) atomicAdd(box + (lx[a] * g.BY + ly[b]) * g.BZ + lz[c], k);
-            else atomicAdd(mesh + ((long long)ix[a] * g.ny + iy[b]) * g.nz + iz[c], k);
-          }
-      if (!inside) atomicAdd(stats, 1ull);
+      for (int cc = 0; cc < 8; ++cc) {
+        const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+        if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
+        atomicAdd(mesh + ((long long)c.ix[a] * g.ny + c.iy[b]) * g.nz + c.iz[d],
+                  (c.wx[a] * c.wy[b]) * c.wz[d]);
+      }
+      atomicAdd(stats, 1ull);
     }
-    warp_claim<false>(count, tt, valid);
+    // occupancy of the next ordering: shared counters for the 27 surrounding tiles
+    const int i0 = max(cx.i0, 0) >> TS, j0 = max(cy.i0, 0) >> TS, k0 = max(cz.i0, 0) >> TS;
+    int dx = i0 - tx, dy = j0 - ty, dz = k0 - tz;
+    if (dx > 1) dx -= g.ntx; else if (dx < -1) dx += g.ntx;
+    if (dy > 1) dy -= g.nty; else if (dy < -1) dy += g.nty;
+    if (dz > 1) dz -= g.ntz; else if (dz < -1) dz += g.ntz;
+    if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1)
+      atomicAdd(scnt + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1), 1);
+    else
+      atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, 1);
   }
   __syncthreads();
-  // flush the box: rows along z are contiguous in the global mesh
-  for (int i = threadIdx.x; i < nbox; i += blockDim.x) {
-    const float v = box[i];
-    if (v == 0.f) continue;
-    const int lz = i % g.BZ, r = i / g.BZ;
-    const int ly = r % g.BY, lx = r / g.BY;
-    int gx = ox + lx, gy = oy + ly, gz = oz + lz;
-    gx = pymod(gx, g.nx); gy = pymod(gy, g.ny); gz = pymod(gz, g.nz);
-    atomicAdd(mesh + ((long long)gx * g.ny + gy) * g.nz + gz, v);
+  if (threadIdx.x < 27 && scnt[threadIdx.x]) {
+    const int dx = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x % 3 - 1;
+    const int i0 = pymod(tx + dx, g.ntx), j0 = pymod(ty + dy, g.nty), k0 = pymod(tz + dz, g.ntz);
+    atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, scnt[threadIdx.x]);
+  }
+  // flush: pairs along z (8-byte vector reductions when the pair cannot straddle the wrap)
+  const bool vec = ((oz & 1) == 0) && ((g.nz & 1) == 0) && g.nz >= BZ;
+  for (int e = threadIdx.x; e < NBOX / 2; e += blockDim.x) {
+    const float2 v = reinterpret_cast<const float2*>(box)[e];
+    if (v.x == 0.f && v.y == 0.f) continue;
+    const int zp = e % (BZ / 2), r = e / (BZ / 2);
+    const int ly = r % B, lx = r / B;
+    const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
+    float* row = mesh + ((long long)gx * g.ny + gy) * g.nz;
+    const int z0 = oz + 2 * zp;
+    if (vec) {
+      red_add_v2(row + wrap_global(z0, g.nz), v.x, v.y);
+    } else {
+      if (v.x != 0.f) atomicAdd(row + wrap_global(z0, g.nz), v.x);
+      if (v.y != 0.f) atomicAdd(row + wrap_global(z0 + 1, g.nz), v.y);
+    }
   }
 }
 
 // ---- read3 + kick + drift + scatter into the next ordering --------------------------------------
-template <bool REL>
+template <bool REL, int TS, int M>
 __global__ void __launch_bounds__(512)
 sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restrict__ svel,
                 const int* __restrict__ start, const float* __restrict__ f0,
                 const float* __restrict__ f1, const float* __restrict__ f2, float kick, float drift,
                 long long np, int* __restrict__ cursor, float4* __restrict__ npos,
                 float* __restrict__ nvel, unsigned long long* __restrict__ stats) {
+  constexpr int T = 1 << TS, B = T + 2 * M + 1, NBOX = B * B * B;
   extern __shared__ float box[];
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
   const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-  const int ox = (tx << g.tshift) - g.m, oy = (ty << g.tshift) - g.m, oz = (tz << g.tshift) - g.m;
-  const int nbox = g.BX * g.BY * g.BZ;
+  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
   const float* fm[3] = {f0, f1, f2};
-  for (int i = threadIdx.x; i < nbox; i += blockDim.x) {
-    const int lz = i % g.BZ, r = i / g.BZ;
-    const int ly = r % g.BY, lx = r / g.BY;
-    const int gx = pymod(ox + lx, g.nx), gy = pymod(oy + ly, g.ny), gz = pymod(oz + lz, g.nz);
+  for (int e = threadIdx.x; e < NBOX; e += blockDim.x) {
+    const int lz = e % B, r = e / B;
+    const int ly = r % B, lx = r / B;
+    const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny), gz = wrap_global(oz + lz, g.nz);
     const long long o = ((long long)gx * g.ny + gy) * g.nz + gz;
 #pragma unroll
-    for (int f = 0; f < 3; ++f) box[f * nbox + i] = __ldg(fm[f] + o);
+    for (int f = 0; f < 3; ++f) box[f * NBOX + e] = __ldg(fm[f] + o);
   }
   __syncthreads();
   for (int qb = beg; qb < end; qb += blockDim.x) {
@@ -276,38 +347,26 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
       p = __ldcs(spos + q);
       Cic1 cx, cy, cz;
       sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-      tt = tile_of(g, cx.i0, cy.i0, cz.i0);
-      const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
-      const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
-      int lx[2], ly[2], lz[2];
-      bool inside = true;
-#pragma unroll
-      for (int a = 0; a < 2; ++a) {
-        lx[a] = wrap_local(max(ix[a], 0), ox, g.nx);
-        ly[a] = wrap_local(max(iy[a], 0), oy, g.ny);
-        lz[a] = wrap_local(max(iz[a], 0), oz, g.nz);
-        inside = inside && lx[a] < g.BX && ly[a] < g.BY && lz[a] < g.BZ;
-      }
+      tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
+      Corners c;
+      make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
       float acc[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-      for (int a = 0; a < 2; ++a)
+      for (int cc = 0; cc < 8; ++cc) {
+        const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+        if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
+        const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
+        if (c.inside) {
+          const int o = (c.lx[a] * B + c.ly[b]) * B + c.lz[d];
 #pragma unroll
-        for (int b = 0; b < 2; ++b)
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
+        } else {
+          const long long o = ((long long)c.ix[a] * g.ny + c.iy[b]) * g.nz + c.iz[d];
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
-            const float k = (wx[a] * wy[b]) * wz[c];
-            if (inside) {
-              const int o = (lx[a] * g.BY + ly[b]) * g.BZ + lz[c];
-#pragma unroll
-              for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * nbox + o], k, acc[f]);
-            } else {
-              const long long o = ((long long)ix[a] * g.ny + iy[b]) * g.nz + iz[c];
-#pragma unroll
-              for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
-            }
-          }
-      if (!inside) atomicAdd(stats + 1, 1ull);
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
+        }
+      }
+      if (!c.inside) atomicAdd(stats + 1, 1ull);
 #pragma unroll
       for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], __ldcs(svel + f * np + q));
       p.x = fmaf(drift, v[0], p.x);
@@ -322,6 +381,29 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
     }
   }
 }
+
+template <int TS, int M> constexpr int paint_smem() {
+  constexpr int B = (1 << TS) + 2 * M + 1;
+  return B * B * ((B + 1) & ~1) * (int)sizeof(float);
+}
+template <int TS, int M> constexpr int read_smem() {
+  constexpr int B = (1 << TS) + 2 * M + 1;
+  return 3 * B * B * B * (int)sizeof(float);
+}
+
+// (tile shift, margin) instantiations
+#define JPM_SIM_DISPATCH(ts, m, MACRO)                        \
+  do {                                                        \
+    if (ts == 3 && m == 0) { MACRO(3, 0); }                   \
+    else if (ts == 3 && m == 1) { MACRO(3, 1); }              \
+    else if (ts == 3 && m == 2) { MACRO(3, 2); }              \
+    else if (ts == 3 && m == 3) { MACRO(3, 3); }              \
+    else if (ts == 4 && m == 0) { MACRO(4, 0); }              \
+    else if (ts == 4 && m == 1) { MACRO(4, 1); }              \
+    else if (ts == 4 && m == 2) { MACRO(4, 2); }              \
+    else if (ts == 4 && m == 3) { MACRO(4, 3); }              \
+    else { set_error("unsupported tile/margin"); return JPM_ERR_INVALID; } \
+  } while (0)
 
 static SimGeom make_geom(int nx, int ny, int nz, int pny, int pnz, int hx, int hy, int tile, int m) {
   SimGeom g;
@@ -347,11 +429,15 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && pnx > 0 && pny > 0 && pnz > 0, "bad shape");
   JPM_CHECK_ARG((int64_t)nx * ny * nz < (1ll << 31), "mesh too large for int32 cell ids");
   JPM_CHECK_ARG((int64_t)pnx * pny * pnz < (1ll << 31), "too many particles for int32 ids");
-  JPM_CHECK_ARG(tile == 8 || tile == 16 || tile == 32, "tile must be 8, 16 or 32");
-  JPM_CHECK_ARG(margin >= 0 && margin <= 8, "margin must be in [0, 8]");
+  JPM_CHECK_ARG(tile == 8 || tile == 16, "tile must be 8 or 16");
+  JPM_CHECK_ARG(margin >= 0 && margin <= 3, "margin must be in [0, 3]");
   JPM_CHECK_ARG(hx >= 0 && hy >= 0, "bad halo");
-  if (relative) JPM_CHECK_ARG(pnx + 2 * hx == nx && pny + 2 * hy == ny && pnz == nz,
-                              "relative mode: mesh must be the particle grid padded by the halo");
+  if (relative) {
+    JPM_CHECK_ARG(pnx + 2 * hx == nx && pny + 2 * hy == ny && pnz == nz,
+                  "relative mode: mesh must be the particle grid padded by the halo");
+    JPM_CHECK_ARG(pnx <= 1024 && pny <= 1024 && pnz <= 1024,
+                  "relative mode: local particle grid limited to 1024 per axis (packed ids)");
+  }
   if (plan) {
     int a, b, c;
     plan_dims(plan, &a, &b, &c);
@@ -362,12 +448,20 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   s->relative = relative;
   s->np = (long long)pnx * pny * pnz;
   s->g = make_geom(nx, ny, nz, pny, pnz, hx, hy, tile, margin);
-  const size_t read_smem = (size_t)3 * s->g.BX * s->g.BY * s->g.BZ * sizeof(float);
-  if (read_smem > 227 * 1024) {
-    delete s;
-    set_error("tile %d + margin %d needs %zu B of shared memory (> 227 KB)", tile, margin, read_smem);
-    return JPM_ERR_INVALID;
+  const int ts = s->g.tshift, m = margin;
+#define SET_ATTR(TS_, M_)                                                                          \
+  {                                                                                                \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<false, TS_, M_>,                                \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<true, TS_, M_>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false, TS_, M_>,                                 \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_>()));  \
   }
+  JPM_SIM_DISPATCH(ts, m, SET_ATTR);
+#undef SET_ATTR
   for (int i = 0; i < 2; ++i) {
     JPM_CUDA(cudaMalloc(&s->pos[i], s->np * sizeof(float4)));
     JPM_CUDA(cudaMalloc(&s->vel[i], 3 * s->np * sizeof(float)));
@@ -378,11 +472,6 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   JPM_CUDA(cudaMalloc(&s->stats, 2 * sizeof(unsigned long long)));
   JPM_CUDA(cudaMemset(s->stats, 0, 2 * sizeof(unsigned long long)));
   JPM_CUDA(cudaMemset(s->count, 0, s->g.nt * sizeof(int)));
-  const int paint_smem = s->g.BX * s->g.BY * s->g.BZ * sizeof(float);
-  JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem));
-  JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem));
-  JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)read_smem));
-  JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)read_smem));
   *out = s;
   return JPM_OK;
 }
@@ -406,16 +495,25 @@ extern "C" int32_t jpm_sim_load(jpm_sim* s, void* stream, const float* pos, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = div_up(s->np, 256);
   JPM_CUDA(cudaMemsetAsync(s->count, 0, s->g.nt * sizeof(int), st));
-  if (s->relative) sim_count_kernel<true><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
-  else sim_count_kernel<false><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
+  const bool t8 = s->g.tshift == 3;
+  if (s->relative) {
+    if (t8) sim_count_kernel<true, 3><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
+    else sim_count_kernel<true, 4><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
+  } else {
+    if (t8) sim_count_kernel<false, 3><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
+    else sim_count_kernel<false, 4><<<blocks, 256, 0, st>>>(s->g, pos, s->np, s->count);
+  }
   JPM_LAUNCH_CHECK();
   s->cur = 0;
   sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[0], s->cursor, s->g.nt);
   JPM_LAUNCH_CHECK();
-  if (s->relative)
-    sim_fill_kernel<true><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
-  else
-    sim_fill_kernel<false><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
+  if (s->relative) {
+    if (t8) sim_fill_kernel<true, 3><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
+    else sim_fill_kernel<true, 4><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
+  } else {
+    if (t8) sim_fill_kernel<false, 3><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
+    else sim_fill_kernel<false, 4><<<blocks, 256, 0, st>>>(s->g, pos, vel, s->np, s->cursor, s->pos[0], s->vel[0]);
+  }
   JPM_LAUNCH_CHECK();
   s->loaded = true;
   s->painted = false;
@@ -425,8 +523,11 @@ extern "C" int32_t jpm_sim_load(jpm_sim* s, void* stream, const float* pos, cons
 extern "C" int32_t jpm_sim_store(jpm_sim* s, void* stream, float* pos, float* vel) {
   JPM_CHECK_ARG(s && (pos || vel), "null pointer");
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
-  sim_store_kernel<<<div_up(s->np, 256), 256, 0, (cudaStream_t)stream>>>(s->pos[s->cur], s->vel[s->cur],
-                                                                        s->np, pos, vel);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (s->relative)
+    sim_store_kernel<true><<<div_up(s->np, 256), 256, 0, st>>>(s->g, s->pos[s->cur], s->vel[s->cur], s->np, pos, vel);
+  else
+    sim_store_kernel<false><<<div_up(s->np, 256), 256, 0, st>>>(s->g, s->pos[s->cur], s->vel[s->cur], s->np, pos, vel);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }
@@ -435,14 +536,19 @@ extern "C" int32_t jpm_sim_paint(jpm_sim* s, void* stream, float* mesh) {
   JPM_CHECK_ARG(s && mesh, "null pointer");
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
   cudaStream_t st = (cudaStream_t)stream;
-  const int smem = s->g.BX * s->g.BY * s->g.BZ * sizeof(float);
   JPM_CUDA(cudaMemsetAsync(s->count, 0, s->g.nt * sizeof(int), st));
-  if (s->relative)
-    sim_paint_kernel<true><<<s->g.nt, 256, smem, st>>>(s->g, s->pos[s->cur], s->start[s->cur], mesh,
-                                                       s->count, s->stats);
-  else
-    sim_paint_kernel<false><<<s->g.nt, 256, smem, st>>>(s->g, s->pos[s->cur], s->start[s->cur], mesh,
-                                                        s->count, s->stats);
+  const int ts = s->g.tshift, m = s->g.m;
+#define LAUNCH_PAINT(TS_, M_)                                                                        \
+  {                                                                                                  \
+    if (s->relative)                                                                                 \
+      sim_paint_kernel<true, TS_, M_><<<s->g.nt, 256, paint_smem<TS_, M_>(), st>>>(                  \
+          s->g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                         \
+    else                                                                                             \
+      sim_paint_kernel<false, TS_, M_><<<s->g.nt, 256, paint_smem<TS_, M_>(), st>>>(                 \
+          s->g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                         \
+  }
+  JPM_SIM_DISPATCH(ts, m, LAUNCH_PAINT);
+#undef LAUNCH_PAINT
   JPM_LAUNCH_CHECK();
   s->painted = true;
   return JPM_OK;
@@ -456,15 +562,20 @@ extern "C" int32_t jpm_sim_read_kick_drift(jpm_sim* s, void* stream, const float
   const int nxt = s->cur ^ 1;
   sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt);
   JPM_LAUNCH_CHECK();
-  const int smem = 3 * s->g.BX * s->g.BY * s->g.BZ * sizeof(float);
-  if (s->relative)
-    sim_read_kernel<true><<<s->g.nt, 512, smem, st>>>(s->g, s->pos[s->cur], s->vel[s->cur],
-                                                      s->start[s->cur], fx, fy, fz, kick_coef, drift_coef,
-                                                      s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);
-  else
-    sim_read_kernel<false><<<s->g.nt, 512, smem, st>>>(s->g, s->pos[s->cur], s->vel[s->cur],
-                                                       s->start[s->cur], fx, fy, fz, kick_coef, drift_coef,
-                                                       s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);
+  const int ts = s->g.tshift, m = s->g.m;
+#define LAUNCH_READ(TS_, M_)                                                                         \
+  {                                                                                                  \
+    if (s->relative)                                                                                 \
+      sim_read_kernel<true, TS_, M_><<<s->g.nt, 512, read_smem<TS_, M_>(), st>>>(                    \
+          s->g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef, drift_coef, \
+          s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                                     \
+    else                                                                                             \
+      sim_read_kernel<false, TS_, M_><<<s->g.nt, 512, read_smem<TS_, M_>(), st>>>(                   \
+          s->g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef, drift_coef, \
+          s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                                     \
+  }
+  JPM_SIM_DISPATCH(ts, m, LAUNCH_READ);
+#undef LAUNCH_READ
   JPM_LAUNCH_CHECK();
   s->cur = nxt;
   s->painted = false;

@@ -37,6 +37,27 @@ __global__ void __launch_bounds__(256) k_smem(float* out, int iters){
   else for(int i=threadIdx.x;i<TILE;i+=256) if(tile[i]!=0.f) atomicAdd(&out[i], tile[i]);
 }
 
+// 64-bit fixed-point accumulation in shared memory (ATOMS.ADD.64?)
+template<bool CLUSTERED>
+__global__ void __launch_bounds__(256) k_smem64(float* out, int iters){
+  __shared__ unsigned long long tile[TILE];
+  for(int i=threadIdx.x;i<TILE;i+=256) tile[i]=0ull;
+  __syncthreads();
+  unsigned s = hash(blockIdx.x*256+threadIdx.x+1);
+  for(int it=0; it<iters; ++it){
+    s = hash(s);
+    int cx = CLUSTERED ? (s&3) : (s&15), cy = CLUSTERED ? ((s>>4)&3) : ((s>>4)&15), cz=(s>>8)&15;
+    float w = (float)(s>>24)*(1.f/256.f);
+    #pragma unroll
+    for(int c=0;c<8;++c){
+      int a = ((cx+(c&1))*17 + (cy+((c>>1)&1)))*17 + cz+((c>>2)&1);
+      atomicAdd(&tile[a], (unsigned long long)__float2ll_rn(w*4294967296.f));
+    }
+  }
+  __syncthreads();
+  for(int i=threadIdx.x;i<TILE;i+=256) if(tile[i]!=0ull) atomicAdd(&out[i], (float)((double)(long long)tile[i]*2.3283064365386963e-10));
+}
+
 // global atomics: REDG f32 / int with return, scattered over `span` floats (L2-resident or DRAM-resident)
 template<int MODE>
 __global__ void __launch_bounds__(256) k_glob(float* mesh, size_t span, int iters, int* sink){
@@ -76,6 +97,8 @@ int main(){
   RUN(2,false,"smem atomicAdd int (native), random");
   RUN(2,true, "smem atomicAdd int (native), clustered");
   RUN(3,false,"smem LDS gather x8, random");
+  { float ms=timeit([&]{k_smem64<false><<<blocks,256>>>(out,iters);}); printf("%-44s %8.3f ms  %7.2f G upd/s  %6.2f cyc/particle/SM\n","smem atomicAdd u64 fixed-point, random",ms,nupd/ms*1e-6, ms*1e-3*1.9e9*148/(nupd/8)); }
+  { float ms=timeit([&]{k_smem64<true><<<blocks,256>>>(out,iters);}); printf("%-44s %8.3f ms  %7.2f G upd/s  %6.2f cyc/particle/SM\n","smem atomicAdd u64 fixed-point, clustered",ms,nupd/ms*1e-6, ms*1e-3*1.9e9*148/(nupd/8)); }
   size_t big=(size_t)512*512*512, small=(size_t)256*256*64;
   float* mesh; CK(cudaMalloc(&mesh,big*4)); CK(cudaMemset(mesh,0,big*4));
   const int gb=148*16, gi=200; double ng=(double)gb*256*gi;
