@@ -238,34 +238,56 @@ __global__ void __launch_bounds__(256, 4)
 sim_paint_kernel(SimGeom g, const float4* __restrict__ spos, const int* __restrict__ start,
                  float* __restrict__ mesh, int* __restrict__ count, unsigned long long* __restrict__ stats) {
   constexpr int T = 1 << TS, B = T + 2 * M + 1, BZ = (B + 1) & ~1, NBOX = B * B * BZ;
-  extern __shared__ float box[];
+  extern __shared__ __align__(16) float box[];
   __shared__ int scnt[27];
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
   const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
   const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
-  for (int i = threadIdx.x; i < NBOX; i += blockDim.x) box[i] = 0.f;
+  // first particle of this thread is in flight while the box is being zeroed
+  int q = beg + threadIdx.x;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < end) p = __ldcs(spos + q);
+  for (int i = threadIdx.x; i < NBOX / 2; i += blockDim.x) reinterpret_cast<float2*>(box)[i] = make_float2(0.f, 0.f);
   if (threadIdx.x < 27) scnt[threadIdx.x] = 0;
   __syncthreads();
-  const int rot = threadIdx.x & 7;
-  for (int q = beg + threadIdx.x; q < end; q += blockDim.x) {
-    const float4 p = __ldcs(spos + q);
+  // Lanes walk the 8 corners in lane-dependent (XOR-permuted) order: particles sharing a cell then
+  // update 8 different addresses at any instant, so the shared-memory CAS loops rarely retry.
+  const bool sx = threadIdx.x & 1, sy = threadIdx.x & 2, sz = threadIdx.x & 4;
+  while (q < end) {
+    const int qn = q + blockDim.x;
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qn < end) pn = __ldcs(spos + qn);  // prefetch
     Cic1 cx, cy, cz;
     sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
     Corners c;
     make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
     if (c.inside) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int cc = (j + rot) & 7;   // run-time corner: select with predicates, not array indexing
-        const bool a = cc & 1, b = cc & 2, d = cc & 4;
-        if (REL && ((a ? c.ix[1] : c.ix[0]) < 0 || (b ? c.iy[1] : c.iy[0]) < 0 || (d ? c.iz[1] : c.iz[0]) < 0))
-          continue;
-        // reference order (kx*ky)*kz, weight 1
-        const float k = ((a ? c.wx[1] : c.wx[0]) * (b ? c.wy[1] : c.wy[0])) * (d ? c.wz[1] : c.wz[0]);
-        atomicAdd(box + ((a ? c.lx[1] : c.lx[0]) * B + (b ? c.ly[1] : c.ly[0])) * BZ + (d ? c.lz[1] : c.lz[0]), k);
+      // per-axis swap (once per particle) instead of per-corner selects
+      const int lxa = sx ? c.lx[1] : c.lx[0], lxb = sx ? c.lx[0] : c.lx[1];
+      const int lya = sy ? c.ly[1] : c.ly[0], lyb = sy ? c.ly[0] : c.ly[1];
+      const int lza = sz ? c.lz[1] : c.lz[0], lzb = sz ? c.lz[0] : c.lz[1];
+      float wxa = sx ? c.wx[1] : c.wx[0], wxb = sx ? c.wx[0] : c.wx[1];
+      float wya = sy ? c.wy[1] : c.wy[0], wyb = sy ? c.wy[0] : c.wy[1];
+      float wza = sz ? c.wz[1] : c.wz[0], wzb = sz ? c.wz[0] : c.wz[1];
+      if (REL) {  // a dropped corner (index -1, relative rule only) contributes nothing
+        if ((sx ? c.ix[1] : c.ix[0]) < 0) wxa = 0.f;
+        if ((sx ? c.ix[0] : c.ix[1]) < 0) wxb = 0.f;
+        if ((sy ? c.iy[1] : c.iy[0]) < 0) wya = 0.f;
+        if ((sy ? c.iy[0] : c.iy[1]) < 0) wyb = 0.f;
+        if ((sz ? c.iz[1] : c.iz[0]) < 0) wza = 0.f;
+        if ((sz ? c.iz[0] : c.iz[1]) < 0) wzb = 0.f;
       }
+      const int lxs[2] = {lxa * (B * BZ), lxb * (B * BZ)}, lys[2] = {lya * BZ, lyb * BZ}, lzs[2] = {lza, lzb};
+      const float wxs[2] = {wxa, wxb}, wys[2] = {wya, wyb}, wzs[2] = {wza, wzb};
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int d = 0; d < 2; ++d)  // reference order (kx*ky)*kz, weight 1
+            atomicAdd(box + lxs[a] + lys[b] + lzs[d], (wxs[a] * wys[b]) * wzs[d]);
     } else {
 #pragma unroll
       for (int cc = 0; cc < 8; ++cc) {
@@ -286,6 +308,8 @@ sim_paint_kernel(SimGeom g, const float4* __restrict__ spos, const int* __restri
       atomicAdd(scnt + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1), 1);
     else
       atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, 1);
+    p = pn;
+    q = qn;
   }
   __syncthreads();
   if (threadIdx.x < 27 && scnt[threadIdx.x]) {
@@ -293,23 +317,33 @@ sim_paint_kernel(SimGeom g, const float4* __restrict__ spos, const int* __restri
     const int i0 = pymod(tx + dx, g.ntx), j0 = pymod(ty + dy, g.nty), k0 = pymod(tz + dz, g.ntz);
     atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, scnt[threadIdx.x]);
   }
-  // flush: pairs along z (8-byte vector reductions when the pair cannot straddle the wrap)
+  // flush: two box rows per warp pass, one z-pair per lane (8-byte vector reductions when the pair
+  // cannot straddle the periodic wrap); the z index of a lane is loop invariant.
+  constexpr int HP = BZ / 2;                 // pairs per row (<= 16)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int sub = lane / HP, zp = lane - sub * HP;     // sub-row 0/1 (lanes >= 2*HP idle)
   const bool vec = ((oz & 1) == 0) && ((g.nz & 1) == 0) && g.nz >= BZ;
-  for (int e = threadIdx.x; e < NBOX / 2; e += blockDim.x) {
-    const float2 v = reinterpret_cast<const float2*>(box)[e];
-    if (v.x == 0.f && v.y == 0.f) continue;
-    const int zp = e % (BZ / 2), r = e / (BZ / 2);
-    const int ly = r % B, lx = r / B;
-    const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
-    float* row = mesh + ((long long)gx * g.ny + gy) * g.nz;
-    const int z0 = oz + 2 * zp;
-    if (vec) {
-      red_add_v2(row + wrap_global(z0, g.nz), v.x, v.y);
-    } else {
-      if (v.x != 0.f) atomicAdd(row + wrap_global(z0, g.nz), v.x);
-      if (v.y != 0.f) atomicAdd(row + wrap_global(z0 + 1, g.nz), v.y);
+  const int gz0 = wrap_global(oz + 2 * zp, g.nz), gz1 = wrap_global(oz + 2 * zp + 1, g.nz);
+  if (sub < 2) {
+    for (int r = 2 * warp + sub; r < B * B; r += 2 * nwarp) {
+      const float2 v = reinterpret_cast<const float2*>(box)[r * HP + zp];
+      if (v.x == 0.f && v.y == 0.f) continue;
+      const int lx = r / B, ly = r - lx * B;
+      const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
+      float* row = mesh + ((long long)gx * g.ny + gy) * g.nz;
+      if (vec) {
+        red_add_v2(row + gz0, v.x, v.y);
+      } else {
+        if (v.x != 0.f) atomicAdd(row + gz0, v.x);
+        if (v.y != 0.f && 2 * zp + 1 < B) atomicAdd(row + gz1, v.y);
+      }
     }
   }
+}
+
+__device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(sa), "l"(gmem) : "memory");
 }
 
 // ---- read3 + kick + drift + scatter into the next ordering --------------------------------------
@@ -321,54 +355,88 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
                 long long np, int* __restrict__ cursor, float4* __restrict__ npos,
                 float* __restrict__ nvel, unsigned long long* __restrict__ stats) {
   constexpr int T = 1 << TS, B = T + 2 * M + 1, NBOX = B * B * B;
-  extern __shared__ float box[];
+  extern __shared__ __align__(16) float box[];
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
   const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
   const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
   const float* fm[3] = {f0, f1, f2};
-  for (int e = threadIdx.x; e < NBOX; e += blockDim.x) {
-    const int lz = e % B, r = e / B;
-    const int ly = r % B, lx = r / B;
-    const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny), gz = wrap_global(oz + lz, g.nz);
-    const long long o = ((long long)gx * g.ny + gy) * g.nz + gz;
+  // stage the three force boxes with cp.async (LDGSTS): one box row (B contiguous floats) per
+  // warp pass, no registers held, all rows of a warp in flight at once
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (lane < B) {
+      const int gz = wrap_global(oz + lane, g.nz);
+      for (int r = warp; r < B * B; r += nwarp) {
+        const int lx = r / B, ly = r - lx * B;
+        const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
+        const long long o = ((long long)gx * g.ny + gy) * g.nz + gz;
 #pragma unroll
-    for (int f = 0; f < 3; ++f) box[f * NBOX + e] = __ldg(fm[f] + o);
+        for (int f = 0; f < 3; ++f) cp_async4(box + f * NBOX + r * B + lane, fm[f] + o);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
   }
+  // first particle of this thread streams in while the boxes land
+  int q = beg + threadIdx.x;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float vin[3] = {0.f, 0.f, 0.f};
+  if (q < end) {
+    p = __ldcs(spos + q);
+#pragma unroll
+    for (int f = 0; f < 3; ++f) vin[f] = __ldcs(svel + f * np + q);
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   __syncthreads();
   for (int qb = beg; qb < end; qb += blockDim.x) {
-    const int q = qb + threadIdx.x;
     const bool valid = q < end;
+    const int qn = q + blockDim.x;
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vn[3] = {0.f, 0.f, 0.f};
+    if (qn < end) {  // prefetch the next particle of this thread
+      pn = __ldcs(spos + qn);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
+    }
     int tt = 0;
-    float4 p = make_float4(0, 0, 0, 0);
     float v[3] = {0, 0, 0};
     if (valid) {
-      p = __ldcs(spos + q);
       Cic1 cx, cy, cz;
       sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
       tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
       Corners c;
       make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
       float acc[3] = {0.f, 0.f, 0.f};
+      if (c.inside) {
+        float mv[3][8], kk[8];
 #pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
-        if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
-        const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
-        if (c.inside) {
+        for (int cc = 0; cc < 8; ++cc) {   // all 24 shared-memory gathers issued back to back
+          const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
           const int o = (c.lx[a] * B + c.ly[b]) * B + c.lz[d];
 #pragma unroll
-          for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
-        } else {
+          for (int f = 0; f < 3; ++f) mv[f][cc] = box[f * NBOX + o];
+          kk[cc] = (c.wx[a] * c.wy[b]) * c.wz[d];
+          if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) kk[cc] = 0.f;
+        }
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc)
+#pragma unroll
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(mv[f][cc], kk[cc], acc[f]);
+      } else {
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+          if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
+          const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
           const long long o = ((long long)c.ix[a] * g.ny + c.iy[b]) * g.nz + c.iz[d];
 #pragma unroll
           for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
         }
+        atomicAdd(stats + 1, 1ull);
       }
-      if (!c.inside) atomicAdd(stats + 1, 1ull);
 #pragma unroll
-      for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], __ldcs(svel + f * np + q));
+      for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], vin[f]);
       p.x = fmaf(drift, v[0], p.x);
       p.y = fmaf(drift, v[1], p.y);
       p.z = fmaf(drift, v[2], p.z);
@@ -379,6 +447,10 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
 #pragma unroll
       for (int f = 0; f < 3; ++f) nvel[f * np + slot] = v[f];
     }
+    p = pn;
+    q = qn;
+#pragma unroll
+    for (int f = 0; f < 3; ++f) vin[f] = vn[f];
   }
 }
 
