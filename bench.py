@@ -313,6 +313,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--tile", type=int, default=16)
     ap.add_argument("--margin", type=int, default=2)
+    ap.add_argument("--halo", type=int, default=64, help="halo width of the sharded path (N > 1)")
+    ap.add_argument("--no-resident", action="store_true", help="N > 1: order-preserving kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":

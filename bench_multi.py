@@ -1,0 +1,109 @@
+"""N > 1 leg of bench.py: the sharded force loop (slab decomposition over N GPUs of one box).
+
+Strong scaling: the SIZE^3 workload is fixed and split over the ranks; `value` = all particles
+advanced per second, timed on the device (CUDA events), max over ranks."""
+import json
+import os
+import time
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def run_multi(args, world, rank, dev):
+    from bench import METRIC, UNIT, ClockSampler, _peaks
+    from jaxpm_b200 import _lib, halo, ops
+    from jaxpm_b200.cosmology import Planck15, linear_matter_power
+    from jaxpm_b200.distributed import Sharding
+    from jaxpm_b200.ode import kick_drift_coefficients
+    from jaxpm_b200.pm import linear_field, lpt
+
+    N = args.size
+    pdims = (world, 1)
+    sh = Sharding(pdims)
+    h = args.halo
+    shape = (N, N, N)
+    cosmo = Planck15()
+    K, W = args.steps, args.warmup
+    lx, ly = N // pdims[0], N // pdims[1]
+
+    # identical ICs on every rank (generated redundantly, untimed), then keep the local block
+    ic = linear_field(shape, (float(N),) * 3, lambda k: linear_matter_power(cosmo, k), seed=0, device=dev)
+    dx, p, _ = lpt(cosmo, ic, a=0.1, order=1)
+    blk = lambda a: a[sh.rx * lx:(sh.rx + 1) * lx, sh.ry * ly:(sh.ry + 1) * ly].contiguous()
+    disp, vel = blk(dx), blk(p)
+    del ic, dx, p
+    ops.clear_plans()
+    torch.cuda.empty_cache()
+    d, k = kick_drift_coefficients(cosmo, 0.1, 1.0, K + W, "symplectic")
+    ops.axpby(1.0, disp, d[0], vel, out=disp)
+    stepper = halo.ShardedStepper(disp, vel, h, sh, resident=not args.no_resident, tile=args.tile,
+                                  margin=args.margin)
+
+    def step(n):
+        stepper.step(k[n], d[n + 1] if n + 1 < K + W else 0.0)
+
+    for n in range(W):
+        step(n)
+    dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for n in range(W, W + K):
+        step(n)
+    e1.record()
+    torch.cuda.synchronize()
+    dist.barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.stop()
+    t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_dev = float(t)
+    npart = N**3
+    value = npart * K / t_dev
+
+    # end to end: host-resident local state in, one step, host-resident state out (every rank)
+    e2e_steps = max(1, min(K, args.e2e_steps))
+    stepper.store(disp, vel)
+    ph, vh = disp.cpu().pin_memory(), vel.cpu().pin_memory()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for n in range(e2e_steps):
+        disp.copy_(ph, non_blocking=True)
+        vel.copy_(vh, non_blocking=True)
+        stepper.load(disp, vel)
+        stepper.step(1e-6, 1e-6)
+        stepper.store(disp, vel)
+        ph.copy_(disp, non_blocking=True)
+        vh.copy_(vel, non_blocking=True)
+        torch.cuda.synchronize()
+    dist.barrier()
+    te = torch.tensor([time.perf_counter() - t0], device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    bytes_state = 2 * npart * 12
+    e2e = {"value": npart * e2e_steps / float(te), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
+           "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
+           "entry": "per-rank pinned host state -> sharded PM step -> host state (all ranks concurrently)"}
+    peak, peak_kind = _peaks()
+    step_alg_bytes = (60 + 64) * npart
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then PM drift-kick steps to a=1 "
+                                   f"(relative mode), Planck15, L={N} Mpc/h",
+                       "l2": "inputs larger than L2", "parallelism": f"slab pdims={pdims}, halo={h}",
+                       "resident": not args.no_resident},
+            "roofline": {"bound": "hbm", "kernel": "whole step (per-GPU share of 124 B/particle-step)",
+                         "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,
+                         "unit": "GB/s", "frac": step_alg_bytes * K / t_dev / 1e9 / world / peak, "traffic": None},
+            "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+            "timing": stepper.timing_summary(),
+        }))
+    dist.destroy_process_group()

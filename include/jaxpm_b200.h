@@ -249,6 +249,31 @@ int32_t jpm_grid_plus_disp_f32(void* stream, float* out, const float* disp, int3
 /* ------------------------------------------------------------------------
  * multi-GPU building blocks (jaxpm/distributed.py:45-113; one process per GPU)
  * ---------------------------------------------------------------------- */
+/* 1-D batched FFT plans for the slab/pencil transform ([ext] jaxdecomp.pfft3d, called from
+ * jaxpm/distributed.py:37-42): `batch` contiguous transforms of length n.
+ * kind 0 = R2C (n reals -> n/2+1 complex), 1 = C2R, 2 = C2C (direction chosen at exec). Host calls. */
+typedef struct jpm_fft1d jpm_fft1d;
+int32_t jpm_fft1d_create(jpm_fft1d** plan, int32_t n, int64_t batch, int32_t kind);
+int32_t jpm_fft1d_destroy(jpm_fft1d* plan);
+int32_t jpm_fft1d_exec(jpm_fft1d* plan, void* stream, void* in, void* out, int32_t inverse);
+/* Batched tiled transpose of complex64: dst[b*dsb + j*dsj + i] = src[b*ssb + i*ssi + j]
+ * (pack/unpack around the all-to-all transposes). Strides in complex elements. */
+int32_t jpm_transpose_c64(void* stream, void* dst, const void* src, int32_t ni, int32_t nj,
+                          int64_t nb, int64_t src_stride_i, int64_t src_stride_b,
+                          int64_t dst_stride_j, int64_t dst_stride_b);
+/* Strided row copy of complex64: dst[r*drs + c] = src[r*srs + c], c < ncols. */
+int32_t jpm_copy2d_c64(void* stream, void* dst, const void* src, int64_t nrows, int32_t ncols,
+                       int64_t src_row_stride, int64_t dst_row_stride);
+/* The fused k-space passes (jpm_greens_grad_c64 = kind 0, jpm_lpt2_shear_c64 = kind 1,
+ * jpm_greens_div_c64 = kind 2) on a LOCAL block [n0][n1][n2] of a distributed spectrum whose array
+ * axes are a permutation of (x,y,z): w0..2 and a0..2 are the per-array-axis slices of the tables of
+ * jaxpm/kernels.py:10-23 and :62-66; axis_of_{x,y,z} map physical directions to array axes. */
+int32_t jpm_kspace_local_c64(void* stream, int32_t kind, const void* in, void* out, const float* w0,
+                             const float* w1, const float* w2, const float* a0, const float* a1,
+                             const float* a2, int32_t n0, int32_t n1, int32_t n2, int32_t axis_of_x,
+                             int32_t axis_of_y, int32_t axis_of_z, float norm, float r_split,
+                             const float* filter_tab, int32_t n_tab, float filter_kmax);
+
 /* Copy / add a [x0:x1) x [y0:y1) x nz sub-box between a strided mesh and a packed buffer. */
 int32_t jpm_pack_box_f32(void* stream, float* packed, const float* mesh, int32_t ny, int32_t nz,
                          int32_t x0, int32_t x1, int32_t y0, int32_t y1);

@@ -52,6 +52,13 @@ SIGNATURES = {
     "jpm_kernel_launch_count": ([], i64),
     "jpm_axpby_f32": ([vp, vp, f32, vp, f32, vp, i64], i32),
     "jpm_grid_plus_disp_f32": ([vp, vp, vp, i32, i32, i32, i32, i32], i32),
+    "jpm_fft1d_create": ([C.POINTER(vp), i32, i64, i32], i32),
+    "jpm_fft1d_destroy": ([vp], i32),
+    "jpm_fft1d_exec": ([vp, vp, vp, vp, i32], i32),
+    "jpm_transpose_c64": ([vp, vp, vp, i32, i32, i64, i64, i64, i64, i64], i32),
+    "jpm_copy2d_c64": ([vp, vp, vp, i64, i32, i64, i64], i32),
+    "jpm_kspace_local_c64": ([vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, f32,
+                              vp, i32, f32], i32),
     "jpm_pack_box_f32": ([vp, vp, vp, i32, i32, i32, i32, i32, i32], i32),
     "jpm_unpack_box_f32": ([vp, vp, vp, i32, i32, i32, i32, i32, i32, i32], i32),
 }

@@ -29,11 +29,36 @@ class Sharding:
         import torch.distributed as dist
         self.pdims = (int(pdims[0]), int(pdims[1]))
         self.group = group
-        if rank is None:
-            rank = dist.get_rank(group) if dist.is_available() and dist.is_initialized() else 0
-        self.rank = rank
         self.size = self.pdims[0] * self.pdims[1]
+        live = dist.is_available() and dist.is_initialized()
+        if rank is None:
+            rank = dist.get_rank(group) if live else 0
+        self.rank = rank
         self.rx, self.ry = divmod(rank, self.pdims[1])
+        self.ygroup = self.xgroup = None
+        if live and self.size > 1:
+            if dist.get_world_size(group) != self.size:
+                raise ValueError(f"pdims {self.pdims} needs {self.size} ranks, group has {dist.get_world_size(group)}")
+            px, py = self.pdims
+            # every rank must create every sub-group, in the same order
+            for rx in range(px):
+                g = dist.new_group([self.global_rank(rx * py + j) for j in range(py)]) if py > 1 else None
+                if rx == self.rx:
+                    self.ygroup = g
+            for ry in range(py):
+                g = dist.new_group([self.global_rank(i * py + ry) for i in range(px)]) if px > 1 else None
+                if ry == self.ry:
+                    self.xgroup = g
+
+    def global_rank(self, r):
+        """Rank `r` of this sharding's group as a global (world) rank."""
+        import torch.distributed as dist
+        if self.group is None:
+            return r
+        return dist.get_global_rank(self.group, r)
+
+    def global_shape(self, local_shape):
+        return (local_shape[0] * self.pdims[0], local_shape[1] * self.pdims[1], *local_shape[2:])
 
     def neighbor(self, dx, dy):
         px, py = self.pdims

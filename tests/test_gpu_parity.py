@@ -298,3 +298,83 @@ def test_sim_step_matches_order_preserving_path(cuda, relative):
                                 paint_absolute_pos=not relative, **kw)
         assert np.abs(p.cpu().numpy() - rp).max() < 2e-4, kw
         assert rel_err(v.cpu().numpy(), rv) < 1e-4, kw
+
+
+# ---- K6 adjoints: what jax.grad of the reference produces ----------------------
+@pytest.mark.parametrize("relative", [False, True])
+def test_paint_read_vjp(cuda, relative):
+    from jaxpm_b200.painting import cic_paint, cic_paint_dx, cic_read, cic_read_dx
+    shape = (12, 16, 10)
+    grid, disp = displaced(shape, 1.3, dtype=np.float64)
+    rng = np.random.default_rng(11)
+    mesh = rng.standard_normal(shape)
+    cot_p = rng.standard_normal(shape)     # cotangent of a read (one value per particle)
+    cot_m = rng.standard_normal(shape)     # cotangent of a painted mesh
+    w = rng.uniform(0.5, 1.5, shape)
+    pos = grid + disp
+    # oracle adjoints (absolute rule; the relative rule is the same function of grid+disp)
+    gmesh_ref, gpos_ref = OP.cic_read_vjp(mesh, pos, cot_p.reshape(-1))
+    gppos_ref, gw_ref = OP.cic_paint_vjp(shape, pos, w.reshape(-1), cot_m)
+    x = torch.tensor((disp if relative else pos).astype(np.float32), device=cuda, requires_grad=True)
+    m = torch.tensor(mesh.astype(np.float32), device=cuda, requires_grad=True)
+    wt = torch.tensor(w.astype(np.float32), device=cuda, requires_grad=True)
+    out = cic_read_dx(m, x) if relative else cic_read(m, x)
+    out.backward(T(cot_p.astype(np.float32), cuda))
+    assert rel_err(m.grad.cpu().numpy(), gmesh_ref) < 1e-5
+    assert rel_err(x.grad.cpu().numpy(), gpos_ref) < 1e-5
+    x.grad = None
+    painted = cic_paint_dx(x, weight=wt) if relative else cic_paint(torch.zeros(shape, device=cuda), x, wt)
+    painted.backward(T(cot_m.astype(np.float32), cuda))
+    assert rel_err(x.grad.cpu().numpy(), gppos_ref) < 1e-5
+    assert rel_err(wt.grad.cpu().numpy().reshape(-1), gw_ref) < 1e-5
+
+
+def test_on_grid_gradient_sign_convention(cuda):
+    """JAX's abs'(0) = 0: at zero displacement (lpt's particles, pm.py:73-75) the position
+    gradient of a read is -m[c] + ... with sign(0)=0 terms vanishing, not a one-sided slope."""
+    from jaxpm_b200.painting import cic_read_dx
+    shape = (8, 8, 8)
+    mesh = np.random.default_rng(0).standard_normal(shape).astype(np.float32)
+    d = torch.zeros((*shape, 3), device=cuda, requires_grad=True)
+    cic_read_dx(T(mesh, cuda), d).sum().backward()
+    _, gpos = OP.cic_read_vjp(mesh.astype(np.float64), lagrangian_grid(shape, np.float64), np.ones(mesh.size))
+    assert rel_err(d.grad.cpu().numpy(), gpos) < 1e-5
+
+
+@pytest.mark.parametrize("relative", [False, True])
+def test_pm_forces_vjp_dot_product_and_fd(cuda, relative):
+    """<J v, u> = <v, J^T u> with J v from central finite differences of the float64 oracle."""
+    from jaxpm_b200.pm import pm_forces
+    shape = (8, 8, 8)
+    grid, disp = displaced(shape, 0.6, dtype=np.float64)
+    x0 = disp if relative else grid + disp
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal(x0.shape)
+    v = rng.standard_normal(x0.shape)
+    x = torch.tensor(x0.astype(np.float32), device=cuda, requires_grad=True)
+    F = pm_forces(x, mesh_shape=shape, paint_absolute_pos=not relative)
+    F.backward(T(u.astype(np.float32), cuda))
+    lhs_gpu = float((x.grad.cpu().numpy().astype(np.float64) * v).sum())
+    eps = 1e-5
+    fwd = lambda xx: OPM.pm_forces(xx, mesh_shape=shape, paint_absolute_pos=not relative)
+    jv = (fwd(x0 + eps * v) - fwd(x0 - eps * v)) / (2 * eps)
+    rhs = float((jv * u).sum())
+    assert abs(lhs_gpu - rhs) < 2e-3 * max(abs(rhs), 1e-3), (lhs_gpu, rhs)
+
+
+def test_lpt_gradient_wrt_initial_conditions(cuda):
+    """Mirrors tests/test_gradients.py: d/dIC of a scalar of the 1LPT displacement."""
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.pm import lpt
+    shape = (8, 8, 8)
+    rng = np.random.default_rng(5)
+    ic0 = 0.1 * rng.standard_normal(shape)
+    u = rng.standard_normal((*shape, 3))
+    ic = torch.tensor(ic0.astype(np.float32), device=cuda, requires_grad=True)
+    dx, p, f = lpt(Planck15(), ic, a=0.1, order=1)
+    (dx * T(u.astype(np.float32), cuda)).sum().backward()
+    ocos = OC.Planck15()
+    # lpt is linear in the initial conditions: directional derivative = lpt(v)
+    v = rng.standard_normal(shape)
+    jv = OPM.lpt(ocos, v, a=0.1, order=1)[0]
+    assert abs(float((ic.grad.cpu().numpy() * v).sum()) - float((jv * u).sum())) < 1e-4 * abs(float((jv * u).sum()))
