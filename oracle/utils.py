@@ -8,7 +8,7 @@ import scipy.fft as sfft
 from scipy.special import legendre
 
 
-def _initialize_pk(mesh_shape, box_shape, kedges, los):
+def _initialize_pk(mesh_shape, box_shape, kedges, los, x64=False):
     mesh_shape = np.asarray(mesh_shape)
     box_shape = np.asarray(box_shape, dtype=np.float64)
     kmax = np.pi * np.min(mesh_shape / box_shape)
@@ -24,6 +24,8 @@ def _initialize_pk(mesh_shape, box_shape, kedges, los):
     kvec = [(2 * np.pi * m / l) * np.fft.fftfreq(m).reshape(ks)
             for m, l, ks in zip(mesh_shape, box_shape, kshapes)]
     kmesh = np.sqrt(sum(ki**2 for ki in kvec))
+    if not x64:   # utils.py:54 is a jnp.sqrt: float32 unless jax_enable_x64 (decides edge-on-bin modes)
+        kmesh = kmesh.astype(np.float32)
     dig = np.digitize(kmesh.reshape(-1), kedges)
     kcount = np.bincount(dig, minlength=len(kedges) + 1)
     kavg = np.bincount(dig, weights=kmesh.reshape(-1), minlength=len(kedges) + 1) / kcount
@@ -37,7 +39,7 @@ def _initialize_pk(mesh_shape, box_shape, kedges, los):
     return dig, kcount, kavg, mumesh
 
 
-def power_spectrum(mesh, mesh2=None, box_shape=None, kedges=None, multipoles=0, los=(0., 0., 1.)):
+def power_spectrum(mesh, mesh2=None, box_shape=None, kedges=None, multipoles=0, los=(0., 0., 1.), x64=False):
     mesh = np.asarray(mesh, dtype=np.float64)
     mesh_shape = np.array(mesh.shape)
     box_shape = mesh_shape if box_shape is None else np.asarray(box_shape)
@@ -47,7 +49,7 @@ def power_spectrum(mesh, mesh2=None, box_shape=None, kedges=None, multipoles=0, 
         los = np.asarray(los, dtype=np.float64)
         los = los / np.linalg.norm(los)
     poles = np.atleast_1d(multipoles)
-    dig, kcount, kavg, mumesh = _initialize_pk(mesh_shape, box_shape, kedges, los)
+    dig, kcount, kavg, mumesh = _initialize_pk(mesh_shape, box_shape, kedges, los, x64)
     n_bins = len(kavg) + 2
     meshk = sfft.fftn(mesh, norm='ortho', workers=-1)
     if mesh2 is None:

@@ -1,0 +1,140 @@
+"""GPU parity against the committed golden fixtures (tests/golden/*.npz): the CUDA path, through the
+C ABI, compared DIRECTLY with what the reference's own source computed (no oracle in between).
+Bars (BASELINE.json north_star): cell indices bit-exact, fields 1e-5 relative (fp32)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+FIELD_TOL = 1e-5
+
+
+def gold(name):
+    return np.load(os.path.join(GOLD, name + ".npz"))
+
+
+def T(x, dev):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def test_golden_cell_indices_bit_exact(cuda):
+    from jaxpm_b200 import ops
+    g = gold("paint_read_abs")
+    shape = g["base"].shape
+    c0 = g["idx"][:, 0]                                           # corner (0,0,0) of every particle
+    flat = (c0[:, 0] * shape[1] + c0[:, 1]) * shape[2] + c0[:, 2]
+    np.testing.assert_array_equal(N(ops.cell_index(T(g["pos"], cuda), shape)), flat)
+    r = gold("paint_read_rel")
+    for tag, halo in (("h00", (0, 0)), ("h23", (2, 3))):
+        shp = r["disp"].shape[:3]
+        pshape = (shp[0] + 2 * halo[0], shp[1] + 2 * halo[1], shp[2])
+        c0 = r[f"idx_{tag}"][:, 0]
+        ok = np.all((c0 >= 0) & (c0 < np.asarray(pshape)), axis=-1)
+        flat = np.where(ok, (c0[:, 0] * pshape[1] + c0[:, 1]) * pshape[2] + c0[:, 2], -1)
+        got = N(ops.cell_index(T(r["disp"], cuda), pshape, relative=True, halo=halo))
+        np.testing.assert_array_equal(got, flat)
+
+
+def test_golden_paint_read_absolute(cuda):
+    from jaxpm_b200.painting import cic_paint, cic_read
+    g = gold("paint_read_abs")
+    shape = g["base"].shape
+    pos = T(g["pos"], cuda)
+    assert rel_err(N(cic_paint(torch.zeros(shape, device=cuda), pos)), g["mesh_w1"]) < FIELD_TOL
+    assert rel_err(N(cic_paint(T(g["base"], cuda), pos, T(g["weight"], cuda))), g["mesh_warr_on_base"]) < FIELD_TOL
+    assert rel_err(N(cic_paint(T(g["base"], cuda), pos, 2.5)), g["mesh_w2p5_on_base"]) < FIELD_TOL
+    assert rel_err(N(cic_read(T(g["base"], cuda), pos)), g["read_base"]) < FIELD_TOL
+
+
+@pytest.mark.parametrize("tag,halo", [("h00", (0, 0)), ("h23", (2, 3))])
+def test_golden_paint_read_relative(cuda, tag, halo):
+    from jaxpm_b200 import ops
+    from jaxpm_b200.painting import cic_paint_dx, cic_read_dx
+    g = gold("paint_read_rel")
+    disp = T(g["disp"], cuda)
+    pshape = g[f"mesh_{tag}"].shape
+    m = ops.cic_paint_dx_(torch.zeros(pshape, device=cuda), disp, 1.0, halo)
+    assert rel_err(N(m), g[f"mesh_{tag}"]) < FIELD_TOL
+    m = ops.cic_paint_dx_(torch.zeros(pshape, device=cuda), disp, T(g["weight"], cuda), halo)
+    assert rel_err(N(m), g[f"mesh_warr_{tag}"]) < FIELD_TOL
+    assert rel_err(N(ops.cic_read_dx(T(g[f"field_{tag}"], cuda), disp, halo)), g[f"read_{tag}"]) < FIELD_TOL
+    if tag == "h00":
+        assert rel_err(N(cic_paint_dx(disp)), g["paint_dx_api"]) < FIELD_TOL
+        assert rel_err(N(cic_read_dx(T(g["field_h00"], cuda), disp)), g["read_dx_api"]) < FIELD_TOL
+
+
+def test_golden_resident_state_paint_read(cuda):
+    """The tile-sorted resident path (csrc/sim.cu) against the same fixtures."""
+    from jaxpm_b200 import ops
+    g = gold("paint_read_rel")
+    disp = T(g["disp"], cuda)
+    shp = tuple(disp.shape[:3])
+    sim = ops.Sim(shp, shp, True, cuda, tile=8, margin=2, with_plan=False)
+    sim.load(disp, torch.zeros_like(disp))
+    m = sim.paint_(torch.zeros(shp, device=cuda))
+    assert rel_err(N(m), g["mesh_h00"]) < FIELD_TOL
+    a = gold("paint_read_abs")
+    pos = T(a["pos"], cuda)
+    sim = ops.Sim(shp, shp, False, cuda, tile=8, margin=2, with_plan=False)
+    sim.load(pos, torch.zeros_like(pos))
+    m = sim.paint_(torch.zeros(shp, device=cuda))
+    assert rel_err(N(m), a["mesh_w1"]) < FIELD_TOL
+
+
+def test_golden_pm_forces(cuda):
+    from jaxpm_b200.distributed import fft3d
+    from jaxpm_b200.pm import pm_forces
+    g = gold("pm_forces")
+    shape = g["delta"].shape
+    pos, disp, delta = T(g["pos"], cuda), T(g["disp"], cuda), T(g["delta"], cuda)
+    assert rel_err(N(pm_forces(pos, mesh_shape=shape)), g["f_abs"]) < FIELD_TOL
+    assert rel_err(N(pm_forces(disp, mesh_shape=shape, paint_absolute_pos=False)), g["f_rel"]) < FIELD_TOL
+    assert rel_err(N(pm_forces(pos, mesh_shape=shape, r_split=2.0)), g["f_abs_rsplit2"]) < FIELD_TOL
+    assert rel_err(N(pm_forces(pos, delta=delta)), g["f_abs_delta_real"]) < FIELD_TOL
+    assert rel_err(N(pm_forces(disp, delta=fft3d(delta), paint_absolute_pos=False)), g["f_rel_delta_cplx"]) < FIELD_TOL
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("mode", ["rel", "abs"])
+def test_golden_lpt(cuda, order, mode):
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.distributed import uniform_particles
+    from jaxpm_b200.pm import lpt
+    g = gold("lpt")
+    ic = T(g["ic"], cuda)
+    part = uniform_particles(ic.shape, device=cuda) if mode == "abs" else None
+    dx, p, f = lpt(Planck15(), ic, particles=part, a=float(g["a"]), order=order)
+    for got, name in ((dx, "dx"), (p, "p"), (f, "f")):
+        assert rel_err(N(got), g[f"{mode}_o{order}_{name}"]) < FIELD_TOL, name
+
+
+def test_golden_growth_and_ode_terms(cuda):
+    from jaxpm_b200 import growth
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.ode import make_diffrax_ode, make_ode_fn, symplectic_fpm_ode, symplectic_ode
+    g = gold("growth_ode")
+    cosmo = Planck15()
+    for name in ("E", "dEa", "gp", "Gf", "Gf2", "dGfa", "dGf2a", "growth_factor", "growth_rate",
+                 "growth_factor_second", "growth_rate_second"):
+        np.testing.assert_allclose(getattr(growth, name)(cosmo, g["a"]), g["g_" + name], rtol=2e-5, err_msg=name)
+    shape = g["pos"].shape[:3]
+    pos, vel, a0, dt0 = T(g["pos"], cuda), T(g["vel"], cuda), float(g["ode_a"]), float(g["fpm_dt0"])
+    dpos, dvel = make_ode_fn(shape)((pos, vel), a0, cosmo)
+    assert rel_err(N(dpos), g["ode_dpos"]) < FIELD_TOL and rel_err(N(dvel), g["ode_dvel"]) < FIELD_TOL
+    assert rel_err(N(make_diffrax_ode(shape)(a0, torch.stack([pos, vel]), cosmo)), g["diffrax_rhs"]) < FIELD_TOL
+    drift, kick = symplectic_ode(shape, cosmo)
+    assert rel_err(N(drift(a0, vel, None)), g["sym_drift"]) < FIELD_TOL
+    assert rel_err(N(kick(a0, pos, None)), g["sym_kick"]) < FIELD_TOL
+    drift, kick, first = symplectic_fpm_ode(shape, dt0, cosmo)
+    assert rel_err(N(drift(a0, vel, None)), g["fpm_drift"]) < 3e-5     # growth-table (host scalar) tolerance
+    assert rel_err(N(kick(a0, pos, None)), g["fpm_kick"]) < 3e-5
+    assert rel_err(N(first(a0, pos, cosmo)), g["fpm_first_kick"]) < 3e-5
