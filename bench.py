@@ -123,6 +123,16 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------------------
+def schedule(cosmo, args, kick_drift_coefficients):
+    """(n_pre, d, k): untimed step count and the drift/kick coefficients of n_pre + K equal steps of
+    da = 0.9 / schedule_steps starting at a = 0.1 (the timed K steps end at a = 1 when K <= schedule)."""
+    S, K, W = args.schedule_steps, args.steps, args.warmup
+    n_pre = max(W, S - K)
+    total = n_pre + K
+    d, k = kick_drift_coefficients(cosmo, 0.1, 0.1 + total * 0.9 / S, total, "symplectic")
+    return n_pre, d, k
+
+
 def time_kernel(fn, iters=5, warm=2):
     import torch
     for _ in range(warm):
@@ -173,7 +183,10 @@ def run_gpu(args):
     del ic
     disp, vel = dx.contiguous(), p.contiguous()
     plan = ops.get_plan(shape, dev)
-    d, k = kick_drift_coefficients(cosmo, 0.1, 1.0, K + W, "symplectic")
+    # physical schedule: `--schedule-steps` (40, the step count of BASELINE.json's configs) equal steps in
+    # a from 0.1 to 1; the timed region is the LAST K steps of that run (the most clustered state), the
+    # steps before it are untimed (at least W of them)
+    n_pre, d, k = schedule(cosmo, args, kick_drift_coefficients)
     ops.axpby(1.0, disp, d[0], vel, out=disp)
     torch.cuda.empty_cache()
     # resident tile-sorted state (jaxpm_b200/csrc/sim.cu): loaded once, like the LPT set-up
@@ -181,9 +194,9 @@ def run_gpu(args):
     sim.load(disp, vel)
 
     def step(n):
-        sim.step(k[n], d[n + 1] if n + 1 < K + W else 0.0)
+        sim.step(k[n], d[n + 1] if n + 1 < n_pre + K else 0.0)
 
-    for n in range(W):
+    for n in range(n_pre):
         step(n)
     if world > 1:
         dist.barrier()
@@ -193,7 +206,7 @@ def run_gpu(args):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for n in range(W, W + K):
+    for n in range(n_pre, n_pre + K):
         step(n)
     e1.record()
     torch.cuda.synchronize()
@@ -293,13 +306,15 @@ def run_gpu(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then PM drift-kick steps "
-                                   f"to a=1 (relative mode), Planck15, L={N} Mpc/h",
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then {args.schedule_steps} PM "
+                                   f"drift-kick steps to a=1 (relative mode), Planck15, L={N} Mpc/h; timed = the "
+                                   f"last {K} steps, {n_pre} untimed before",
                        "l2": "inputs larger than L2 (particle state 3.2 GB, mesh 0.5 GB at 512^3)",
                        "parallelism": "single GPU"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
             "clocks": clocks, "sim": {"tile": sim.tile, "margin": sim.margin,
-                                      "fallback_particles_paint_read": fallbacks},
+                                      "global_fallback_particles_paint_read": fallbacks[:2],
+                                      "generic_stencil_particles_paint_read": fallbacks[2:]},
         }))
 
 
@@ -312,7 +327,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--tile", type=int, default=16)
-    ap.add_argument("--margin", type=int, default=2)
+    ap.add_argument("--margin", type=int, default=1)
+    ap.add_argument("--schedule-steps", type=int, default=40,
+                    help="number of equal steps in a from 0.1 to 1 (the timed steps are the last K of them)")
     ap.add_argument("--halo", type=int, default=64, help="halo width of the sharded path (N > 1)")
     ap.add_argument("--no-resident", action="store_true", help="N > 1: order-preserving kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")

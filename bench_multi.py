@@ -12,7 +12,7 @@ import torch.distributed as dist
 
 
 def run_multi(args, world, rank, dev):
-    from bench import METRIC, UNIT, ClockSampler, _peaks
+    from bench import METRIC, UNIT, ClockSampler, _peaks, schedule
     from jaxpm_b200 import _lib, halo, ops
     from jaxpm_b200.cosmology import Planck15, linear_matter_power
     from jaxpm_b200.distributed import Sharding
@@ -36,15 +36,15 @@ def run_multi(args, world, rank, dev):
     del ic, dx, p
     ops.clear_plans()
     torch.cuda.empty_cache()
-    d, k = kick_drift_coefficients(cosmo, 0.1, 1.0, K + W, "symplectic")
+    n_pre, d, k = schedule(cosmo, args, kick_drift_coefficients)
     ops.axpby(1.0, disp, d[0], vel, out=disp)
     stepper = halo.ShardedStepper(disp, vel, h, sh, resident=not args.no_resident, tile=args.tile,
                                   margin=args.margin)
 
     def step(n):
-        stepper.step(k[n], d[n + 1] if n + 1 < K + W else 0.0)
+        stepper.step(k[n], d[n + 1] if n + 1 < n_pre + K else 0.0)
 
-    for n in range(W):
+    for n in range(n_pre):
         step(n)
     dist.barrier()
     torch.cuda.synchronize()
@@ -53,7 +53,7 @@ def run_multi(args, world, rank, dev):
     l0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for n in range(W, W + K):
+    for n in range(n_pre, n_pre + K):
         step(n)
     e1.record()
     torch.cuda.synchronize()
@@ -96,8 +96,9 @@ def run_multi(args, world, rank, dev):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then PM drift-kick steps to a=1 "
-                                   f"(relative mode), Planck15, L={N} Mpc/h",
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then {args.schedule_steps} PM "
+                                   f"drift-kick steps to a=1 (relative mode), Planck15, L={N} Mpc/h; timed = the "
+                                   f"last {K} steps, {n_pre} untimed before",
                        "l2": "inputs larger than L2", "parallelism": f"slab pdims={pdims}, halo={h}",
                        "resident": not args.no_resident},
             "roofline": {"bound": "hbm", "kernel": "whole step (per-GPU share of 124 B/particle-step)",

@@ -229,9 +229,10 @@ int32_t jpm_sim_read_kick_drift(jpm_sim* sim, void* stream, const float* fx, con
                                 const float* fz, float kick_coef, float drift_coef);
 /* One PM step on the resident state: memset, paint, R2C, greens-grad, 3x C2R, read+kick+drift. */
 int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_coef);
-/* out2_host[0..1] = particles that took the global-memory fallback in paint / read so far
- * (synchronises the stream). */
-int32_t jpm_sim_stats_host(jpm_sim* sim, void* stream, int64_t* out2_host);
+/* out4_host[0..1] = particles that took the global-memory fallback (drifted beyond the margin) in
+ * paint / read so far; [2..3] = particles that took the generic (periodic-wrap) stencil inside the
+ * shared-memory box in paint / read.  Synchronises the stream. */
+int32_t jpm_sim_stats_host(jpm_sim* sim, void* stream, int64_t* out4_host);
 
 /* Number of kernels of THIS library launched since process start (for bench accounting). */
 int64_t jpm_kernel_launch_count(void);

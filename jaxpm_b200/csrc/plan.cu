@@ -2,27 +2,13 @@
 // composed force / step entry points.
 //   reference: jaxpm/distributed.py:37-42 (fft3d/ifft3d), jaxpm/kernels.py:10-23,41-115,139-165,
 //              jaxpm/pm.py:12-58 (pm_forces), :88-124 (2LPT source), jaxpm/ode.py:91-117
-#include <cufft.h>
-
+#include <algorithm>
 #include <cmath>
 #include <vector>
 
 #include "common.cuh"
 
-struct jpm_plan {
-  int nx, ny, nz, nzh;
-  long long ncell, nspec;
-  cufftHandle r2c = 0, c2r1 = 0, c2r3 = 0;
-  void* work = nullptr;
-  size_t work_bytes = 0;
-  // per-axis tables (device): w_d (rad/cell, fp32) and a_d = (8 sin w - sin 2w)/6
-  float *wx = nullptr, *wy = nullptr, *wz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
-  // scratch owned by the plan, used by the composed entry points
-  float* density = nullptr;   // [ncell]
-  float2* spec = nullptr;     // [nspec]
-  float2* spec3 = nullptr;    // [3*nspec]
-  float* force3 = nullptr;    // [3*ncell]
-};
+#include "plan_internal.cuh"
 
 namespace jpm {
 
@@ -138,10 +124,6 @@ lpt2_source_kernel(float* __restrict__ d2, const float* __restrict__ s, long lon
   }
 }
 
-float* plan_density(jpm_plan* p) { return p->density; }
-float* plan_force3(jpm_plan* p) { return p->force3; }
-long long plan_ncell(jpm_plan* p) { return p->ncell; }
-void plan_dims(jpm_plan* p, int* nx, int* ny, int* nz) { *nx = p->nx; *ny = p->ny; *nz = p->nz; }
 
 static void build_tables(int n, int nh, std::vector<float>& w, std::vector<float>& a) {
   // fftk: w = 2*pi*fftfreq(n) (kernels.py:10-23, [ext] jaxdecomp.fftfreq3d), stored fp32;
@@ -171,6 +153,152 @@ static int kspace_grid(const jpm_plan* p) {
   const long long rows = (long long)p->nx * p->ny;
   const long long cap = (long long)kNumSMs * 8;
   return (int)(rows < cap ? rows : cap);
+}
+
+
+// ---------------------------------------------------------------------------------
+// Ghost zones of the padded meshes.  Along one axis of interior length n with G ghosts per side
+// (padded coordinates): ghost [0, G) is the periodic image of interior [n, n+G), ghost
+// [n+G, n+2G) is the image of interior [G, 2G).
+//   FOLD (after paint):  interior += ghost, axes in the order x, y, z with shrinking extents of the
+//                        other axes, so that edge/corner ghosts end up in the interior;
+//   FILL (before read):  ghost = interior, axes in the order z, y, x with growing extents.
+// One thread per ghost cell of the slab pair; u/v enumerate the other two axes (v fastest).
+// ---------------------------------------------------------------------------------
+template <bool FOLD>
+__global__ void __launch_bounds__(256)
+ghost_kernel(float* __restrict__ a, long long batch_stride, int G, int n, long long sa, int nu, int u0,
+             long long su, int nv, int v0, long long sv, bool g_fastest) {
+  float* m = a + blockIdx.y * batch_stride;
+  const long long total = 2LL * G * nu * nv;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+       t += (long long)gridDim.x * blockDim.x) {
+    int g2, u, v;
+    if (g_fastest) {  // z-axis slabs: the ghost index is the contiguous one
+      g2 = (int)(t % (2 * G));
+      const long long r = t / (2 * G);
+      v = (int)(r % nv);
+      u = (int)(r / nv);
+    } else {
+      v = (int)(t % nv);
+      const long long r = t / nv;
+      u = (int)(r % nu);
+      g2 = (int)(r / nu);
+    }
+    const int ghost = g2 < G ? g2 : n + g2;                 // [0,G) or [n+G, n+2G)
+    const int inner = g2 < G ? g2 + n : g2;                 // its periodic image inside
+    const long long base = (long long)(u + u0) * su + (long long)(v + v0) * sv;
+    if (FOLD) m[base + inner * sa] += m[base + ghost * sa];
+    else m[base + ghost * sa] = m[base + inner * sa];
+  }
+}
+
+template <bool FOLD>
+static int32_t ghost_pass(jpm_plan* p, cudaStream_t st, float* a, int batch) {
+  const int G = p->G;
+  const long long sx = (long long)p->nyp * p->nzp, sy = p->nzp, sz = 1;
+  // axis, other axes (u, v) with [start, count)
+  for (int step = 0; step < 3; ++step) {
+    const int axis = FOLD ? step : 2 - step;
+    long long total;
+    if (axis == 0) {        // x slabs: y, z over the full padded extents
+      total = 2LL * G * p->nyp * p->nzp;
+      ghost_kernel<FOLD><<<dim3((unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16), batch), 256, 0, st>>>(
+          a, p->npad, G, p->nx, sx, p->nyp, 0, sy, p->nzp, 0, sz, false);
+    } else if (axis == 1) { // y slabs: x interior, z full
+      total = 2LL * G * p->nx * p->nzp;
+      ghost_kernel<FOLD><<<dim3((unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16), batch), 256, 0, st>>>(
+          a, p->npad, G, p->ny, sy, p->nx, G, sx, p->nzp, 0, sz, false);
+    } else {                // z slabs: x, y interior
+      total = 2LL * G * p->nx * p->ny;
+      ghost_kernel<FOLD><<<dim3((unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16), batch), 256, 0, st>>>(
+          a, p->npad, G, p->nz, sz, p->nx, G, sx, p->ny, G, sy, true);
+    }
+    JPM_LAUNCH_CHECK();
+  }
+  return JPM_OK;
+}
+
+int32_t encode_tensor_map(CUtensorMap* out, float* base, int rank, const unsigned long long* dims,
+                          const unsigned long long* strides_bytes, const unsigned* box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                               const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                               CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn fn = nullptr;
+  if (!fn) {
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    JPM_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &q));
+    if (q != cudaDriverEntryPointSuccess || !sym) {
+      set_error("cuTensorMapEncodeTiled not available from the driver");
+      return JPM_ERR_CUDA;
+    }
+    fn = (EncodeFn)sym;
+  }
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], e[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; e[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, base, d, s, b, e,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+    return JPM_ERR_CUDA;
+  }
+  return JPM_OK;
+}
+
+int32_t plan_enable_padded(jpm_plan* p) {
+  if (p->G || p->density_p) return JPM_OK;
+  if (p->nz % 4 != 0) return JPM_OK;  // TMA needs 16-byte row strides
+  const int G = kGhost;
+  p->nxp = p->nx + 2 * G; p->nyp = p->ny + 2 * G; p->nzp = p->nz + 2 * G;
+  p->npad = (long long)p->nxp * p->nyp * p->nzp;
+  if (p->npad >= (1ll << 31)) return JPM_OK;
+  JPM_CUDA(cudaMalloc(&p->density_p, p->npad * sizeof(float)));
+  JPM_CUDA(cudaMalloc(&p->force3_p, 3 * p->npad * sizeof(float)));
+  JPM_CUDA(cudaMemset(p->force3_p, 0, 3 * p->npad * sizeof(float)));
+  int n[3] = {p->nx, p->ny, p->nz};
+  int remb[3] = {p->nxp, p->nyp, p->nzp};      // real side: embedded in the padded array
+  int cemb[3] = {p->nx, p->ny, p->nzh};        // spectrum side: compact
+  size_t ws[2] = {0, 0};
+  JPM_CUFFT(cufftCreate(&p->r2c_p));
+  JPM_CUFFT(cufftSetAutoAllocation(p->r2c_p, 0));
+  JPM_CUFFT(cufftMakePlanMany(p->r2c_p, 3, n, remb, 1, (int)p->npad, cemb, 1, (int)p->nspec, CUFFT_R2C, 1, &ws[0]));
+  JPM_CUFFT(cufftCreate(&p->c2r3_p));
+  JPM_CUFFT(cufftSetAutoAllocation(p->c2r3_p, 0));
+  JPM_CUFFT(cufftMakePlanMany(p->c2r3_p, 3, n, cemb, 1, (int)p->nspec, remb, 1, (int)p->npad, CUFFT_C2R, 3, &ws[1]));
+  const size_t need = ws[0] > ws[1] ? ws[0] : ws[1];
+  if (need > p->work_bytes) {
+    if (p->work) cudaFree(p->work);
+    p->work = nullptr;
+    JPM_CUDA(cudaMalloc(&p->work, need));
+    p->work_bytes = need;
+    JPM_CUFFT(cufftSetWorkArea(p->r2c, p->work));
+    JPM_CUFFT(cufftSetWorkArea(p->c2r1, p->work));
+    JPM_CUFFT(cufftSetWorkArea(p->c2r3, p->work));
+  }
+  JPM_CUFFT(cufftSetWorkArea(p->r2c_p, p->work));
+  JPM_CUFFT(cufftSetWorkArea(p->c2r3_p, p->work));
+  p->G = G;
+  return JPM_OK;
+}
+
+int32_t plan_padded_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
+                           float filter_kmax) {
+  JPM_CHECK_ARG(p->G > 0, "padded meshes not enabled");
+  const long long off = ((long long)p->G * p->nyp + p->G) * p->nzp + p->G;   // interior origin
+  int32_t rc;
+  if ((rc = ghost_pass<true>(p, st, p->density_p, 1))) return rc;
+  JPM_CUFFT(cufftSetStream(p->r2c_p, st));
+  JPM_CUFFT(cufftExecR2C(p->r2c_p, p->density_p + off, (cufftComplex*)p->spec));
+  if ((rc = jpm_greens_grad_c64(p, st, p->spec, p->spec3, 1.0f / (float)p->ncell, r_split, filter_tab, n_tab,
+                                filter_kmax)))
+    return rc;
+  JPM_CUFFT(cufftSetStream(p->c2r3_p, st));
+  JPM_CUFFT(cufftExecC2R(p->c2r3_p, (cufftComplex*)p->spec3, p->force3_p + off));
+  return ghost_pass<false>(p, st, p->force3_p, 3);
 }
 
 }  // namespace jpm
@@ -222,6 +350,10 @@ extern "C" int32_t jpm_plan_destroy(jpm_plan* p) {
   if (p->r2c) cufftDestroy(p->r2c);
   if (p->c2r1) cufftDestroy(p->c2r1);
   if (p->c2r3) cufftDestroy(p->c2r3);
+  if (p->r2c_p) cufftDestroy(p->r2c_p);
+  if (p->c2r3_p) cufftDestroy(p->c2r3_p);
+  if (p->density_p) cudaFree(p->density_p);
+  if (p->force3_p) cudaFree(p->force3_p);
   void* bufs[] = {p->work, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->density, p->spec, p->spec3, p->force3};
   for (void* b : bufs)
     if (b) cudaFree(b);

@@ -1,0 +1,46 @@
+// Internal layout of the opaque jpm_plan handle (shared by plan.cu and sim.cu).
+#pragma once
+#include <cuda.h>
+#include <cufft.h>
+
+#include "common.cuh"
+
+struct jpm_plan {
+  int nx, ny, nz, nzh;
+  long long ncell, nspec;
+  cufftHandle r2c = 0, c2r1 = 0, c2r3 = 0;
+  void* work = nullptr;
+  size_t work_bytes = 0;
+  // per-axis tables (device): w_d (rad/cell, fp32) and a_d = (8 sin w - sin 2w)/6
+  float *wx = nullptr, *wy = nullptr, *wz = nullptr, *ax = nullptr, *ay = nullptr, *az = nullptr;
+  // scratch owned by the plan, used by the composed entry points
+  float* density = nullptr;   // [ncell]
+  float2* spec = nullptr;     // [nspec]
+  float2* spec3 = nullptr;    // [3*nspec]
+  float* force3 = nullptr;    // [3*ncell]
+  // ---- ghost-zone ("padded") meshes for the TMA tile path of csrc/sim.cu ------------------------
+  // Every axis carries G ghost cells on both sides: array dims (n+2G)^3, interior starts at index G.
+  // Ghost cells are periodic images: paint accumulates into them and jpm::ghost_fold adds them back
+  // onto the interior; jpm::ghost_fill copies interior faces out before the read.  With ghosts no
+  // tile box ever wraps, so a box is ONE TMA tensor op (cp.async.bulk.tensor / cp.reduce.async.bulk.tensor).
+  int G = 0;                  // 0 = padded path not available (nz % 4 != 0, or no driver entry point)
+  int nxp = 0, nyp = 0, nzp = 0;
+  long long npad = 0;
+  float* density_p = nullptr; // [nxp][nyp][nzp]
+  float* force3_p = nullptr;  // [3][nxp][nyp][nzp]
+  cufftHandle r2c_p = 0, c2r3_p = 0;
+};
+
+namespace jpm {
+constexpr int kGhost = 4;
+// Lazily allocate the padded meshes and their cuFFT plans.  Returns JPM_OK and leaves p->G == 0 when
+// the shape does not qualify.
+int32_t plan_enable_padded(jpm_plan* p);
+// density_p (painted, ghosts not yet folded) -> force3_p (ghosts filled), all on `stream`.
+int32_t plan_padded_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab,
+                           int n_tab, float filter_kmax);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
+// dims/strides innermost first, rank 3 or 4, fp32, no swizzle/interleave, OOB -> zero fill.
+int32_t encode_tensor_map(CUtensorMap* out, float* base, int rank, const unsigned long long* dims,
+                          const unsigned long long* strides_bytes, const unsigned* box);
+}  // namespace jpm

@@ -20,29 +20,34 @@
 //             its slot of the NEXT ordering (exclusive scan of count[] -> cursor[]), so the
 //             re-sort costs no extra pass over the particles.
 // The user-visible order is restored by jpm_sim_store (scatter by id).
-#include "common.cuh"
-
-struct jpm_plan;
-extern "C" int32_t jpm_density_to_force_meshes(jpm_plan*, void*, const float*, float*, float,
-                                               const float*, int32_t, float);
-namespace jpm {
-float* plan_density(jpm_plan* p);
-float* plan_force3(jpm_plan* p);
-long long plan_ncell(jpm_plan* p);
-void plan_dims(jpm_plan* p, int* nx, int* ny, int* nz);
-}  // namespace jpm
+//
+// Two flavours of the tile kernels (template flag TMA):
+//   TMA = false: the mesh is a plain compact [nx][ny][nz] array (public jpm_sim_paint /
+//                jpm_sim_read_kick_drift on caller-owned meshes); boxes are staged with cp.async rows and
+//                flushed with vector red.global.add, wrapping periodically cell by cell;
+//   TMA = true : the mesh is the plan's ghost-zone array (plan_internal.cuh), where no box ever wraps:
+//                the read box (3 force meshes) arrives as ONE cp.async.bulk.tensor.4d signalled on an
+//                mbarrier, the paint box leaves as ONE cp.reduce.async.bulk.tensor.3d (.add.f32).
+#include "plan_internal.cuh"
 
 struct SimGeom {
-  int nx, ny, nz;            // mesh painted into / read from
+  int nx, ny, nz;            // mesh painted into / read from (logical, periodic)
   int pny, pnz, hx, hy;      // particle grid (relative rule) and halo offsets
   int tshift, T, m;          // tile edge = 1 << tshift, margin
   int ntx, nty, ntz, nt;     // tile grid
   int BX, BY, BZ;            // shared-memory box = T + 2m + 1 per axis
+  // storage of the mesh the kernels address directly (fallback atomics / gathers, non-TMA rows):
+  // element (i, j, k) lives at ((i + mo) * msx + (j + mo) * msy + (k + mo)); batch stride mb
+  long long msx, msy, mb;
+  int mo;
 };
 
 struct jpm_sim {
   jpm_plan* plan = nullptr;
-  SimGeom g;
+  SimGeom g;                           // compact-mesh geometry
+  SimGeom gp;                          // same tiles on the plan's ghost-zone meshes (TMA path)
+  bool tma = false;
+  CUtensorMap tm_rho, tm_f3;           // box maps of density_p (3-D) and force3_p (4-D)
   int relative = 0;
   long long np = 0;
   float4* pos[2] = {nullptr, nullptr};
@@ -50,12 +55,15 @@ struct jpm_sim {
   int* start[2] = {nullptr, nullptr};  // [nt+1]
   int* count = nullptr;                // [nt]  occupancy of the next ordering
   int* cursor = nullptr;               // [nt]  slot cursors while scattering
-  unsigned long long* stats = nullptr; // [0] paint fallbacks, [1] read fallbacks
+  unsigned long long* stats = nullptr; // [0]/[1] paint/read global-memory fallbacks, [2]/[3] generic-stencil particles
   int cur = 0;
   bool painted = false, loaded = false;
 };
 
 namespace jpm {
+
+constexpr int kTmaMz = 4;   // z margin below a tile in the TMA flavour (== kGhost: box z origin = tile origin in padded coordinates)
+static_assert(kTmaMz == kGhost, "TMA box z origin must coincide with a 16-byte aligned padded coordinate");
 
 __device__ __forceinline__ int wrap_local(int i, int o, int n) {
   int a = i - o;
@@ -173,41 +181,46 @@ sim_store_kernel(SimGeom g, const float4* __restrict__ spos, const float* __rest
   if (vel) { vel[3 * id] = svel[q]; vel[3 * id + 1] = svel[np + q]; vel[3 * id + 2] = svel[2 * np + q]; }
 }
 
-// exclusive scan of count[nt] -> start[nt+1]; cursor = start; count = 0.  One CTA.
+// exclusive scan of count[nt] -> start[nt+1]; cursor = start; count = 0.  One CTA of 32 warps; warp w
+// owns the contiguous segment [w*seg, (w+1)*seg) and walks it 32 entries at a time (coalesced).
 __global__ void __launch_bounds__(1024)
 sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int nt) {
-  __shared__ int part[1024];
-  const int tid = threadIdx.x;
-  const int chunk = (nt + 1023) / 1024;
-  const int b = tid * chunk, e = min(b + chunk, nt);
+  __shared__ int wsum[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int seg = ((nt + 31) / 32 + 31) & ~31;
+  const int b = warp * seg, e = min(b + seg, nt);
   int s = 0;
-  for (int i = b; i < e; ++i) s += count[i];
-  part[tid] = s;
+  for (int i = b + lane; i < e; i += 32) s += count[i];
+#pragma unroll
+  for (int off = 16; off; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) wsum[warp] = s;
   __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const int v = (tid >= off) ? part[tid - off] : 0;
-    __syncthreads();
-    part[tid] += v;
-    __syncthreads();
+  int run = 0;
+  for (int w = 0; w < warp; ++w) run += wsum[w];
+  for (int i0 = b; i0 < e; i0 += 32) {
+    const int i = i0 + lane;
+    const int c = (i < e) ? count[i] : 0;
+    int incl = c;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    if (i < e) {
+      start[i] = run + incl - c;
+      cursor[i] = run + incl - c;
+      count[i] = 0;
+    }
+    run += __shfl_sync(0xffffffffu, incl, 31);
   }
-  int run = part[tid] - s;  // exclusive prefix of this chunk
-  for (int i = b; i < e; ++i) {
-    const int c = count[i];
-    start[i] = run;
-    cursor[i] = run;
-    count[i] = 0;
-    run += c;
-  }
-  if (tid == 1023) start[nt] = part[1023];
+  if (threadIdx.x == 1023) start[nt] = run;   // the last warp's running total is the grand total
 }
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
 }
 
-// Per-lane view of the 8 corners, selectable at run time so that each lane can walk the corners
-// in a different order (lane-rotated): particles that share a cell then update 8 DIFFERENT
-// addresses at any instant and the shared-memory CAS loops rarely retry.
+// Generic (slow-path) view of the 8 corners: wrapped global indices, box-local coordinates, weights.
 struct Corners {
   int ix[2], iy[2], iz[2];     // wrapped global cell indices (-1 = dropped)
   int lx[2], ly[2], lz[2];     // box-local coordinates
@@ -215,7 +228,7 @@ struct Corners {
   bool inside;
 };
 
-template <int B>
+template <int B, int BZV>
 __device__ __forceinline__ void make_corners(const SimGeom& g, const Cic1& cx, const Cic1& cy,
                                              const Cic1& cz, int ox, int oy, int oz, Corners& c) {
   c.ix[0] = cx.i0; c.ix[1] = cx.i1; c.iy[0] = cy.i0; c.iy[1] = cy.i1; c.iz[0] = cz.i0; c.iz[1] = cz.i1;
@@ -226,116 +239,280 @@ __device__ __forceinline__ void make_corners(const SimGeom& g, const Cic1& cx, c
     c.lx[a] = wrap_local(max(c.ix[a], 0), ox, g.nx);
     c.ly[a] = wrap_local(max(c.iy[a], 0), oy, g.ny);
     c.lz[a] = wrap_local(max(c.iz[a], 0), oz, g.nz);
-    c.inside = c.inside && c.lx[a] < B && c.ly[a] < B && c.lz[a] < B;
+    c.inside = c.inside && c.lx[a] < B && c.ly[a] < B && c.lz[a] < BZV;
   }
+}
+
+// ---- fast stencil ---------------------------------------------------------------------------------
+// Per axis: cell of corner 0 and the two weights, plus "the two corners are periodic neighbours
+// (i1 == i0 + 1 mod n) and neither is dropped".  The common case (no wrap on this axis) reduces the
+// generic rules of common.cuh to a handful of operations with bit-identical results:
+//   relative (painting_utils.py:48-65): pp = base + d; corner c: r = pp + c (in [0, L), no mod),
+//       idx = floor(r), nd = pp - idx (|nd| <= 1 < L/4, no rint correction), w = 1 - |nd|;
+//   absolute (painting.py:22-37): idx = floor(p) + c, w = 1 - |p - idx|, 0 <= idx < n (no mod).
+// Lanes at the periodic edge run the generic rule for that axis only.
+template <bool REL>
+__device__ __forceinline__ bool axis_fast(int base, float v, int n, int& i0, float& w0, float& w1) {
+  if (REL) {
+    const float pp = (float)base + v;
+    const float x1 = pp + 1.0f;
+    if (pp >= 0.0f && x1 < (float)n) {
+      const float f0 = floorf(pp), f1 = floorf(x1);
+      w0 = 1.0f - fabsf(pp - f0);
+      w1 = 1.0f - fabsf(pp - f1);
+      i0 = (int)f0;
+      return f1 == f0 + 1.0f;
+    }
+    const Cic1 c = cic_rel<false>(base, v, n);
+    i0 = c.i0; w0 = c.w0; w1 = c.w1;
+    return c.i0 >= 0 && c.i1 >= 0 && (c.i1 == c.i0 + 1 || (c.i0 == n - 1 && c.i1 == 0));
+  } else {
+    const float f = floorf(v);
+    w0 = 1.0f - fabsf(v - f);
+    w1 = 1.0f - fabsf(v - (f + 1.0f));
+    i0 = (int)f;
+    if ((unsigned)i0 < (unsigned)(n - 1)) return true;
+    i0 = pymod(i0, n);                      // i1 = pymod((int)(f + 1)) is its periodic neighbour
+    return fabsf(f) < 1.0e9f;               // int conversion exact
+  }
+}
+
+// box-local coordinate of global cell i for a box starting at o (o in [-M, n)), periodic
+__device__ __forceinline__ int local_wrap(int i, int o, int n) {
+  int l = i - o;
+  if (l < 0) l += n;
+  else if (l >= n) l -= n;
+  return l;
+}
+
+struct FastStencil {
+  int i0, j0, k0;               // global cell of corner (0,0,0)
+  float wx0, wx1, wy0, wy1, wz0, wz1;
+};
+
+template <bool REL>
+__device__ __forceinline__ bool stencil_fast(const SimGeom& g, const float4& p, FastStencil& s) {
+  int bi = 0, bj = 0, bk = 0;
+  if (REL) {
+    const int w = __float_as_int(p.w);
+    bk = w & 1023;
+    bj = ((w >> 10) & 1023) + g.hy;
+    bi = (w >> 20) + g.hx;
+  }
+  const bool fx = axis_fast<REL>(bi, p.x, g.nx, s.i0, s.wx0, s.wx1);
+  const bool fy = axis_fast<REL>(bj, p.y, g.ny, s.j0, s.wy0, s.wy1);
+  const bool fz = axis_fast<REL>(bk, p.z, g.nz, s.k0, s.wz0, s.wz1);
+  return fx && fy && fz;
+}
+
+// ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG / UTMAREDG, SYNCS) ------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+// global (4-D tensor map: z, y, x, component) -> shared box, completion counted on `bar`
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2, int c3,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_u32(bar))
+      : "memory");
+}
+// shared box -> global += (3-D tensor map), f32 add performed by the TMA unit at L2
+__device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ long long mesh_index(const SimGeom& g, int i, int j, int k) {
+  return (long long)(i + g.mo) * g.msx + (long long)(j + g.mo) * g.msy + (k + g.mo);
 }
 
 // ---- paint -------------------------------------------------------------------------------------
 // One CTA per tile.  Box = (T+2M+1)^3 cells, rows padded to an even length BZ so that the flush
 // can use 8-byte vector reductions (REDG.E.ADD.F32x2).
-template <bool REL, int TS, int M>
-__global__ void __launch_bounds__(256, 4)
-sim_paint_kernel(SimGeom g, const float4* __restrict__ spos, const int* __restrict__ start,
-                 float* __restrict__ mesh, int* __restrict__ count, unsigned long long* __restrict__ stats) {
-  constexpr int T = 1 << TS, B = T + 2 * M + 1, BZ = (B + 1) & ~1, NBOX = B * B * BZ;
-  extern __shared__ __align__(16) float box[];
-  __shared__ int scnt[27];
+//
+// Accumulation is 40.24 fixed point on NATIVE 32-bit shared-memory integer atomics: fp32
+// atomicAdd on shared memory is a compare-and-swap loop that retries whenever two lanes of a warp
+// hit the same cell (3.4 passes on average on a clustered 512^3 set, profiles/r01a), integer ATOMS.ADD
+// resolves the conflict in hardware.  lo[] holds the low 32 bits (weights scaled by 2^24, rounded to
+// nearest: |error| <= 3e-8 per corner, below fp32 resolution of the weights themselves), a carry
+// out of lo bumps a 16-bit field of hi[] (two cells per word), so a cell can take 2^24 particles.
+// The sum inside a tile is therefore order-independent (bit-reproducible); only the fp32 merge of
+// overlapping tile margins into the global mesh is not.
+constexpr float kFixScale = 16777216.0f;           // 2^24
+constexpr float kFixInv = 1.0f / 16777216.0f;
+
+__device__ __forceinline__ void fixed_carry(unsigned* hi, int idx) {
+  atomicAdd(hi + (idx >> 1), 1u << ((idx & 1) * 16));
+}
+
+__device__ __forceinline__ float fixed_to_float(unsigned lo, unsigned hi16) {
+  return (hi16 ? __ull2float_rn(((unsigned long long)hi16 << 32) | lo) : __uint2float_rn(lo)) * kFixInv;
+}
+
+template <bool REL, int TS, int M, bool TMA>
+__global__ void __launch_bounds__(256, 3)
+sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
+                 const int* __restrict__ start, float* __restrict__ mesh, int* __restrict__ count,
+                 unsigned long long* __restrict__ stats) {
+  // TMA boxes must start on a 16-byte boundary of the innermost (z) axis (misaligned coordinates raise
+  // "illegal instruction", tools/tma_probe.cu): the z margin below the tile is kTmaMz = 4 cells there.
+  constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
+  constexpr int BZ = TMA ? ((T + MZ + M + 1 + 3) & ~3) : ((B + 1) & ~1), NBOX = B * B * BZ;
+  constexpr int BZV = TMA ? BZ : B;          // z cells of the box that may be touched
+  constexpr int SX = B * BZ, SY = BZ;
+  extern __shared__ __align__(128) unsigned sbox[];    // lo[NBOX] | hi[NBOX / 2]
+  unsigned* const lo = sbox;
+  unsigned* const hi = sbox + NBOX;
+  __shared__ int scnt[28];                             // 27 neighbour tiles + generic-stencil count
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
   const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
+  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - MZ;
+  const int lane = threadIdx.x & 31;
+  int nslow = 0;
   // first particle of this thread is in flight while the box is being zeroed
+  // the first two particles of this thread are in flight while the box is being zeroed; the loop
+  // keeps two loads per thread outstanding (the kernel is otherwise latency-bound on this stream)
   int q = beg + threadIdx.x;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f), pn = p;
   if (q < end) p = __ldcs(spos + q);
-  for (int i = threadIdx.x; i < NBOX / 2; i += blockDim.x) reinterpret_cast<float2*>(box)[i] = make_float2(0.f, 0.f);
-  if (threadIdx.x < 27) scnt[threadIdx.x] = 0;
+  if (q + (int)blockDim.x < end) pn = __ldcs(spos + q + blockDim.x);
+  for (int i = threadIdx.x; i < NBOX + NBOX / 2; i += blockDim.x) sbox[i] = 0u;
+  if (threadIdx.x < 28) scnt[threadIdx.x] = 0;
   __syncthreads();
-  // Lanes walk the 8 corners in lane-dependent (XOR-permuted) order: particles sharing a cell then
-  // update 8 different addresses at any instant, so the shared-memory CAS loops rarely retry.
-  const bool sx = threadIdx.x & 1, sy = threadIdx.x & 2, sz = threadIdx.x & 4;
-  while (q < end) {
+  for (int qb = beg + (threadIdx.x & ~31); qb < end; qb += blockDim.x) {   // warp-uniform trip count
+    const bool valid = q < end;
     const int qn = q + blockDim.x;
-    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (qn < end) pn = __ldcs(spos + qn);  // prefetch
-    Cic1 cx, cy, cz;
-    sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-    Corners c;
-    make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
-    if (c.inside) {
-      // per-axis swap (once per particle) instead of per-corner selects
-      const int lxa = sx ? c.lx[1] : c.lx[0], lxb = sx ? c.lx[0] : c.lx[1];
-      const int lya = sy ? c.ly[1] : c.ly[0], lyb = sy ? c.ly[0] : c.ly[1];
-      const int lza = sz ? c.lz[1] : c.lz[0], lzb = sz ? c.lz[0] : c.lz[1];
-      float wxa = sx ? c.wx[1] : c.wx[0], wxb = sx ? c.wx[0] : c.wx[1];
-      float wya = sy ? c.wy[1] : c.wy[0], wyb = sy ? c.wy[0] : c.wy[1];
-      float wza = sz ? c.wz[1] : c.wz[0], wzb = sz ? c.wz[0] : c.wz[1];
-      if (REL) {  // a dropped corner (index -1, relative rule only) contributes nothing
-        if ((sx ? c.ix[1] : c.ix[0]) < 0) wxa = 0.f;
-        if ((sx ? c.ix[0] : c.ix[1]) < 0) wxb = 0.f;
-        if ((sy ? c.iy[1] : c.iy[0]) < 0) wya = 0.f;
-        if ((sy ? c.iy[0] : c.iy[1]) < 0) wyb = 0.f;
-        if ((sz ? c.iz[1] : c.iz[0]) < 0) wza = 0.f;
-        if ((sz ? c.iz[0] : c.iz[1]) < 0) wzb = 0.f;
+    float4 pnn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (qn + (int)blockDim.x < end) pnn = __ldcs(spos + qn + blockDim.x);  // prefetch, two ahead
+    int ti = 0, tj = 0, tk = 0;            // tile the particle is in now (next ordering)
+    if (valid) {
+      FastStencil s;
+      bool fast = stencil_fast<REL>(g, p, s);
+      const int lx = local_wrap(s.i0, ox, g.nx), ly = local_wrap(s.j0, oy, g.ny), lz = local_wrap(s.k0, oz, g.nz);
+      fast = fast && (unsigned)lx < (unsigned)(B - 1) && (unsigned)ly < (unsigned)(B - 1) &&
+             (unsigned)lz < (unsigned)(BZV - 1);
+      if (fast) {
+        const int o = lx * SX + ly * SY + lz;
+        const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
+        // reference order (kx*ky)*kz, weight 1; corner offsets are compile-time constants
+        const unsigned v[8] = {__float2uint_rn(w00 * s.wz0 * kFixScale), __float2uint_rn(w00 * s.wz1 * kFixScale),
+                               __float2uint_rn(w01 * s.wz0 * kFixScale), __float2uint_rn(w01 * s.wz1 * kFixScale),
+                               __float2uint_rn(w10 * s.wz0 * kFixScale), __float2uint_rn(w10 * s.wz1 * kFixScale),
+                               __float2uint_rn(w11 * s.wz0 * kFixScale), __float2uint_rn(w11 * s.wz1 * kFixScale)};
+        constexpr int off[8] = {0, 1, SY, SY + 1, SX, SX + 1, SX + SY, SX + SY + 1};
+        unsigned old[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) old[c] = atomicAdd(lo + o + off[c], v[c]);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          if (old[c] + v[c] < old[c]) fixed_carry(hi, o + off[c]);
+        ti = s.i0 >> TS; tj = s.j0 >> TS; tk = s.k0 >> TS;
+      } else {
+        Cic1 cx, cy, cz;
+        sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+        Corners c;
+        make_corners<B, BZV>(g, cx, cy, cz, ox, oy, oz, c);
+#pragma unroll
+        for (int cc = 0; cc < 8; ++cc) {
+          const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+          if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;   // dropped by the reference
+          const float w = (c.wx[a] * c.wy[b]) * c.wz[d];
+          if (c.inside) {
+            const int idx = c.lx[a] * SX + c.ly[b] * SY + c.lz[d];
+            const unsigned v = __float2uint_rn(w * kFixScale);
+            const unsigned old = atomicAdd(lo + idx, v);
+            if (old + v < old) fixed_carry(hi, idx);
+          } else {
+            atomicAdd(mesh + mesh_index(g, c.ix[a], c.iy[b], c.iz[d]), w);
+          }
+        }
+        if (c.inside) ++nslow; else atomicAdd(stats, 1ull);
+        ti = max(cx.i0, 0) >> TS; tj = max(cy.i0, 0) >> TS; tk = max(cz.i0, 0) >> TS;
       }
-      const int lxs[2] = {lxa * (B * BZ), lxb * (B * BZ)}, lys[2] = {lya * BZ, lyb * BZ}, lzs[2] = {lza, lzb};
-      const float wxs[2] = {wxa, wxb}, wys[2] = {wya, wyb}, wzs[2] = {wza, wzb};
-#pragma unroll
-      for (int a = 0; a < 2; ++a)
-#pragma unroll
-        for (int b = 0; b < 2; ++b)
-#pragma unroll
-          for (int d = 0; d < 2; ++d)  // reference order (kx*ky)*kz, weight 1
-            atomicAdd(box + lxs[a] + lys[b] + lzs[d], (wxs[a] * wys[b]) * wzs[d]);
-    } else {
-#pragma unroll
-      for (int cc = 0; cc < 8; ++cc) {
-        const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
-        if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
-        atomicAdd(mesh + ((long long)c.ix[a] * g.ny + c.iy[b]) * g.nz + c.iz[d],
-                  (c.wx[a] * c.wy[b]) * c.wz[d]);
-      }
-      atomicAdd(stats, 1ull);
     }
-    // occupancy of the next ordering: shared counters for the 27 surrounding tiles
-    const int i0 = max(cx.i0, 0) >> TS, j0 = max(cy.i0, 0) >> TS, k0 = max(cz.i0, 0) >> TS;
-    int dx = i0 - tx, dy = j0 - ty, dz = k0 - tz;
-    if (dx > 1) dx -= g.ntx; else if (dx < -1) dx += g.ntx;
-    if (dy > 1) dy -= g.nty; else if (dy < -1) dy += g.nty;
-    if (dz > 1) dz -= g.ntz; else if (dz < -1) dz += g.ntz;
-    if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1)
-      atomicAdd(scnt + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1), 1);
-    else
-      atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, 1);
+    // occupancy of the next ordering: the home tile is counted once per warp, the 26 neighbours in
+    // shared counters, anything further away straight in global memory
+    const bool home = valid && ti == tx && tj == ty && tk == tz;
+    const unsigned mh = __ballot_sync(0xffffffffu, home);
+    if (lane == 0 && mh) atomicAdd(scnt + 13, __popc(mh));
+    if (valid && !home) {
+      int dx = ti - tx, dy = tj - ty, dz = tk - tz;
+      if (dx > 1) dx -= g.ntx; else if (dx < -1) dx += g.ntx;
+      if (dy > 1) dy -= g.nty; else if (dy < -1) dy += g.nty;
+      if (dz > 1) dz -= g.ntz; else if (dz < -1) dz += g.ntz;
+      if (dx >= -1 && dx <= 1 && dy >= -1 && dy <= 1 && dz >= -1 && dz <= 1)
+        atomicAdd(scnt + (dx + 1) * 9 + (dy + 1) * 3 + (dz + 1), 1);
+      else
+        atomicAdd(count + (ti * g.nty + tj) * g.ntz + tk, 1);
+    }
     p = pn;
+    pn = pnn;
     q = qn;
   }
+  if (nslow) atomicAdd(scnt + 27, nslow);
   __syncthreads();
+  if (threadIdx.x == 27 && scnt[27]) atomicAdd(stats + 2, (unsigned long long)scnt[27]);
   if (threadIdx.x < 27 && scnt[threadIdx.x]) {
     const int dx = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x % 3 - 1;
     const int i0 = pymod(tx + dx, g.ntx), j0 = pymod(ty + dy, g.nty), k0 = pymod(tz + dz, g.ntz);
     atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, scnt[threadIdx.x]);
   }
+  if (TMA) {
+    // convert the fixed-point box to fp32 in place, then ONE tensor reduce-add moves it into the
+    // ghost-zone mesh (the box never wraps there; cells past the array edge are clipped by the TMA unit)
+    for (int i = threadIdx.x; i < NBOX; i += blockDim.x) {
+      const unsigned h = (hi[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
+      reinterpret_cast<float*>(lo)[i] = fixed_to_float(lo[i], h);
+    }
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) tma_reduce_add_3d(&tm, oz + g.mo, oy + g.mo, ox + g.mo, lo);
+    return;
+  }
   // flush: two box rows per warp pass, one z-pair per lane (8-byte vector reductions when the pair
   // cannot straddle the periodic wrap); the z index of a lane is loop invariant.
   constexpr int HP = BZ / 2;                 // pairs per row (<= 16)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  const int warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
   const int sub = lane / HP, zp = lane - sub * HP;     // sub-row 0/1 (lanes >= 2*HP idle)
   const bool vec = ((oz & 1) == 0) && ((g.nz & 1) == 0) && g.nz >= BZ;
   const int gz0 = wrap_global(oz + 2 * zp, g.nz), gz1 = wrap_global(oz + 2 * zp + 1, g.nz);
   if (sub < 2) {
     for (int r = 2 * warp + sub; r < B * B; r += 2 * nwarp) {
-      const float2 v = reinterpret_cast<const float2*>(box)[r * HP + zp];
-      if (v.x == 0.f && v.y == 0.f) continue;
+      const uint2 l = reinterpret_cast<const uint2*>(lo)[r * HP + zp];
+      const unsigned h = hi[r * HP + zp];
+      if ((l.x | l.y | h) == 0u) continue;
+      const float vx = fixed_to_float(l.x, h & 0xffffu), vy = fixed_to_float(l.y, h >> 16);
       const int lx = r / B, ly = r - lx * B;
       const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
-      float* row = mesh + ((long long)gx * g.ny + gy) * g.nz;
+      float* row = mesh + mesh_index(g, gx, gy, 0);
       if (vec) {
-        red_add_v2(row + gz0, v.x, v.y);
+        red_add_v2(row + gz0, vx, vy);
       } else {
-        if (v.x != 0.f) atomicAdd(row + gz0, v.x);
-        if (v.y != 0.f && 2 * zp + 1 < B) atomicAdd(row + gz1, v.y);
+        if (vx != 0.f) atomicAdd(row + gz0, vx);
+        if (vy != 0.f && 2 * zp + 1 < B) atomicAdd(row + gz1, vy);
       }
     }
   }
@@ -347,31 +524,42 @@ __device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
 }
 
 // ---- read3 + kick + drift + scatter into the next ordering --------------------------------------
-template <bool REL, int TS, int M>
-__global__ void __launch_bounds__(512)
-sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restrict__ svel,
-                const int* __restrict__ start, const float* __restrict__ f0,
+template <bool REL, int TS, int M, bool TMA>
+__global__ void __launch_bounds__(512, 2)
+sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
+                const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ f0,
                 const float* __restrict__ f1, const float* __restrict__ f2, float kick, float drift,
                 long long np, int* __restrict__ cursor, float4* __restrict__ npos,
                 float* __restrict__ nvel, unsigned long long* __restrict__ stats) {
-  constexpr int T = 1 << TS, B = T + 2 * M + 1, NBOX = B * B * B;
-  extern __shared__ __align__(16) float box[];
+  constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
+  constexpr int BZ = TMA ? ((T + MZ + M + 1 + 3) & ~3) : B, NBOX = B * B * BZ;
+  extern __shared__ __align__(128) float box[];        // [3][B][B][BZ]
+  __shared__ __align__(8) unsigned long long mbar;
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
   const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - M;
+  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - MZ;
   const float* fm[3] = {f0, f1, f2};
-  // stage the three force boxes with cp.async (LDGSTS): one box row (B contiguous floats) per
-  // warp pass, no registers held, all rows of a warp in flight at once
-  {
+  int nslow = 0;
+  if (TMA) {
+    // one 4-D tensor load brings the (z, y, x, component) box of all three force meshes
+    if (threadIdx.x == 0) {
+      mbar_init(&mbar, 1);
+      fence_async_smem();
+      mbar_expect_tx(&mbar, 3u * NBOX * (unsigned)sizeof(float));
+      tma_load_4d(box, &tm, oz + g.mo, oy + g.mo, ox + g.mo, 0, &mbar);
+    }
+  } else {
+    // stage the three force boxes with cp.async (LDGSTS): one box row (B contiguous floats) per
+    // warp pass, no registers held, all rows of a warp in flight at once
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     if (lane < B) {
       const int gz = wrap_global(oz + lane, g.nz);
       for (int r = warp; r < B * B; r += nwarp) {
         const int lx = r / B, ly = r - lx * B;
         const int gx = wrap_global(ox + lx, g.nx), gy = wrap_global(oy + ly, g.ny);
-        const long long o = ((long long)gx * g.ny + gy) * g.nz + gz;
+        const long long o = mesh_index(g, gx, gy, gz);
 #pragma unroll
         for (int f = 0; f < 3; ++f) cp_async4(box + f * NBOX + r * B + lane, fm[f] + o);
       }
@@ -387,8 +575,13 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
 #pragma unroll
     for (int f = 0; f < 3; ++f) vin[f] = __ldcs(svel + f * np + q);
   }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
+  if (TMA) {
+    __syncthreads();           // the barrier initialisation by thread 0 is visible
+    mbar_wait(&mbar, 0);
+  } else {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+  }
   for (int qb = beg; qb < end; qb += blockDim.x) {
     const bool valid = q < end;
     const int qn = q + blockDim.x;
@@ -399,41 +592,69 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
 #pragma unroll
       for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
     }
-    int tt = 0;
+    // (1) stencil and destination tile; the slot claim (a global atomic with ~1 us round trip) is
+    //     issued right away so that its latency is covered by the gather below
+    int tt = 0, lx = 0, ly = 0, lz = 0;
+    bool fast = false;
+    FastStencil s;
+    if (valid) {
+      fast = stencil_fast<REL>(g, p, s);
+      lx = local_wrap(s.i0, ox, g.nx); ly = local_wrap(s.j0, oy, g.ny); lz = local_wrap(s.k0, oz, g.nz);
+      fast = fast && (unsigned)lx < (unsigned)(B - 1) && (unsigned)ly < (unsigned)(B - 1) &&
+             (unsigned)lz < (unsigned)(BZ - 1);
+      if (fast) {
+        tt = ((s.i0 >> TS) * g.nty + (s.j0 >> TS)) * g.ntz + (s.k0 >> TS);
+      } else {
+        Cic1 cx, cy, cz;
+        sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+        tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    const unsigned peers = __match_any_sync(0xffffffffu, valid ? tt : (0x40000000 | lane));
+    const int leader = __ffs(peers) - 1;
+    int slot = 0;
+    if (valid && lane == leader) slot = atomicAdd(cursor + tt, __popc(peers));
+    // (2) gather + kick + drift
     float v[3] = {0, 0, 0};
     if (valid) {
-      Cic1 cx, cy, cz;
-      sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-      tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
-      Corners c;
-      make_corners<B>(g, cx, cy, cz, ox, oy, oz, c);
       float acc[3] = {0.f, 0.f, 0.f};
-      if (c.inside) {
-        float mv[3][8], kk[8];
+      if (fast) {
+        const float* b0 = box + (lx * B + ly) * BZ + lz;
+        const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
+        const float kk[8] = {w00 * s.wz0, w00 * s.wz1, w01 * s.wz0, w01 * s.wz1,
+                             w10 * s.wz0, w10 * s.wz1, w11 * s.wz0, w11 * s.wz1};
+        constexpr int off[8] = {0, 1, BZ, BZ + 1, B * BZ, B * BZ + 1, B * BZ + BZ, B * BZ + BZ + 1};
+        float mv[3][8];
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc) {   // all 24 shared-memory gathers issued back to back
-          const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
-          const int o = (c.lx[a] * B + c.ly[b]) * B + c.lz[d];
+        for (int f = 0; f < 3; ++f)
 #pragma unroll
-          for (int f = 0; f < 3; ++f) mv[f][cc] = box[f * NBOX + o];
-          kk[cc] = (c.wx[a] * c.wy[b]) * c.wz[d];
-          if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) kk[cc] = 0.f;
-        }
+          for (int c = 0; c < 8; ++c) mv[f][c] = b0[f * NBOX + off[c]];   // 24 LDS, immediate offsets
 #pragma unroll
-        for (int cc = 0; cc < 8; ++cc)
+        for (int c = 0; c < 8; ++c)
 #pragma unroll
-          for (int f = 0; f < 3; ++f) acc[f] = fmaf(mv[f][cc], kk[cc], acc[f]);
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(mv[f][c], kk[c], acc[f]);
       } else {
+        Cic1 cx, cy, cz;
+        sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+        Corners c;
+        make_corners<B, BZ>(g, cx, cy, cz, ox, oy, oz, c);
 #pragma unroll
         for (int cc = 0; cc < 8; ++cc) {
           const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
           if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
           const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
-          const long long o = ((long long)c.ix[a] * g.ny + c.iy[b]) * g.nz + c.iz[d];
+          if (c.inside) {
+            const int o = (c.lx[a] * B + c.ly[b]) * BZ + c.lz[d];
 #pragma unroll
-          for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
+            for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
+          } else {
+            const long long o = mesh_index(g, c.ix[a], c.iy[b], c.iz[d]);
+#pragma unroll
+            for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
+          }
         }
-        atomicAdd(stats + 1, 1ull);
+        if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
       }
 #pragma unroll
       for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], vin[f]);
@@ -441,7 +662,8 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
       p.y = fmaf(drift, v[1], p.y);
       p.z = fmaf(drift, v[2], p.z);
     }
-    const int slot = warp_claim<true>(cursor, tt, valid);
+    // (3) finish the claim: broadcast the group's base slot, rank within the group
+    slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
     if (valid) {
       npos[slot] = p;
 #pragma unroll
@@ -452,15 +674,18 @@ sim_read_kernel(SimGeom g, const float4* __restrict__ spos, const float* __restr
 #pragma unroll
     for (int f = 0; f < 3; ++f) vin[f] = vn[f];
   }
+  nslow = __reduce_add_sync(0xffffffffu, nslow);
+  if ((threadIdx.x & 31) == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
 }
 
-template <int TS, int M> constexpr int paint_smem() {
+template <int TS, int M, bool TMA> constexpr int paint_smem() {
   constexpr int B = (1 << TS) + 2 * M + 1;
-  return B * B * ((B + 1) & ~1) * (int)sizeof(float);
+  constexpr int NBOX = B * B * (TMA ? (((1 << TS) + kTmaMz + M + 1 + 3) & ~3) : ((B + 1) & ~1));
+  return (NBOX + NBOX / 2) * (int)sizeof(unsigned);   // lo[NBOX] + hi[NBOX / 2]
 }
-template <int TS, int M> constexpr int read_smem() {
+template <int TS, int M, bool TMA> constexpr int read_smem() {
   constexpr int B = (1 << TS) + 2 * M + 1;
-  return 3 * B * B * B * (int)sizeof(float);
+  return 3 * B * B * (TMA ? (((1 << TS) + kTmaMz + M + 1 + 3) & ~3) : B) * (int)sizeof(float);
 }
 
 // (tile shift, margin) instantiations
@@ -476,6 +701,16 @@ template <int TS, int M> constexpr int read_smem() {
     else if (ts == 4 && m == 3) { MACRO(4, 3); }              \
     else { set_error("unsupported tile/margin"); return JPM_ERR_INVALID; } \
   } while (0)
+// the TMA flavour is instantiated for the tile/margin pairs the step driver uses
+#define JPM_SIM_DISPATCH_TMA(ts, m, MACRO)                    \
+  do {                                                        \
+    if (ts == 3 && m == 1) { MACRO(3, 1); }                   \
+    else if (ts == 3 && m == 2) { MACRO(3, 2); }              \
+    else if (ts == 4 && m == 1) { MACRO(4, 1); }              \
+    else if (ts == 4 && m == 2) { MACRO(4, 2); }              \
+    else { set_error("unsupported tile/margin for the TMA path"); return JPM_ERR_INVALID; } \
+  } while (0)
+static bool tma_pair(int ts, int m) { return (ts == 3 || ts == 4) && (m == 1 || m == 2); }
 
 static SimGeom make_geom(int nx, int ny, int nz, int pny, int pnz, int hx, int hy, int tile, int m) {
   SimGeom g;
@@ -487,6 +722,7 @@ static SimGeom make_geom(int nx, int ny, int nz, int pny, int pnz, int hx, int h
   g.ntx = (nx + g.T - 1) / g.T; g.nty = (ny + g.T - 1) / g.T; g.ntz = (nz + g.T - 1) / g.T;
   g.nt = g.ntx * g.nty * g.ntz;
   g.BX = g.BY = g.BZ = g.T + 2 * m + 1;
+  g.msx = (long long)ny * nz; g.msy = nz; g.mb = (long long)nx * ny * nz; g.mo = 0;   // compact mesh
   return g;
 }
 
@@ -510,30 +746,61 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
     JPM_CHECK_ARG(pnx <= 1024 && pny <= 1024 && pnz <= 1024,
                   "relative mode: local particle grid limited to 1024 per axis (packed ids)");
   }
-  if (plan) {
-    int a, b, c;
-    plan_dims(plan, &a, &b, &c);
-    JPM_CHECK_ARG(a == nx && b == ny && c == nz, "plan shape != sim mesh shape");
-  }
+  if (plan) JPM_CHECK_ARG(plan->nx == nx && plan->ny == ny && plan->nz == nz, "plan shape != sim mesh shape");
   jpm_sim* s = new jpm_sim();
   s->plan = plan;
   s->relative = relative;
   s->np = (long long)pnx * pny * pnz;
   s->g = make_geom(nx, ny, nz, pny, pnz, hx, hy, tile, margin);
   const int ts = s->g.tshift, m = margin;
-#define SET_ATTR(TS_, M_)                                                                          \
-  {                                                                                                \
-    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<false, TS_, M_>,                                \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_>())); \
-    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<true, TS_, M_>,                                 \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_>())); \
-    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false, TS_, M_>,                                 \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_>()));  \
-    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_>,                                  \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_>()));  \
+#define SET_ATTR(TS_, M_)                                                                                   \
+  {                                                                                                         \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<false, TS_, M_, false>,                                  \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_, false>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<true, TS_, M_, false>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_, false>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false, TS_, M_, false>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, false>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_, false>,                                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, false>()));  \
   }
   JPM_SIM_DISPATCH(ts, m, SET_ATTR);
 #undef SET_ATTR
+  // TMA path: needs the plan's ghost-zone meshes (jpm_sim_step only) and a supported tile/margin pair
+  memset(&s->tm_rho, 0, sizeof(CUtensorMap));
+  memset(&s->tm_f3, 0, sizeof(CUtensorMap));
+  if (plan && tma_pair(ts, m) && nx >= s->g.T && ny >= s->g.T && nz >= s->g.T) {
+    int32_t rc = plan_enable_padded(plan);
+    if (rc) return rc;
+    if (plan->G > 0) {
+      const int B = s->g.T + 2 * m + 1, BZ = (s->g.T + kTmaMz + m + 1 + 3) & ~3;
+      const unsigned long long d3[3] = {(unsigned long long)plan->nzp, (unsigned long long)plan->nyp,
+                                        (unsigned long long)plan->nxp};
+      const unsigned long long st3[2] = {(unsigned long long)plan->nzp * 4, (unsigned long long)plan->nyp * plan->nzp * 4};
+      const unsigned b3[3] = {(unsigned)BZ, (unsigned)B, (unsigned)B};
+      if ((rc = encode_tensor_map(&s->tm_rho, plan->density_p, 3, d3, st3, b3))) return rc;
+      const unsigned long long d4[4] = {d3[0], d3[1], d3[2], 3ull};
+      const unsigned long long st4[3] = {st3[0], st3[1], (unsigned long long)plan->npad * 4};
+      const unsigned b4[4] = {(unsigned)BZ, (unsigned)B, (unsigned)B, 3u};
+      if ((rc = encode_tensor_map(&s->tm_f3, plan->force3_p, 4, d4, st4, b4))) return rc;
+      s->gp = s->g;
+      s->gp.msx = (long long)plan->nyp * plan->nzp; s->gp.msy = plan->nzp; s->gp.mb = plan->npad; s->gp.mo = plan->G;
+      s->tma = true;
+#define SET_ATTR_TMA(TS_, M_)                                                                              \
+  {                                                                                                         \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<false, TS_, M_, true>,                                   \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_, true>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_paint_kernel<true, TS_, M_, true>,                                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, paint_smem<TS_, M_, true>())); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false, TS_, M_, true>,                                    \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_, true>,                                     \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+  }
+      JPM_SIM_DISPATCH_TMA(ts, m, SET_ATTR_TMA);
+#undef SET_ATTR_TMA
+    }
+  }
   for (int i = 0; i < 2; ++i) {
     JPM_CUDA(cudaMalloc(&s->pos[i], s->np * sizeof(float4)));
     JPM_CUDA(cudaMalloc(&s->vel[i], 3 * s->np * sizeof(float)));
@@ -541,8 +808,8 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   }
   JPM_CUDA(cudaMalloc(&s->count, s->g.nt * sizeof(int)));
   JPM_CUDA(cudaMalloc(&s->cursor, s->g.nt * sizeof(int)));
-  JPM_CUDA(cudaMalloc(&s->stats, 2 * sizeof(unsigned long long)));
-  JPM_CUDA(cudaMemset(s->stats, 0, 2 * sizeof(unsigned long long)));
+  JPM_CUDA(cudaMalloc(&s->stats, 4 * sizeof(unsigned long long)));
+  JPM_CUDA(cudaMemset(s->stats, 0, 4 * sizeof(unsigned long long)));
   JPM_CUDA(cudaMemset(s->count, 0, s->g.nt * sizeof(int)));
   *out = s;
   return JPM_OK;
@@ -604,76 +871,103 @@ extern "C" int32_t jpm_sim_store(jpm_sim* s, void* stream, float* pos, float* ve
   return JPM_OK;
 }
 
-extern "C" int32_t jpm_sim_paint(jpm_sim* s, void* stream, float* mesh) {
-  JPM_CHECK_ARG(s && mesh, "null pointer");
-  JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
-  cudaStream_t st = (cudaStream_t)stream;
+// paint into a compact caller mesh (TMA = false) or into the plan's ghost-zone density (TMA = true)
+static int32_t sim_paint_impl(jpm_sim* s, cudaStream_t st, float* mesh, bool tma) {
   JPM_CUDA(cudaMemsetAsync(s->count, 0, s->g.nt * sizeof(int), st));
   const int ts = s->g.tshift, m = s->g.m;
-#define LAUNCH_PAINT(TS_, M_)                                                                        \
-  {                                                                                                  \
-    if (s->relative)                                                                                 \
-      sim_paint_kernel<true, TS_, M_><<<s->g.nt, 256, paint_smem<TS_, M_>(), st>>>(                  \
-          s->g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                         \
-    else                                                                                             \
-      sim_paint_kernel<false, TS_, M_><<<s->g.nt, 256, paint_smem<TS_, M_>(), st>>>(                 \
-          s->g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                         \
+  const SimGeom& g = tma ? s->gp : s->g;
+#define LAUNCH_PAINT_T(TS_, M_, TMA_)                                                                    \
+  {                                                                                                      \
+    if (s->relative)                                                                                     \
+      sim_paint_kernel<true, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(             \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                     \
+    else                                                                                                 \
+      sim_paint_kernel<false, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(            \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                     \
   }
-  JPM_SIM_DISPATCH(ts, m, LAUNCH_PAINT);
+#define LAUNCH_PAINT(TS_, M_) LAUNCH_PAINT_T(TS_, M_, false)
+#define LAUNCH_PAINT_TMA(TS_, M_) LAUNCH_PAINT_T(TS_, M_, true)
+  if (tma) JPM_SIM_DISPATCH_TMA(ts, m, LAUNCH_PAINT_TMA);
+  else JPM_SIM_DISPATCH(ts, m, LAUNCH_PAINT);
 #undef LAUNCH_PAINT
+#undef LAUNCH_PAINT_TMA
+#undef LAUNCH_PAINT_T
   JPM_LAUNCH_CHECK();
   s->painted = true;
   return JPM_OK;
 }
 
-extern "C" int32_t jpm_sim_read_kick_drift(jpm_sim* s, void* stream, const float* fx, const float* fy,
-                                           const float* fz, float kick_coef, float drift_coef) {
-  JPM_CHECK_ARG(s && fx && fy && fz, "null pointer");
-  JPM_CHECK_ARG(s->painted, "jpm_sim_read_kick_drift must follow jpm_sim_paint (tile occupancy)");
-  cudaStream_t st = (cudaStream_t)stream;
+static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const float* fy, const float* fz,
+                             float kick_coef, float drift_coef, bool tma) {
   const int nxt = s->cur ^ 1;
   sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt);
   JPM_LAUNCH_CHECK();
   const int ts = s->g.tshift, m = s->g.m;
-#define LAUNCH_READ(TS_, M_)                                                                         \
-  {                                                                                                  \
-    if (s->relative)                                                                                 \
-      sim_read_kernel<true, TS_, M_><<<s->g.nt, 512, read_smem<TS_, M_>(), st>>>(                    \
-          s->g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef, drift_coef, \
-          s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                                     \
-    else                                                                                             \
-      sim_read_kernel<false, TS_, M_><<<s->g.nt, 512, read_smem<TS_, M_>(), st>>>(                   \
-          s->g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef, drift_coef, \
-          s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                                     \
+  const SimGeom& g = tma ? s->gp : s->g;
+#define LAUNCH_READ_T(TS_, M_, TMA_)                                                                     \
+  {                                                                                                      \
+    if (s->relative)                                                                                     \
+      sim_read_kernel<true, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(               \
+          s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                             \
+    else                                                                                                 \
+      sim_read_kernel<false, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(              \
+          s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                             \
   }
-  JPM_SIM_DISPATCH(ts, m, LAUNCH_READ);
+#define LAUNCH_READ(TS_, M_) LAUNCH_READ_T(TS_, M_, false)
+#define LAUNCH_READ_TMA(TS_, M_) LAUNCH_READ_T(TS_, M_, true)
+  if (tma) JPM_SIM_DISPATCH_TMA(ts, m, LAUNCH_READ_TMA);
+  else JPM_SIM_DISPATCH(ts, m, LAUNCH_READ);
 #undef LAUNCH_READ
+#undef LAUNCH_READ_TMA
+#undef LAUNCH_READ_T
   JPM_LAUNCH_CHECK();
   s->cur = nxt;
   s->painted = false;
   return JPM_OK;
 }
 
-extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float drift_coef) {
-  JPM_CHECK_ARG(s && s->plan, "sim has no FFT plan attached");
-  cudaStream_t st = (cudaStream_t)stream;
-  float* rho = plan_density(s->plan);
-  float* f3 = plan_force3(s->plan);
-  const long long nc = plan_ncell(s->plan);
-  JPM_CUDA(cudaMemsetAsync(rho, 0, nc * sizeof(float), st));
-  int32_t rc;
-  if ((rc = jpm_sim_paint(s, stream, rho))) return rc;
-  if ((rc = jpm_density_to_force_meshes(s->plan, stream, rho, f3, 0.f, nullptr, 0, 0.f))) return rc;
-  return jpm_sim_read_kick_drift(s, stream, f3, f3 + nc, f3 + 2 * nc, kick_coef, drift_coef);
+extern "C" int32_t jpm_sim_paint(jpm_sim* s, void* stream, float* mesh) {
+  JPM_CHECK_ARG(s && mesh, "null pointer");
+  JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
+  return sim_paint_impl(s, (cudaStream_t)stream, mesh, false);
 }
 
-extern "C" int32_t jpm_sim_stats_host(jpm_sim* s, void* stream, int64_t* out2_host) {
-  JPM_CHECK_ARG(s && out2_host, "null pointer");
+extern "C" int32_t jpm_sim_read_kick_drift(jpm_sim* s, void* stream, const float* fx, const float* fy,
+                                           const float* fz, float kick_coef, float drift_coef) {
+  JPM_CHECK_ARG(s && fx && fy && fz, "null pointer");
+  JPM_CHECK_ARG(s->painted, "jpm_sim_read_kick_drift must follow jpm_sim_paint (tile occupancy)");
+  return sim_read_impl(s, (cudaStream_t)stream, fx, fy, fz, kick_coef, drift_coef, false);
+}
+
+extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float drift_coef) {
+  JPM_CHECK_ARG(s && s->plan, "sim has no FFT plan attached");
+  JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
   cudaStream_t st = (cudaStream_t)stream;
-  unsigned long long h[2];
+  jpm_plan* p = s->plan;
+  int32_t rc;
+  if (s->tma) {
+    // ghost-zone meshes: TMA reduce-add paint -> ghost fold -> R2C -> k-space -> 3x C2R -> ghost fill -> TMA read
+    JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+    if ((rc = sim_paint_impl(s, st, p->density_p, true))) return rc;
+    if ((rc = plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f))) return rc;
+    return sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
+                         drift_coef, true);
+  }
+  JPM_CUDA(cudaMemsetAsync(p->density, 0, p->ncell * sizeof(float), st));
+  if ((rc = sim_paint_impl(s, st, p->density, false))) return rc;
+  if ((rc = jpm_density_to_force_meshes(p, stream, p->density, p->force3, 0.f, nullptr, 0, 0.f))) return rc;
+  return sim_read_impl(s, st, p->force3, p->force3 + p->ncell, p->force3 + 2 * p->ncell, kick_coef, drift_coef,
+                       false);
+}
+
+extern "C" int32_t jpm_sim_stats_host(jpm_sim* s, void* stream, int64_t* out4_host) {
+  JPM_CHECK_ARG(s && out4_host, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  unsigned long long h[4];
   JPM_CUDA(cudaMemcpyAsync(h, s->stats, sizeof(h), cudaMemcpyDeviceToHost, st));
   JPM_CUDA(cudaStreamSynchronize(st));
-  out2_host[0] = (int64_t)h[0];
-  out2_host[1] = (int64_t)h[1];
+  for (int i = 0; i < 4; ++i) out4_host[i] = (int64_t)h[i];
   return JPM_OK;
 }

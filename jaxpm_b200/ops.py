@@ -320,6 +320,6 @@ class Sim:
         call("jpm_sim_step", self.handle, stream(), float(kick), float(drift))
 
     def fallback_counts(self):
-        out = (C.c_int64 * 2)()
+        out = (C.c_int64 * 4)()
         call("jpm_sim_stats_host", self.handle, stream(), out)
-        return int(out[0]), int(out[1])
+        return tuple(int(v) for v in out)

@@ -280,12 +280,13 @@ def test_sim_load_paint_store(cuda, shape, tile, margin, sigma, relative):
 
 
 @pytest.mark.parametrize("relative", [False, True])
-def test_sim_step_matches_order_preserving_path(cuda, relative):
+@pytest.mark.parametrize("shape", [(32, 32, 32), (32, 48, 24)])
+def test_sim_step_matches_order_preserving_path(cuda, relative, shape):
     """K resident steps == K order-preserving steps == oracle, including particles that leave
-    their box (margin 0 forces the global-memory fallback)."""
+    their box (margin 0 forces the global-memory fallback).  tile/margin pairs (8,2), (16,1) run the
+    TMA ghost-zone path of jpm_sim_step, (8,0) the compact-mesh path."""
     from jaxpm_b200.cosmology import Planck15
     from jaxpm_b200.ode import nbody_kick_drift
-    shape = (32, 32, 32)
     grid, disp = displaced(shape, 1.0)
     x = disp if relative else grid + disp
     vel = (0.3 * np.random.default_rng(9).standard_normal(x.shape)).astype(np.float32)

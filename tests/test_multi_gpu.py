@@ -46,8 +46,8 @@ def _worker(rank, world, port, pdims, shape, halo):
         xk = fft3d(blk(mesh), sh)
         assert rel(ifft3d(xk, sh), blk(mesh)) < 1e-5
         # forces
-        f_ref = pm_forces(disp, paint_absolute_pos=False)
-        f = pm_forces(blk(disp), paint_absolute_pos=False, halo_size=halo, sharding=sh)
+        f_ref = pm_forces(disp, mesh_shape=shape, paint_absolute_pos=False)
+        f = pm_forces(blk(disp), mesh_shape=shape, paint_absolute_pos=False, halo_size=halo, sharding=sh)
         assert rel(f, blk(f_ref)) < 1e-5
         # LPT (order 2) and a short drift-kick run
         cosmo = Planck15()

@@ -25,14 +25,14 @@ if [[ $STAGES == *bench* ]]; then
   cat $OUT/bench_reference.json
 fi
 if [[ $STAGES == *launches* ]]; then
-  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv \
-      --log-file $OUT/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/launches_run.log 2>&1
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv \
+      --log-file $OUT/launches.csv python bench.py --no-cpu --e2e-steps 1 > $OUT/launches_run.log 2>&1
   echo "launches rc=$?"
 fi
 if [[ $STAGES == *full* ]]; then
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'sim_paint_kernel|sim_read_kernel|kspace_kernel' -s 12 -c 3 -f -o $OUT/prof_sim \
-      python bench.py --steps 2 --warmup 3 --no-cpu --e2e-steps 1 > $OUT/full_run.log 2>&1
+      -k regex:'sim_paint_kernel|sim_read_kernel|kspace_kernel' -s 106 -c 3 -f -o $OUT/prof_sim \
+      python bench.py --no-cpu --e2e-steps 1 > $OUT/full_run.log 2>&1
   echo "full rc=$?"
 fi
 ls -la $OUT
