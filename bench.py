@@ -217,50 +217,42 @@ def run_gpu(args):
     t_dev = e0.elapsed_time(e1) * 1e-3
     value = npart * K / t_dev
 
-    # ---- per-kernel durations (CUDA events, live, on the evolved particle set) -----------------
+    # ---- per-stage durations of the SAME step (CUDA events on the launching stream, recorded inside
+    #      jpm_sim_step at every stage boundary; 5 more steps on the evolved particle set) -------------
     peak, peak_kind = _peaks()
-    mesh = torch.zeros(shape, dtype=torch.float32, device=dev)
-    f3 = torch.empty((3, *shape), dtype=torch.float32, device=dev)
-    spec = torch.empty(plan.spec_shape, dtype=torch.complex64, device=dev)
-    spec3 = torch.empty((3, *plan.spec_shape), dtype=torch.complex64, device=dev)
-    scratch_p, scratch_v = disp.clone(), vel.clone()
-
-    def k_paint():
-        mesh.zero_()
-        sim.paint_(mesh)
-
-    def k_paint_direct():
-        mesh.zero_()
-        ops.cic_paint_dx_(mesh, disp)
-
-    t_zero = time_kernel(lambda: mesh.zero_())
-    t_paint = time_kernel(k_paint) - t_zero
-    t_paint_direct = time_kernel(k_paint_direct) - t_zero
-    ops.call("jpm_fft3d_r2c", plan.handle, ops.stream(), ops.ptr(mesh), ops.ptr(spec))
-    t_r2c = time_kernel(lambda: ops.call("jpm_fft3d_r2c", plan.handle, ops.stream(), ops.ptr(mesh), ops.ptr(spec)))
-    t_ksp = time_kernel(lambda: ops.call("jpm_greens_grad_c64", plan.handle, ops.stream(), ops.ptr(spec),
-                                         ops.ptr(spec3), 1.0 / npart, 0.0, None, 0, 0.0))
-    t_c2r = time_kernel(lambda: ops.call("jpm_ifft3d_c2r", plan.handle, ops.stream(), ops.ptr(spec3), ops.ptr(f3), 3))
-    t_read_direct = time_kernel(lambda: ops.read3_kick_drift_(f3, scratch_p, scratch_v, 0.0, 0.0, True))
-
-    def k_read():
-        sim.paint_(mesh)            # supplies the tile occupancy the read pass consumes
-        sim.read_kick_drift(f3, 0.0, 0.0)
-
-    t_read = time_kernel(k_read) - t_paint
     nc = npart
-    kernels = {
-        "sim_paint": {"s": t_paint, "alg_bytes": 12 * npart + 4 * nc},
-        "direct_paint_dx(order-preserving)": {"s": t_paint_direct, "alg_bytes": 12 * npart + 4 * nc},
-        "mesh_memset": {"s": t_zero, "alg_bytes": 4 * nc},
-        "fft_r2c(cuFFT)": {"s": t_r2c, "alg_bytes": 8 * nc},
-        "greens_grad": {"s": t_ksp, "alg_bytes": 16 * nc},
-        "ifft_c2r_x3(cuFFT)": {"s": t_c2r, "alg_bytes": 24 * nc},
-        "sim_read3_kick_drift": {"s": t_read, "alg_bytes": 48 * npart + 12 * nc},
-        "direct_read3_kick_drift(order-preserving)": {"s": t_read_direct, "alg_bytes": 48 * npart + 12 * nc},
+    alg = {  # algorithmic bytes per launch
+        "mesh_memset": 4 * nc, "sim_paint": 12 * npart + 4 * nc,
+        "tile_scan+sim_read3_kick_drift": 48 * npart + 12 * nc,
+        "fft_z_r2c+ghost_fold": 8 * nc, "fft_y_fwd": 8 * nc, "fft_x_fwd+greens_grad+ifft_x_x3": 16 * nc,
+        "ifft_y_x3": 24 * nc, "ifft_z_c2r_x3+ghost_fill": 24 * nc,
+        "ghost_fold": 0, "ghost_fill": 0, "fft_r2c(cuFFT)": 8 * nc, "greens_grad": 16 * nc,
+        "ifft_c2r_x3(cuFFT)": 24 * nc,
     }
+    acc, reps = {}, 5
+    for _ in range(reps):
+        for name, ms in sim.step_profile(0.0, 0.0):
+            acc[name] = acc.get(name, 0.0) + ms / reps
+    kernels = {n: {"s": ms * 1e-3, "alg_bytes": alg.get(n, 0)} for n, ms in acc.items()}
+    if args.direct:
+        # the order-preserving kernels of the functional API on the same particle set, for comparison
+        mesh = torch.zeros(shape, dtype=torch.float32, device=dev)
+        f3 = torch.zeros((3, *shape), dtype=torch.float32, device=dev)
+        scratch_p, scratch_v = disp.clone(), vel.clone()
+        t_zero = time_kernel(lambda: mesh.zero_())
+
+        def k_paint_direct():
+            mesh.zero_()
+            ops.cic_paint_dx_(mesh, disp)
+
+        kernels["direct_paint_dx(order-preserving)"] = {"s": time_kernel(k_paint_direct) - t_zero,
+                                                        "alg_bytes": 12 * npart + 4 * nc}
+        kernels["direct_read3_kick_drift(order-preserving)"] = {
+            "s": time_kernel(lambda: ops.read3_kick_drift_(f3, scratch_p, scratch_v, 0.0, 0.0, True)),
+            "alg_bytes": 48 * npart + 12 * nc}
+        del mesh, f3, scratch_p, scratch_v
     for v in kernels.values():
-        v["GBps"] = v["alg_bytes"] / v["s"] / 1e9
+        v["GBps"] = v["alg_bytes"] / v["s"] / 1e9 if v["s"] > 0 else 0.0
         v["frac"] = v["GBps"] / peak
     own = {n: v for n, v in kernels.items() if "cuFFT" not in n and n != "mesh_memset" and "direct" not in n}
     dom_name = max(own, key=lambda n: own[n]["s"])
@@ -272,7 +264,6 @@ def run_gpu(args):
                 "step_frac": step_alg_bytes * K / t_dev / 1e9 / peak,
                 "kernels": {n: {"ms": round(v["s"] * 1e3, 4), "GBps": round(v["GBps"], 1),
                                 "frac": round(v["frac"], 4)} for n, v in kernels.items()}}
-    del mesh, f3, spec, spec3, scratch_p, scratch_v
     torch.cuda.empty_cache()
 
     # ---- end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step) -
@@ -333,6 +324,8 @@ def main():
     ap.add_argument("--halo", type=int, default=64, help="halo width of the sharded path (N > 1)")
     ap.add_argument("--no-resident", action="store_true", help="N > 1: order-preserving kernels")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--direct", action="store_true",
+                    help="also time the order-preserving paint/read kernels of the functional API")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "b200":
         args.warmup = 3

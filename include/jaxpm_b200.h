@@ -191,6 +191,14 @@ int32_t jpm_density_to_force_meshes(jpm_plan* plan, void* stream, const float* d
                                     float* force3, float r_split, const float* filter_tab,
                                     int32_t n_tab, float filter_kmax);
 
+/* Same result as jpm_density_to_force_meshes, computed on the plan's ghost-zone meshes by the fused
+ * five-pass FFT chain of csrc/pmfft.cu (power-of-two shapes: R2C along z, FFT along y, FFT along x with
+ * the Green's function x gradient and the three inverse x transforms in the same kernel, inverse y, C2R
+ * along z) or, for other shapes, by cuFFT on the padded arrays.  Replaces jaxpm/pm.py:41-56. */
+int32_t jpm_density_to_force_meshes_fused(jpm_plan* plan, void* stream, const float* density,
+                                          float* force3, float r_split, const float* filter_tab,
+                                          int32_t n_tab, float filter_kmax);
+
 /* One full PM step on resident particles (single GPU, absolute or relative positions):
  * memset mesh -> paint -> R2C -> greens-grad -> 3x C2R -> read3+kick+drift (kick-drift
  * form, in place on pos/vel).  jaxpm/ode.py:100-117 + :91-98 around jaxpm/pm.py:12-58. */
@@ -229,6 +237,12 @@ int32_t jpm_sim_read_kick_drift(jpm_sim* sim, void* stream, const float* fx, con
                                 const float* fz, float kick_coef, float drift_coef);
 /* One PM step on the resident state: memset, paint, R2C, greens-grad, 3x C2R, read+kick+drift. */
 int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_coef);
+/* One jpm_sim_step with a CUDA event recorded on `stream` at every stage boundary (memset, paint, each
+ * FFT pass, read).  Synchronises the stream; fills names_out[i] (static strings) and ms_out[i] for the
+ * *n_out <= cap stages.  This is how bench.py measures the per-kernel roofline live. */
+int32_t jpm_sim_step_profile(jpm_sim* sim, void* stream, float kick_coef, float drift_coef,
+                             const char** names_out, float* ms_out, int32_t cap, int32_t* n_out);
+
 /* out4_host[0..1] = particles that took the global-memory fallback (drifted beyond the margin) in
  * paint / read so far; [2..3] = particles that took the generic (periodic-wrap) stencil inside the
  * shared-memory box in paint / read.  Synchronises the stream. */

@@ -39,6 +39,7 @@ SIGNATURES = {
     "jpm_lpt2_source_f32": ([vp, vp, vp, i64], i32),
     "jpm_kfilter_logtab_c64": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),
     "jpm_density_to_force_meshes": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
+    "jpm_density_to_force_meshes_fused": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_pm_step_f32": ([vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_pm_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_sim_create": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
@@ -48,6 +49,7 @@ SIGNATURES = {
     "jpm_sim_paint": ([vp, vp, vp], i32),
     "jpm_sim_read_kick_drift": ([vp, vp, vp, vp, vp, f32, f32], i32),
     "jpm_sim_step": ([vp, vp, f32, f32], i32),
+    "jpm_sim_step_profile": ([vp, vp, f32, f32, C.POINTER(C.c_char_p), C.POINTER(f32), i32, C.POINTER(i32)], i32),
     "jpm_sim_stats_host": ([vp, vp, C.POINTER(i64)], i32),
     "jpm_kernel_launch_count": ([], i64),
     "jpm_axpby_f32": ([vp, vp, f32, vp, f32, vp, i64], i32),

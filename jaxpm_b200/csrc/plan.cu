@@ -4,6 +4,7 @@
 //              jaxpm/pm.py:12-58 (pm_forces), :88-124 (2LPT source), jaxpm/ode.py:91-117
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
@@ -259,6 +260,14 @@ int32_t plan_enable_padded(jpm_plan* p) {
   JPM_CUDA(cudaMalloc(&p->density_p, p->npad * sizeof(float)));
   JPM_CUDA(cudaMalloc(&p->force3_p, 3 * p->npad * sizeof(float)));
   JPM_CUDA(cudaMemset(p->force3_p, 0, 3 * p->npad * sizeof(float)));
+  p->G = G;
+  // the hand-written chain when the shape allows it (JPM_PMFFT=0 keeps cuFFT for A/B comparisons)
+  const char* env = getenv("JPM_PMFFT");
+  if (!(env && env[0] == '0')) {
+    int32_t rc = pmfft_enable(p);
+    if (rc) return rc;
+    if (p->fft_a) return JPM_OK;
+  }
   int n[3] = {p->nx, p->ny, p->nz};
   int remb[3] = {p->nxp, p->nyp, p->nzp};      // real side: embedded in the padded array
   int cemb[3] = {p->nx, p->ny, p->nzh};        // spectrum side: compact
@@ -281,29 +290,76 @@ int32_t plan_enable_padded(jpm_plan* p) {
   }
   JPM_CUFFT(cufftSetWorkArea(p->r2c_p, p->work));
   JPM_CUFFT(cufftSetWorkArea(p->c2r3_p, p->work));
-  p->G = G;
   return JPM_OK;
 }
 
 int32_t plan_padded_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
                            float filter_kmax) {
   JPM_CHECK_ARG(p->G > 0, "padded meshes not enabled");
+  if (p->fft_a) return pmfft_forces(p, st, r_split, filter_tab, n_tab, filter_kmax);
   const long long off = ((long long)p->G * p->nyp + p->G) * p->nzp + p->G;   // interior origin
   int32_t rc;
   if ((rc = ghost_pass<true>(p, st, p->density_p, 1))) return rc;
+  if (p->timer) p->timer->mark(st, "ghost_fold");
   JPM_CUFFT(cufftSetStream(p->r2c_p, st));
   JPM_CUFFT(cufftExecR2C(p->r2c_p, p->density_p + off, (cufftComplex*)p->spec));
+  if (p->timer) p->timer->mark(st, "fft_r2c(cuFFT)");
   if ((rc = jpm_greens_grad_c64(p, st, p->spec, p->spec3, 1.0f / (float)p->ncell, r_split, filter_tab, n_tab,
                                 filter_kmax)))
     return rc;
+  if (p->timer) p->timer->mark(st, "greens_grad");
   JPM_CUFFT(cufftSetStream(p->c2r3_p, st));
   JPM_CUFFT(cufftExecC2R(p->c2r3_p, (cufftComplex*)p->spec3, p->force3_p + off));
-  return ghost_pass<false>(p, st, p->force3_p, 3);
+  if (p->timer) p->timer->mark(st, "ifft_c2r_x3(cuFFT)");
+  rc = ghost_pass<false>(p, st, p->force3_p, 3);
+  if (p->timer) p->timer->mark(st, "ghost_fill");
+  return rc;
+}
+
+// compact [nx][ny][nz] <-> interior of the padded [nxp][nyp][nzp] array (float4 along z)
+template <bool TO_PADDED>
+__global__ void __launch_bounds__(256)
+pad_copy_kernel(float* __restrict__ padded, float* __restrict__ compact, int nx, int ny, int nz4, int nyp, int nzp,
+                int G, long long pbatch, long long cbatch) {
+  const long long total = (long long)nx * ny * nz4;
+  float* pp = padded + blockIdx.y * pbatch;
+  float* cc = compact + blockIdx.y * cbatch;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int k4 = (int)(t % nz4);
+    const long long r = t / nz4;
+    const int j = (int)(r % ny), i = (int)(r / ny);
+    float4* a = reinterpret_cast<float4*>(pp + ((long long)(i + G) * nyp + (j + G)) * nzp + G) + k4;
+    float4* b = reinterpret_cast<float4*>(cc + ((long long)i * ny + j) * (4 * nz4)) + k4;
+    if (TO_PADDED) *a = *b;
+    else *b = *a;
+  }
 }
 
 }  // namespace jpm
 
 using namespace jpm;
+
+extern "C" int32_t jpm_density_to_force_meshes_fused(jpm_plan* p, void* stream, const float* density,
+                                                     float* force3, float r_split, const float* filter_tab,
+                                                     int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(p && density && force3, "null pointer");
+  JPM_CHECK_ARG(!filter_tab || (n_tab >= 2 && filter_kmax > 0.f), "bad filter table");
+  int32_t rc = plan_enable_padded(p);
+  if (rc) return rc;
+  JPM_CHECK_ARG(p->G > 0, "shape not supported by the ghost-zone path (nz % 4 != 0 or too large)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = p->ncell / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
+  JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+  pad_copy_kernel<true><<<dim3(blocks, 1), 256, 0, st>>>(p->density_p, const_cast<float*>(density), p->nx, p->ny,
+                                                        p->nz / 4, p->nyp, p->nzp, p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  if ((rc = plan_padded_forces(p, st, r_split, filter_tab, n_tab, filter_kmax))) return rc;
+  pad_copy_kernel<false><<<dim3(blocks, 3), 256, 0, st>>>(p->force3_p, force3, p->nx, p->ny, p->nz / 4, p->nyp,
+                                                         p->nzp, p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
 
 extern "C" int32_t jpm_plan_create(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz) {
   JPM_CHECK_ARG(out, "null plan pointer");
@@ -352,6 +408,7 @@ extern "C" int32_t jpm_plan_destroy(jpm_plan* p) {
   if (p->c2r3) cufftDestroy(p->c2r3);
   if (p->r2c_p) cufftDestroy(p->r2c_p);
   if (p->c2r3_p) cufftDestroy(p->c2r3_p);
+  pmfft_destroy(p);
   if (p->density_p) cudaFree(p->density_p);
   if (p->force3_p) cudaFree(p->force3_p);
   void* bufs[] = {p->work, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->density, p->spec, p->spec3, p->force3};
@@ -440,11 +497,16 @@ extern "C" int32_t jpm_density_to_force_meshes(jpm_plan* p, void* stream, const 
                                                int32_t n_tab, float filter_kmax) {
   JPM_CHECK_ARG(p && density && force3, "null pointer");
   int32_t rc;
+  cudaStream_t st = (cudaStream_t)stream;
   if ((rc = jpm_fft3d_r2c(p, stream, density, p->spec))) return rc;
+  if (p->timer) p->timer->mark(st, "fft_r2c(cuFFT)");
   if ((rc = jpm_greens_grad_c64(p, stream, p->spec, p->spec3, 1.0f / (float)p->ncell, r_split,
                                 filter_tab, n_tab, filter_kmax)))
     return rc;
-  return jpm_ifft3d_c2r(p, stream, p->spec3, force3, 3);
+  if (p->timer) p->timer->mark(st, "greens_grad");
+  rc = jpm_ifft3d_c2r(p, stream, p->spec3, force3, 3);
+  if (p->timer) p->timer->mark(st, "ifft_c2r_x3(cuFFT)");
+  return rc;
 }
 
 extern "C" int32_t jpm_pm_step_f32(jpm_plan* p, void* stream, float* pos, float* vel, float kick_coef,

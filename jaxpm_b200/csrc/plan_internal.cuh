@@ -5,7 +5,23 @@
 
 #include "common.cuh"
 
+// Optional per-stage CUDA-event timer of the composed step (jpm_sim_step_profile): every stage boundary
+// records an event on the launching stream; read back after a stream synchronise.
+struct StageTimer {
+  static constexpr int kMax = 24;
+  cudaEvent_t ev[kMax];
+  const char* name[kMax];
+  int n = 0;
+  void mark(cudaStream_t st, const char* label) {
+    if (n < kMax) {
+      cudaEventRecord(ev[n], st);
+      name[n++] = label;
+    }
+  }
+};
+
 struct jpm_plan {
+  StageTimer* timer = nullptr;
   int nx, ny, nz, nzh;
   long long ncell, nspec;
   cufftHandle r2c = 0, c2r1 = 0, c2r3 = 0;
@@ -29,6 +45,11 @@ struct jpm_plan {
   float* density_p = nullptr; // [nxp][nyp][nzp]
   float* force3_p = nullptr;  // [3][nxp][nyp][nzp]
   cufftHandle r2c_p = 0, c2r3_p = 0;
+  // ---- pmfft (csrc/pmfft.cu): hand-written fused FFT chain on the padded meshes, power-of-two shapes --
+  int nzc = 0;                // pitch (complex) of a spectrum row: nzh rounded up to a multiple of 8
+  float2* fft_a = nullptr;    // [nx][ny][nzc]      z- then y-transformed density
+  float2* fft_b3 = nullptr;   // [3][nx][ny][nzc]   x-inverse-transformed force spectra
+  float2 *tw_x = nullptr, *tw_y = nullptr, *tw_zh = nullptr, *tw_zfull = nullptr;   // exp(-2 pi i k / n) tables
 };
 
 namespace jpm {
@@ -39,6 +60,11 @@ int32_t plan_enable_padded(jpm_plan* p);
 // density_p (painted, ghosts not yet folded) -> force3_p (ghosts filled), all on `stream`.
 int32_t plan_padded_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab,
                            int n_tab, float filter_kmax);
+// pmfft: enable (allocates; no-op when the shape is unsupported), run density_p -> force3_p, free.
+int32_t pmfft_enable(jpm_plan* p);
+int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
+                     float filter_kmax);
+void pmfft_destroy(jpm_plan* p);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
 // dims/strides innermost first, rank 3 or 4, fp32, no swizzle/interleave, OOB -> zero fill.
 int32_t encode_tensor_map(CUtensorMap* out, float* base, int rank, const unsigned long long* dims,

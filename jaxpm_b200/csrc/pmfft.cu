@@ -1,0 +1,592 @@
+// pmfft — the fused k-space chain of the PM force evaluation as five hand-written FFT passes
+// (replaces cuFFT R2C + the Green's/gradient pass + 3x cuFFT C2R for power-of-two meshes):
+//
+//   Z-fwd   density_p rows (ghost zones folded on the fly)  --R2C along z-->  A[x][y][kz]
+//   Y-fwd   A columns along y, in place
+//   X-fused A columns along x: forward FFT, delta_k stays in REGISTERS, times
+//           i a_d(k) / k^2 * G(k) * norm for d = x, y, z, three inverse FFTs along x  -->  B3[d][x][y][kz]
+//   Y-inv   B3 columns along y, in place (3 components)
+//   Z-inv   B3 rows --C2R along z--> force3_p rows, ghost zones filled on the fly
+//
+//   reference: jaxpm/pm.py:41-56 (fft3d, invlaplace * longrange, -gradient_kernel, ifft3d x3),
+//              jaxpm/kernels.py:10-23,41-115, jaxpm/distributed.py:37-42.
+//
+// HBM traffic per force evaluation (Nc cells, fp32): 4+4, 4+4, 4+12, 12+12, 12+12 = 80 B/cell against
+// 8+16+24 = 48 B/cell algorithmic and ~130 B/cell for cuFFT (3 passes per 3-D transform) + the k-space pass.
+//
+// Each 1-D FFT is a Stockham autosort transform in shared memory, radix 8/4, twiddles from a table
+// computed in double precision.  Column passes keep a [N][C] tile (C consecutive kz = one 128-byte or
+// 64-byte segment per row, so every global access is a full-sector segment); the first stage loads
+// straight from global memory and the last stage stores straight to it, so an N = 512 transform makes
+// 4 shared-memory passes instead of 8.  Row passes (z) stage 16 rows with a pitch of N/2+1 complex, lanes
+// across rows: conflict-free for every stage permutation.
+#include <cmath>
+#include <vector>
+
+#include "plan_internal.cuh"
+
+namespace jpm {
+namespace fft {
+
+// ---- complex helpers --------------------------------------------------------------------------
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+// multiply by -i (forward transforms) or +i (inverse)
+template <bool INV>
+__device__ __forceinline__ float2 mul_mi(float2 a) {
+  return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x);
+}
+
+template <bool INV>
+__device__ __forceinline__ void dft4(float2& v0, float2& v1, float2& v2, float2& v3) {
+  const float2 t0 = cadd(v0, v2), t1 = csub(v0, v2), t2 = cadd(v1, v3), t3 = mul_mi<INV>(csub(v1, v3));
+  v0 = cadd(t0, t2); v1 = cadd(t1, t3); v2 = csub(t0, t2); v3 = csub(t1, t3);
+}
+
+template <int R, bool INV>
+__device__ __forceinline__ void dft(float2* v) {
+  if (R == 2) {
+    const float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b); v[1] = csub(a, b);
+  } else if (R == 4) {
+    dft4<INV>(v[0], v[1], v[2], v[3]);
+  } else {  // R == 8
+    float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+    dft4<INV>(e0, e1, e2, e3);
+    dft4<INV>(o0, o1, o2, o3);
+    const float h = 0.70710678118654752440f;
+    // o1 *= W8, o2 *= -+i, o3 *= W8^3
+    o1 = INV ? make_float2((o1.x - o1.y) * h, (o1.x + o1.y) * h) : make_float2((o1.x + o1.y) * h, (o1.y - o1.x) * h);
+    o2 = mul_mi<INV>(o2);
+    o3 = INV ? make_float2((-o3.x - o3.y) * h, (o3.x - o3.y) * h) : make_float2((o3.y - o3.x) * h, (-o3.x - o3.y) * h);
+    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+  }
+}
+
+// ---- radix schedule ---------------------------------------------------------------------------
+__host__ __device__ constexpr int pick_radix(int rem) { return rem == 16 ? 4 : (rem >= 8 ? 8 : rem); }
+__host__ __device__ constexpr int radix_count(int N) {
+  int c = 0, ns = 1;
+  while (ns < N) { ns *= pick_radix(N / ns); ++c; }
+  return c;
+}
+__host__ __device__ constexpr int radix_fwd(int N, int i) {
+  int ns = 1, r = 1;
+  for (int s = 0; s <= i; ++s) { r = pick_radix(N / ns); ns *= r; }
+  return r;
+}
+// stage i of the schedule, forward order or reversed
+__host__ __device__ constexpr int radix_at(int N, int i, bool rev) {
+  return rev ? radix_fwd(N, radix_count(N) - 1 - i) : radix_fwd(N, i);
+}
+__host__ __device__ constexpr int ns_at(int N, int i, bool rev) {
+  int ns = 1;
+  for (int s = 0; s < i; ++s) ns *= radix_at(N, s, rev);
+  return ns;
+}
+
+// ---- shared-memory layouts --------------------------------------------------------------------
+template <int C>
+struct LayCols {   // element n of column c
+  __device__ __forceinline__ static int idx(int n, int c) { return n * C + c; }
+};
+template <int N>
+struct LayRows {   // element n of row c, pitch N + 1 (odd number of complex words: conflict-free across rows)
+  __device__ __forceinline__ static int idx(int n, int c) { return c * (N + 1) + n; }
+};
+
+template <class LAY>
+struct SmemIO {
+  static constexpr bool kSmem = true;
+  float2* s;
+  __device__ __forceinline__ float2 operator()(int n, int c) const { return s[LAY::idx(n, c)]; }
+  __device__ __forceinline__ void operator()(int n, int c, float2 v) const { s[LAY::idx(n, c)] = v; }
+};
+struct GlobalIO {   // element (n, c) at base[n * stride + c]
+  static constexpr bool kSmem = false;
+  float2* base;
+  long long stride;
+  __device__ __forceinline__ float2 operator()(int n, int c) const { return __ldcs(base + n * stride + c); }
+  __device__ __forceinline__ void operator()(int n, int c, float2 v) const { __stcs(base + n * stride + c, v); }
+};
+// keeps the values in the caller's registers (X-fused pass): slot = task-local index
+struct NullIO {
+  static constexpr bool kSmem = false;
+};
+
+// One Stockham stage over the tile: N points, radix R, Ns = product of the radices already applied.
+// Tasks (j, c): butterfly j of column c; task t -> c = t % C, j = t / C; TPT tasks per thread.
+// Inputs n = j + r N/R, outputs n = (j / Ns) Ns R + j % Ns + r Ns.
+template <int N, int Ns, int R, int C, int NT, bool INV, bool KEEP_IN, bool KEEP_OUT, class LD, class ST>
+__device__ __forceinline__ void stage(LD ld, ST st, const float2* __restrict__ tw, int ncol,
+                                      float2 (*keep)[8]) {
+  constexpr int TASKS = (N / R) * C;
+  constexpr int TPT = (TASKS + NT - 1) / NT;
+  float2 v[TPT][R];
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    const int task = threadIdx.x + i * NT;
+    const int c = task % C, j = task / C;
+    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if constexpr (KEEP_IN) v[i][r] = keep[i][r];
+        else v[i][r] = ld(j + r * (N / R), c);
+      }
+    }
+  }
+  if constexpr (!KEEP_IN && LD::kSmem) __syncthreads();
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    const int task = threadIdx.x + i * NT;
+    const int c = task % C, j = task / C;
+    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+      const int k = j & (Ns - 1);
+      if (Ns > 1) {
+        const int t = k * (N / (Ns * R));
+#pragma unroll
+        for (int r = 1; r < R; ++r) {
+          float2 w = tw[t * r];
+          if (INV) w.y = -w.y;
+          v[i][r] = cmul(v[i][r], w);
+        }
+      }
+      dft<R, INV>(v[i]);
+      const int j0 = (j - k) * R + k;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if constexpr (KEEP_OUT) keep[i][r] = v[i][r];
+        else st(j0 + r * Ns, c, v[i][r]);
+      }
+    }
+  }
+  if constexpr (!KEEP_OUT && ST::kSmem) __syncthreads();
+}
+
+// All stages of an N-point transform.  Stage 0 reads through `ld0` (or the kept registers), the last
+// stage writes through `stl` (or into the kept registers); everything in between lives in `s`.
+template <int N, int C, int NT, bool INV, bool REV, bool KEEP_IN, bool KEEP_OUT, class LAY, int I, class LD0, class STL>
+__device__ __forceinline__ void run_stages(float2* s, const float2* __restrict__ tw, int ncol, LD0 ld0, STL stl,
+                                           float2 (*keep)[8]) {
+  constexpr int L = radix_count(N);
+  if constexpr (I < L) {
+    constexpr int R = radix_at(N, I, REV), Ns = ns_at(N, I, REV);
+    constexpr bool first = (I == 0), last = (I == L - 1);
+    SmemIO<LAY> sm{s};
+    if constexpr (first && last) {
+      stage<N, Ns, R, C, NT, INV, KEEP_IN, KEEP_OUT>(ld0, stl, tw, ncol, keep);
+    } else if constexpr (first) {
+      stage<N, Ns, R, C, NT, INV, KEEP_IN, false>(ld0, sm, tw, ncol, keep);
+    } else if constexpr (last) {
+      stage<N, Ns, R, C, NT, INV, false, KEEP_OUT>(sm, stl, tw, ncol, keep);
+    } else {
+      stage<N, Ns, R, C, NT, INV, false, false>(sm, sm, tw, ncol, keep);
+    }
+    run_stages<N, C, NT, INV, REV, KEEP_IN, KEEP_OUT, LAY, I + 1>(s, tw, ncol, ld0, stl, keep);
+  }
+}
+
+// threads per CTA: N * C / D (D = points of the tile per thread in a radix-8 stage), clamped to [64, 1024]
+template <int N, int C, int D = 16>
+__host__ __device__ constexpr int threads_for() {
+  return (N * C / D) < 64 ? 64 : ((N * C / D) > 1024 ? 1024 : (N * C / D));
+}
+
+// ---- column pass (Y-fwd, Y-inv): in-place FFT along an axis with element stride `estride` ----------
+// grid: (ntile, nouter, batch).  Tile = C consecutive innermost (kz) columns.
+template <int N, int C, bool INV>
+__global__ void __launch_bounds__(threads_for<N, C>())
+cols_kernel(float2* __restrict__ a, long long batch_stride, long long outer_stride, long long estride, int nzh,
+            const float2* __restrict__ twg) {
+  constexpr int NT = threads_for<N, C>();
+  extern __shared__ __align__(16) float2 sm[];
+  float2* tw = sm;            // [N]
+  float2* s = sm + N;         // [N][C]
+  for (int i = threadIdx.x; i < N; i += NT) tw[i] = twg[i];
+  const int kz0 = blockIdx.x * C;
+  const int ncol = min(C, nzh - kz0);
+  GlobalIO g{a + blockIdx.z * batch_stride + blockIdx.y * outer_stride + kz0, estride};
+  run_stages<N, C, NT, INV, false, false, false, LayCols<C>, 0>(s, tw, ncol, g, g, nullptr);
+}
+
+// ---- X-fused pass ---------------------------------------------------------------------------------
+// grid: (ntile, ny).  Forward FFT along x, Green's function times the gradient for the three
+// components (same operation order as kspace_kernel<0> of plan.cu), three inverse FFTs along x.
+template <int N, int C>
+__global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
+xfused_kernel(const float2* __restrict__ a, float2* __restrict__ b3, long long comp_stride, long long xstride,
+              long long ystride, int nzh, const float2* __restrict__ twg, const float* __restrict__ wx,
+              const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
+              const float* __restrict__ ay, const float* __restrict__ az, float norm, float r_split2,
+              const float* __restrict__ ftab, int ntab, float fscale) {
+  constexpr int NT = threads_for<N, C, 8>();
+  constexpr int L = radix_count(N);
+  constexpr int RL = radix_at(N, L - 1, false);        // radix of the last forward == first inverse stage
+  constexpr int TASKS = (N / RL) * C;
+  constexpr int TPT = (TASKS + NT - 1) / NT;
+  extern __shared__ __align__(16) float2 sm[];
+  float2* tw = sm;            // [N]
+  float2* s = sm + N;         // [N][C]
+  float* swx = reinterpret_cast<float*>(s + N * C);   // [N] k_x table
+  float* sax = swx + N;                               // [N] gradient table
+  for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; swx[i] = wx[i]; sax[i] = ax[i]; }
+  const int kz0 = blockIdx.x * C;
+  const int ncol = min(C, nzh - kz0);
+  const int y = blockIdx.y;
+  const long long off = (long long)y * ystride + kz0;
+  GlobalIO gin{const_cast<float2*>(a) + off, xstride};
+  float2 keep[TPT][8];
+  run_stages<N, C, NT, false, false, false, true, LayCols<C>, 0>(s, tw, ncol, gin, NullIO{}, keep);
+  // delta_k(kx = j + r N/RL, y, kz0 + c) is in keep[i][r]; scale it by norm * G(k) / k^2 in place
+  const float ky = wy[y], a1 = ay[y];
+  float a2[TPT];
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    const int task = threadIdx.x + i * NT;
+    const int c = task % C, j = task / C;
+    a2[i] = 0.f;
+    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+      const float kz = wz[kz0 + c];
+      a2[i] = az[kz0 + c];
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        const float kx = swx[j + r * (N / RL)];
+        const float kxy2 = kx * kx + ky * ky;
+        const float kk = kxy2 + kz * kz;
+        float g = (kk == 0.f) ? 0.f : (1.0f / kk);
+        g *= norm;
+        if (r_split2 != 0.f) g *= expf(-kk * r_split2);
+        if (ftab) {
+          const float t = sqrtf(kk) * fscale;
+          const int ti = min((int)t, ntab - 2);
+          const float fr = fminf(t - (float)ti, 1.0f);
+          g *= ftab[ti] + fr * (ftab[ti + 1] - ftab[ti]);
+        }
+        keep[i][r].x *= g;
+        keep[i][r].y *= g;
+      }
+    }
+  }
+#pragma unroll 1
+  for (int d = 0; d < 3; ++d) {
+    float2 w[TPT][8];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int task = threadIdx.x + i * NT;
+      const int j = task / C;
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        const float ad = (d == 0) ? sax[(j + r * (N / RL)) & (N - 1)] : ((d == 1) ? a1 : a2[i]);
+        w[i][r] = make_float2(-ad * keep[i][r].y, ad * keep[i][r].x);   // i a_d (g delta)
+      }
+    }
+    GlobalIO gout{b3 + d * comp_stride + off, xstride};
+    run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
+  }
+}
+
+// ---- Z-fwd: R2C along z of 16 rows, ghost zones folded while loading -------------------------------
+// grid: (ny / 16, nx).  density_p is [nxp][nyp][nzp] with G ghost cells per side.
+constexpr int kRows = 16;
+template <int NZ>
+__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
+zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int ny, int nyp, int nzp, int G,
+            int nzc, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
+  constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
+  extern __shared__ __align__(16) float2 sm[];
+  float2* tw = sm;            // [NH]
+  float2* s = sm + NH;        // [16][NH + 1]
+  for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
+  const int x = blockIdx.y, y0 = blockIdx.x * kRows;
+  // periodic images of this x plane / these y rows inside the ghost zones (padded indices)
+  int xs[2] = {x + G, -1};
+  if (x < G) xs[1] = x + nx + G;
+  else if (x >= nx - G) xs[1] = x - nx + G;
+  const int GH = G / 2;       // ghost width in float2 units
+  constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
+  static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
+#pragma unroll 1
+  for (int b = 0; b < ITER; b += BATCH) {
+    float2 acc[BATCH];
+    // all loads of the batch are issued before the first use (the pass is latency-bound otherwise)
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = threadIdx.x + (b + i) * NT;
+      const int r = e / NH, m = e - r * NH;
+      const int y = y0 + r;
+      int ys[2] = {y + G, -1};
+      if (y < G) ys[1] = y + ny + G;
+      else if (y >= ny - G) ys[1] = y - ny + G;
+      acc[i] = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int ix = 0; ix < 2; ++ix) {
+        if (xs[ix] < 0) continue;
+#pragma unroll
+        for (int iy = 0; iy < 2; ++iy) {
+          if (ys[iy] < 0) continue;
+          const float2* row = reinterpret_cast<const float2*>(dens + ((long long)xs[ix] * nyp + ys[iy]) * nzp);
+          acc[i] = cadd(acc[i], __ldcs(row + GH + m));
+          if (m < GH) acc[i] = cadd(acc[i], __ldcs(row + NH + GH + m));       // high ghost -> first cells
+          if (m >= NH - GH) acc[i] = cadd(acc[i], __ldcs(row + m - (NH - GH)));   // low ghost -> last cells
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = threadIdx.x + (b + i) * NT;
+      const int r = e / NH, m = e - r * NH;
+      s[LayRows<NH>::idx(m, r)] = acc[i];
+    }
+  }
+  __syncthreads();
+  SmemIO<LayRows<NH>> io{s};
+  run_stages<NH, kRows, NT, false, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
+  // untangle: X[k] = (Z[k] + conj Z[NH-k]) / 2 + W_NZ^k (Z[k] - conj Z[NH-k]) / (2i)
+  for (int e = threadIdx.x; e < kRows * NH; e += NT) {
+    const int r = e / NH, k = e - r * NH;
+    const float2 zk = s[LayRows<NH>::idx(k, r)];
+    const float2 zc = cconj(s[LayRows<NH>::idx((NH - k) & (NH - 1), r)]);
+    const float2 ev = make_float2(0.5f * (zk.x + zc.x), 0.5f * (zk.y + zc.y));
+    const float2 df = csub(zk, zc);
+    const float2 od = make_float2(0.5f * df.y, -0.5f * df.x);       // (zk - zc) / (2i)
+    const float2 w = __ldg(twfull + k);
+    float2* dst = a + ((long long)x * ny + (y0 + r)) * nzc;
+    __stcs(dst + k, cadd(ev, cmul(w, od)));
+    if (k == 0) __stcs(dst + NH, make_float2(zk.x - zk.y, 0.f));
+  }
+}
+
+// ---- Z-inv: C2R along z of 16 rows, ghost zones filled while storing -------------------------------
+// grid: (ny / 16, nx, 3).  Output is unnormalised (the 1/Nc lives in the k-space factor).
+template <int NZ>
+__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
+zinv_kernel(const float2* __restrict__ b3, long long comp_stride, float* __restrict__ f3p, long long fcomp_stride,
+            int nx, int ny, int nyp, int nzp, int G, int nzc, const float2* __restrict__ twh,
+            const float2* __restrict__ twfull) {
+  constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
+  extern __shared__ __align__(16) float2 sm[];
+  float2* tw = sm;            // [NH]
+  float2* s = sm + NH;        // [16][NH + 1]
+  for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
+  const int x = blockIdx.y, y0 = blockIdx.x * kRows;
+  const float2* src = b3 + blockIdx.z * comp_stride + ((long long)x * ny + y0) * nzc;
+  constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
+  static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
+#pragma unroll 1
+  for (int b = 0; b < ITER; b += BATCH) {
+    float2 v[BATCH];
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = threadIdx.x + (b + i) * NT;
+      const int r = e / NH, k = e - r * NH;
+      v[i] = __ldcs(src + (long long)r * nzc + k);
+    }
+#pragma unroll
+    for (int i = 0; i < BATCH; ++i) {
+      const int e = threadIdx.x + (b + i) * NT;
+      const int r = e / NH, k = e - r * NH;
+      s[LayRows<NH>::idx(k, r)] = v[i];
+    }
+  }
+  if (threadIdx.x < kRows) s[LayRows<NH>::idx(NH, threadIdx.x)] = __ldcs(src + (long long)threadIdx.x * nzc + NH);
+  __syncthreads();
+  // tangle pairs (k, NH - k): Z'[k] = (X[k] + conj X[NH-k]) + i conj(W^k) (X[k] - conj X[NH-k])
+  for (int e = threadIdx.x; e < kRows * (NH / 2 + 1); e += NT) {
+    const int r = e / (NH / 2 + 1), k = e - r * (NH / 2 + 1);
+    const int kc = NH - k;
+    const float2 xk = s[LayRows<NH>::idx(k, r)], xc = s[LayRows<NH>::idx(kc, r)];
+    const float2 wk = cconj(__ldg(twfull + k));
+    {
+      const float2 sum = cadd(xk, cconj(xc)), dif = csub(xk, cconj(xc));
+      const float2 t = cmul(wk, dif);
+      s[LayRows<NH>::idx(k, r)] = make_float2(sum.x - t.y, sum.y + t.x);     // sum + i t
+    }
+    if (k != 0 && k != kc) {
+      const float2 wc = cconj(__ldg(twfull + kc));
+      const float2 sum = cadd(xc, cconj(xk)), dif = csub(xc, cconj(xk));
+      const float2 t = cmul(wc, dif);
+      s[LayRows<NH>::idx(kc, r)] = make_float2(sum.x - t.y, sum.y + t.x);
+    }
+  }
+  __syncthreads();
+  SmemIO<LayRows<NH>> io{s};
+  run_stages<NH, kRows, NT, true, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
+  int xs[2] = {x + G, -1};
+  if (x < G) xs[1] = x + nx + G;
+  else if (x >= nx - G) xs[1] = x - nx + G;
+  const int GH = G / 2;
+  float* dstc = f3p + blockIdx.z * fcomp_stride;
+  for (int e = threadIdx.x; e < kRows * NH; e += NT) {
+    const int r = e / NH, m = e - r * NH;
+    const int y = y0 + r;
+    int ys[2] = {y + G, -1};
+    if (y < G) ys[1] = y + ny + G;
+    else if (y >= ny - G) ys[1] = y - ny + G;
+    const float2 v = s[LayRows<NH>::idx(m, r)];
+#pragma unroll
+    for (int ix = 0; ix < 2; ++ix) {
+      if (xs[ix] < 0) continue;
+#pragma unroll
+      for (int iy = 0; iy < 2; ++iy) {
+        if (ys[iy] < 0) continue;
+        float2* row = reinterpret_cast<float2*>(dstc + ((long long)xs[ix] * nyp + ys[iy]) * nzp);
+        row[GH + m] = v;
+        if (m < GH) row[NH + GH + m] = v;
+        if (m >= NH - GH) row[m - (NH - GH)] = v;
+      }
+    }
+  }
+}
+
+static void make_twiddles(int n, int count, std::vector<float2>& out) {
+  out.resize(count);
+  for (int k = 0; k < count; ++k) {
+    const double a = -2.0 * M_PI * (double)k / (double)n;
+    out[k] = make_float2((float)std::cos(a), (float)std::sin(a));
+  }
+}
+
+static int32_t upload2(float2** dst, const std::vector<float2>& v) {
+  JPM_CUDA(cudaMalloc(dst, v.size() * sizeof(float2)));
+  JPM_CUDA(cudaMemcpy(*dst, v.data(), v.size() * sizeof(float2), cudaMemcpyHostToDevice));
+  return JPM_OK;
+}
+
+static bool pow2_in_range(int n) { return n >= 16 && n <= 1024 && (n & (n - 1)) == 0; }
+
+template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C) * sizeof(float2); }
+template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
+template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
+
+constexpr int kColsC = 16;   // kz columns per tile of the Y passes (128-byte segments)
+constexpr int kXC = 8;       // ... of the X-fused pass (64-byte segments; delta_k held in registers)
+
+#define JPM_FFT_SWITCH(n, MACRO)          \
+  switch (n) {                            \
+    case 16: MACRO(16); break;            \
+    case 32: MACRO(32); break;            \
+    case 64: MACRO(64); break;            \
+    case 128: MACRO(128); break;          \
+    case 256: MACRO(256); break;          \
+    case 512: MACRO(512); break;          \
+    case 1024: MACRO(1024); break;        \
+    default: set_error("pmfft: unsupported size %d", n); return JPM_ERR_INVALID; \
+  }
+
+static int32_t set_attrs(jpm_plan* p) {
+#define ATTR_Y(N_)                                                                                              \
+  JPM_CUDA(cudaFuncSetAttribute(cols_kernel<N_, kColsC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                (int)cols_smem<N_, kColsC>()));                                                 \
+  JPM_CUDA(cudaFuncSetAttribute(cols_kernel<N_, kColsC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                (int)cols_smem<N_, kColsC>()));
+  JPM_FFT_SWITCH(p->ny, ATTR_Y)
+#undef ATTR_Y
+#define ATTR_X(N_)                                                                                              \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
+                                (int)xfused_smem<N_, kXC>()));
+  JPM_FFT_SWITCH(p->nx, ATTR_X)
+#undef ATTR_X
+#define ATTR_Z(N_)                                                                                              \
+  JPM_CUDA(cudaFuncSetAttribute(zfwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>())); \
+  JPM_CUDA(cudaFuncSetAttribute(zinv_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>()));
+  JPM_FFT_SWITCH(p->nz, ATTR_Z)
+#undef ATTR_Z
+  return JPM_OK;
+}
+
+}  // namespace fft
+
+bool pmfft_supported(const jpm_plan* p) {
+  return fft::pow2_in_range(p->nx) && fft::pow2_in_range(p->ny) && fft::pow2_in_range(p->nz) && p->G > 0 &&
+         (p->G % 2) == 0;
+}
+
+int32_t pmfft_enable(jpm_plan* p) {
+  if (p->fft_a) return JPM_OK;
+  if (!pmfft_supported(p)) return JPM_OK;
+  p->nzc = (p->nzh + 7) & ~7;
+  const long long na = (long long)p->nx * p->ny * p->nzc;
+  std::vector<float2> t;
+  int32_t rc;
+  fft::make_twiddles(p->nx, p->nx, t);
+  if ((rc = fft::upload2(&p->tw_x, t))) return rc;
+  fft::make_twiddles(p->ny, p->ny, t);
+  if ((rc = fft::upload2(&p->tw_y, t))) return rc;
+  fft::make_twiddles(p->nz / 2, p->nz / 2, t);
+  if ((rc = fft::upload2(&p->tw_zh, t))) return rc;
+  fft::make_twiddles(p->nz, p->nz / 2 + 1, t);
+  if ((rc = fft::upload2(&p->tw_zfull, t))) return rc;
+  if ((rc = fft::set_attrs(p))) return rc;
+  JPM_CUDA(cudaMalloc(&p->fft_a, na * sizeof(float2)));
+  JPM_CUDA(cudaMalloc(&p->fft_b3, 3 * na * sizeof(float2)));
+  JPM_CUDA(cudaMemset(p->fft_a, 0, na * sizeof(float2)));
+  JPM_CUDA(cudaMemset(p->fft_b3, 0, 3 * na * sizeof(float2)));
+  return JPM_OK;
+}
+
+void pmfft_destroy(jpm_plan* p) {
+  void* bufs[] = {p->fft_a, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
+  for (void* b : bufs)
+    if (b) cudaFree(b);
+  p->fft_a = nullptr;
+}
+
+// density_p (painted, ghosts NOT folded) -> force3_p (ghosts filled); five kernels on `st`.
+int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
+                     float filter_kmax) {
+  using namespace fft;
+  JPM_CHECK_ARG(p->fft_a, "pmfft not enabled for this plan");
+  const int nx = p->nx, ny = p->ny, nz = p->nz, nzh = p->nzh, nzc = p->nzc, G = p->G;
+  const long long na = (long long)nx * ny * nzc;
+  const float norm = 1.0f / (float)p->ncell;
+  const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
+  const dim3 gz(ny / kRows, nx, 1), gz3(ny / kRows, nx, 3);
+#define RUN_ZF(N_)                                                                                             \
+  zfwd_kernel<N_><<<gz, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(p->density_p, p->fft_a, nx, ny, p->nyp, \
+                                                                         p->nzp, G, nzc, p->tw_zh, p->tw_zfull);
+  JPM_FFT_SWITCH(nz, RUN_ZF)
+#undef RUN_ZF
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "fft_z_r2c+ghost_fold");
+  const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
+#define RUN_YF(N_)                                                                                             \
+  cols_kernel<N_, kColsC, false><<<dim3(nty, nx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+      p->fft_a, na, (long long)ny * nzc, nzc, nzh, p->tw_y);
+  JPM_FFT_SWITCH(ny, RUN_YF)
+#undef RUN_YF
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "fft_y_fwd");
+#define RUN_X(N_)                                                                                              \
+  xfused_kernel<N_, kXC><<<dim3(ntx, ny, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(            \
+      p->fft_a, p->fft_b3, na, (long long)ny * nzc, nzc, nzh, p->tw_x, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, \
+      norm, r_split * r_split, filter_tab, n_tab, fscale);
+  JPM_FFT_SWITCH(nx, RUN_X)
+#undef RUN_X
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x3");
+#define RUN_YI(N_)                                                                                             \
+  cols_kernel<N_, kColsC, true><<<dim3(nty, nx, 3), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>(  \
+      p->fft_b3, na, (long long)ny * nzc, nzc, nzh, p->tw_y);
+  JPM_FFT_SWITCH(ny, RUN_YI)
+#undef RUN_YI
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "ifft_y_x3");
+#define RUN_ZI(N_)                                                                                             \
+  zinv_kernel<N_><<<gz3, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(p->fft_b3, na, p->force3_p, p->npad, nx, \
+                                                                          ny, p->nyp, p->nzp, G, nzc, p->tw_zh,  \
+                                                                          p->tw_zfull);
+  JPM_FFT_SWITCH(nz, RUN_ZI)
+#undef RUN_ZI
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "ifft_z_c2r_x3+ghost_fill");
+  return JPM_OK;
+}
+
+}  // namespace jpm

@@ -946,20 +946,60 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
   cudaStream_t st = (cudaStream_t)stream;
   jpm_plan* p = s->plan;
+  StageTimer* tm = p->timer;
   int32_t rc;
+  if (tm) tm->mark(st, "start");
   if (s->tma) {
-    // ghost-zone meshes: TMA reduce-add paint -> ghost fold -> R2C -> k-space -> 3x C2R -> ghost fill -> TMA read
+    // ghost-zone meshes: TMA reduce-add paint -> fused FFT chain (or ghost fold, cuFFT, ghost fill) -> TMA read
     JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+    if (tm) tm->mark(st, "mesh_memset");
     if ((rc = sim_paint_impl(s, st, p->density_p, true))) return rc;
+    if (tm) tm->mark(st, "sim_paint");
     if ((rc = plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f))) return rc;
-    return sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
-                         drift_coef, true);
+    rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
+                       drift_coef, true);
+    if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
+    return rc;
   }
   JPM_CUDA(cudaMemsetAsync(p->density, 0, p->ncell * sizeof(float), st));
+  if (tm) tm->mark(st, "mesh_memset");
   if ((rc = sim_paint_impl(s, st, p->density, false))) return rc;
+  if (tm) tm->mark(st, "sim_paint");
   if ((rc = jpm_density_to_force_meshes(p, stream, p->density, p->force3, 0.f, nullptr, 0, 0.f))) return rc;
-  return sim_read_impl(s, st, p->force3, p->force3 + p->ncell, p->force3 + 2 * p->ncell, kick_coef, drift_coef,
-                       false);
+  rc = sim_read_impl(s, st, p->force3, p->force3 + p->ncell, p->force3 + 2 * p->ncell, kick_coef, drift_coef,
+                     false);
+  if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
+  return rc;
+}
+
+// One jpm_sim_step with a CUDA event at every stage boundary.  Synchronises the stream.  names_out
+// receives up to `cap` pointers to static strings, ms_out the stage durations; returns the stage count
+// in *n_out.
+extern "C" int32_t jpm_sim_step_profile(jpm_sim* s, void* stream, float kick_coef, float drift_coef,
+                                        const char** names_out, float* ms_out, int32_t cap, int32_t* n_out) {
+  JPM_CHECK_ARG(s && s->plan && names_out && ms_out && n_out && cap > 0, "bad arguments");
+  StageTimer tm;
+  for (int i = 0; i < StageTimer::kMax; ++i) JPM_CUDA(cudaEventCreate(&tm.ev[i]));
+  s->plan->timer = &tm;
+  int32_t rc = jpm_sim_step(s, stream, kick_coef, drift_coef);
+  s->plan->timer = nullptr;
+  if (rc == JPM_OK) {
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    if (e != cudaSuccess) {
+      set_error("cudaStreamSynchronize failed: %s", cudaGetErrorString(e));
+      rc = JPM_ERR_CUDA;
+    }
+  }
+  int n = 0;
+  if (rc == JPM_OK) {
+    for (int i = 1; i < tm.n && n < cap; ++i, ++n) {
+      names_out[n] = tm.name[i];
+      cudaEventElapsedTime(&ms_out[n], tm.ev[i - 1], tm.ev[i]);
+    }
+  }
+  *n_out = n;
+  for (int i = 0; i < StageTimer::kMax; ++i) cudaEventDestroy(tm.ev[i]);
+  return rc;
 }
 
 extern "C" int32_t jpm_sim_stats_host(jpm_sim* s, void* stream, int64_t* out4_host) {

@@ -210,6 +210,16 @@ def force_meshes_from_density(density, plan, r_split=0.0, filter_tab=None):
     return out
 
 
+def force_meshes_from_density_fused(density, plan, r_split=0.0, filter_tab=None):
+    """Same as force_meshes_from_density through the fused FFT chain on the ghost-zone meshes."""
+    d = as_f32(density)
+    out = torch.empty((3, *plan.shape), dtype=torch.float32, device=d.device)
+    fp, nt, km, keep = _ftab(filter_tab, d.device)
+    call("jpm_density_to_force_meshes_fused", plan.handle, stream(), ptr(d), ptr(out), float(r_split), fp,
+         nt, km)
+    return out
+
+
 def lpt2_source(delta_k, plan):
     """delta2 of jaxpm/pm.py:88-109 from the first-order spectrum."""
     sh = torch.empty((6, *plan.spec_shape), dtype=torch.complex64, device=delta_k.device)
@@ -318,6 +328,14 @@ class Sim:
 
     def step(self, kick, drift):
         call("jpm_sim_step", self.handle, stream(), float(kick), float(drift))
+
+    def step_profile(self, kick, drift):
+        """One step with per-stage CUDA-event timing: [(stage name, milliseconds), ...]."""
+        names = (C.c_char_p * 24)()
+        ms = (C.c_float * 24)()
+        n = C.c_int32(0)
+        call("jpm_sim_step_profile", self.handle, stream(), float(kick), float(drift), names, ms, 24, C.byref(n))
+        return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
 
     def fallback_counts(self):
         out = (C.c_int64 * 4)()

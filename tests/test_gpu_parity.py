@@ -135,6 +135,33 @@ def test_fft_and_kspace(cuda, shape):
         assert rel_err(f3[d], ref) < FIELD_TOL
 
 
+@pytest.mark.parametrize("shape", [(16, 16, 16), (32, 16, 64), (64, 128, 32), (256, 64, 128), (24, 40, 20)])
+def test_fused_fft_chain(cuda, shape):
+    """jpm_density_to_force_meshes_fused (csrc/pmfft.cu: five hand-written FFT passes with the Green's
+    function x gradient fused into the x pass; cuFFT on the padded arrays for non power-of-two shapes)
+    against the unfused reference chain of pm.py:41-56 in float64, incl. r_split and the radial filter."""
+    from jaxpm_b200 import ops
+    from jaxpm_b200.kernels import pgd_filter_table
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal(shape).astype(np.float32)
+    plan = ops.get_plan(shape, cuda)
+    dk = OK.fft3d(x.astype(np.float64))
+    kvec = OK.fftk(dk)
+    for r_split, filt, tab, tol in ((0.0, None, None, FIELD_TOL),
+                                    (1.3, OK.PGD_kernel(kvec, 0.4, 2.5), pgd_filter_table(0.4, 2.5, 1 << 16), 1e-4)):
+        f3 = ops.force_meshes_from_density_fused(T(x, cuda), plan, r_split, tab).cpu().numpy()
+        pot = dk * OK.invlaplace_kernel(kvec) * OK.longrange_kernel(kvec, r_split)
+        if filt is not None:
+            pot = pot * filt
+        for d in range(3):
+            ref = OK.ifft3d(-OK.gradient_kernel(kvec, d) * pot)
+            assert rel_err(f3[d], ref) < tol, (d, r_split)
+    # and against the cuFFT path of the same library
+    f3c = ops.force_meshes_from_density(T(x, cuda), plan).cpu().numpy()
+    f3f = ops.force_meshes_from_density_fused(T(x, cuda), plan).cpu().numpy()
+    assert rel_err(f3f, f3c) < FIELD_TOL
+
+
 @pytest.mark.parametrize("absolute", [True, False])
 @pytest.mark.parametrize("shape", [(16, 16, 16), (32, 32, 64)])
 def test_pm_forces(cuda, shape, absolute):
