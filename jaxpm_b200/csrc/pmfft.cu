@@ -312,19 +312,38 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
   const int GH = G / 2;       // ghost width in float2 units
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
+  // blocks away from the x / y faces have no periodic images to fold: branch-free loads, BATCH in flight
+  const bool interior = xs[1] < 0 && y0 >= G && y0 + kRows <= ny - G;
+  if (interior) {
+    const float2* base = reinterpret_cast<const float2*>(dens + ((long long)xs[0] * nyp + (y0 + G)) * nzp) + GH;
+    const int rowp = nzp / 2;   // row pitch in float2
 #pragma unroll 1
-  for (int b = 0; b < ITER; b += BATCH) {
-    float2 acc[BATCH];
-    // all loads of the batch are issued before the first use (the pass is latency-bound otherwise)
+    for (int b = 0; b < ITER; b += BATCH) {
+      float2 acc[BATCH], lo[BATCH], hi[BATCH];
 #pragma unroll
-    for (int i = 0; i < BATCH; ++i) {
-      const int e = threadIdx.x + (b + i) * NT;
+      for (int i = 0; i < BATCH; ++i) {
+        const int e = threadIdx.x + (b + i) * NT;
+        const int r = e / NH, m = e - r * NH;
+        const float2* q = base + r * rowp + m;
+        acc[i] = __ldcs(q);
+        hi[i] = (m < GH) ? __ldcs(q + NH) : make_float2(0.f, 0.f);          // high ghost -> first cells
+        lo[i] = (m >= NH - GH) ? __ldcs(q - NH) : make_float2(0.f, 0.f);    // low ghost -> last cells
+      }
+#pragma unroll
+      for (int i = 0; i < BATCH; ++i) {
+        const int e = threadIdx.x + (b + i) * NT;
+        const int r = e / NH, m = e - r * NH;
+        s[LayRows<NH>::idx(m, r)] = cadd(cadd(acc[i], hi[i]), lo[i]);
+      }
+    }
+  } else {
+    for (int e = threadIdx.x; e < kRows * NH; e += NT) {
       const int r = e / NH, m = e - r * NH;
       const int y = y0 + r;
       int ys[2] = {y + G, -1};
       if (y < G) ys[1] = y + ny + G;
       else if (y >= ny - G) ys[1] = y - ny + G;
-      acc[i] = make_float2(0.f, 0.f);
+      float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
       for (int ix = 0; ix < 2; ++ix) {
         if (xs[ix] < 0) continue;
@@ -332,17 +351,12 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
         for (int iy = 0; iy < 2; ++iy) {
           if (ys[iy] < 0) continue;
           const float2* row = reinterpret_cast<const float2*>(dens + ((long long)xs[ix] * nyp + ys[iy]) * nzp);
-          acc[i] = cadd(acc[i], __ldcs(row + GH + m));
-          if (m < GH) acc[i] = cadd(acc[i], __ldcs(row + NH + GH + m));       // high ghost -> first cells
-          if (m >= NH - GH) acc[i] = cadd(acc[i], __ldcs(row + m - (NH - GH)));   // low ghost -> last cells
+          acc = cadd(acc, __ldcs(row + GH + m));
+          if (m < GH) acc = cadd(acc, __ldcs(row + NH + GH + m));
+          if (m >= NH - GH) acc = cadd(acc, __ldcs(row + m - (NH - GH)));
         }
       }
-    }
-#pragma unroll
-    for (int i = 0; i < BATCH; ++i) {
-      const int e = threadIdx.x + (b + i) * NT;
-      const int r = e / NH, m = e - r * NH;
-      s[LayRows<NH>::idx(m, r)] = acc[i];
+      s[LayRows<NH>::idx(m, r)] = acc;
     }
   }
   __syncthreads();
