@@ -224,8 +224,9 @@ def run_gpu(args):
     alg = {  # algorithmic bytes per launch
         "mesh_memset": 4 * nc, "sim_paint": 12 * npart + 4 * nc,
         "tile_scan+sim_read3_kick_drift": 48 * npart + 12 * nc,
-        "fft_z_r2c+ghost_fold": 8 * nc, "fft_y_fwd": 8 * nc, "fft_x_fwd+greens_grad+ifft_x_x3": 16 * nc,
-        "ifft_y_x3": 24 * nc, "ifft_z_c2r_x3+ghost_fill": 24 * nc,
+        "fft_z_r2c+ghost_fold": 8 * nc, "fft_y_fwd+transpose": 8 * nc,
+        "fft_x_fwd+greens_grad+ifft_x_x2+transpose": 12 * nc, "ifft_y_x3": 20 * nc,
+        "ifft_z_c2r_x3+ghost_fill": 24 * nc,
         "ghost_fold": 0, "ghost_fill": 0, "fft_r2c(cuFFT)": 8 * nc, "greens_grad": 16 * nc,
         "ifft_c2r_x3(cuFFT)": 24 * nc,
     }

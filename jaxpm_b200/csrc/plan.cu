@@ -266,7 +266,7 @@ int32_t plan_enable_padded(jpm_plan* p) {
   if (!(env && env[0] == '0')) {
     int32_t rc = pmfft_enable(p);
     if (rc) return rc;
-    if (p->fft_a) return JPM_OK;
+    if (p->fft_on) return JPM_OK;
   }
   int n[3] = {p->nx, p->ny, p->nz};
   int remb[3] = {p->nxp, p->nyp, p->nzp};      // real side: embedded in the padded array
@@ -296,7 +296,7 @@ int32_t plan_enable_padded(jpm_plan* p) {
 int32_t plan_padded_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
                            float filter_kmax) {
   JPM_CHECK_ARG(p->G > 0, "padded meshes not enabled");
-  if (p->fft_a) return pmfft_forces(p, st, r_split, filter_tab, n_tab, filter_kmax);
+  if (p->fft_on) return pmfft_forces(p, st, r_split, filter_tab, n_tab, filter_kmax);
   const long long off = ((long long)p->G * p->nyp + p->G) * p->nzp + p->G;   // interior origin
   int32_t rc;
   if ((rc = ghost_pass<true>(p, st, p->density_p, 1))) return rc;

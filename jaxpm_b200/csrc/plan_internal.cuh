@@ -20,8 +20,32 @@ struct StageTimer {
   }
 };
 
+// Geometry + (peer) pointers of the x-slab decomposition the pmfft kernels work on.  One rank = one GPU of
+// the box; rank r owns global x planes [r lx, (r+1) lx).  P == 1 describes the ordinary single-GPU plan.
+// Passed to the kernels by value (__grid_constant__).
+struct Slab {
+  int P, rank;
+  int nx, ny, nz;        // GLOBAL mesh
+  int lx, ly;            // nx / P, ny / P
+  int gx, G;             // ghost planes per side in x (images of the neighbour slabs); ghost cells in y, z
+  int nxp, nyp, nzp;     // local padded real arrays: lx + 2 gx, ny + 2 G, nz + 2 G
+  long long npad;        // nxp * nyp * nzp
+  int nzh, nzc;          // nz / 2 + 1 and its pitch (multiple of 8)
+  float* dens[8];        // [nxp][nyp][nzp]       density (painted into, ghosts not folded)
+  float* force[8];       // [3][nxp][nyp][nzp]    force meshes, ghosts filled
+  float2* at[8];         // [nx][ly][nzc]         z,y-transformed density, transposed: all x of the rank's y rows
+  float2* b3[8];         // [3][lx][ny][nzc]      x-inverse-transformed spectra of the rank's x planes
+  unsigned* flags[8];    // [65] barrier slots (one per peer) + error word
+};
+
 struct jpm_plan {
   StageTimer* timer = nullptr;
+  Slab slab;                  // valid when fft_on
+  bool fft_on = false;        // pmfft chain available (power-of-two shape)
+  unsigned epoch = 0;         // barrier epoch (P > 1)
+  void* sym_base = nullptr;   // P > 1: the IPC-shared allocation every array of `slab` lives in
+  void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  size_t sym_bytes = 0;
   int nx, ny, nz, nzh;
   long long ncell, nspec;
   cufftHandle r2c = 0, c2r1 = 0, c2r3 = 0;
@@ -46,9 +70,8 @@ struct jpm_plan {
   float* force3_p = nullptr;  // [3][nxp][nyp][nzp]
   cufftHandle r2c_p = 0, c2r3_p = 0;
   // ---- pmfft (csrc/pmfft.cu): hand-written fused FFT chain on the padded meshes, power-of-two shapes --
-  int nzc = 0;                // pitch (complex) of a spectrum row: nzh rounded up to a multiple of 8
-  float2* fft_a = nullptr;    // [nx][ny][nzc]      z- then y-transformed density
-  float2* fft_b3 = nullptr;   // [3][nx][ny][nzc]   x-inverse-transformed force spectra
+  float2* fft_at = nullptr;   // P == 1: the AT buffer   [nx][ny][nzc]
+  float2* fft_b3 = nullptr;   // P == 1: the B3 buffer   [3][nx][ny][nzc]
   float2 *tw_x = nullptr, *tw_y = nullptr, *tw_zh = nullptr, *tw_zfull = nullptr;   // exp(-2 pi i k / n) tables
 };
 
@@ -62,6 +85,9 @@ int32_t plan_padded_forces(jpm_plan* p, cudaStream_t stream, float r_split, cons
                            int n_tab, float filter_kmax);
 // pmfft: enable (allocates; no-op when the shape is unsupported), run density_p -> force3_p, free.
 int32_t pmfft_enable(jpm_plan* p);
+int32_t pmfft_setup(jpm_plan* p);
+bool pmfft_shape_ok(int nx, int ny, int nz);
+int32_t slab_barrier(jpm_plan* p, cudaStream_t stream);
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
                      float filter_kmax);
 void pmfft_destroy(jpm_plan* p);

@@ -21,6 +21,7 @@
 // 4 shared-memory passes instead of 8.  Row passes (z) stage 16 rows with a pitch of N/2+1 complex, lanes
 // across rows: conflict-free for every stage permutation.
 #include <cmath>
+#include <cstring>
 #include <vector>
 
 #include "plan_internal.cuh"
@@ -199,33 +200,56 @@ __host__ __device__ constexpr int threads_for() {
   return (N * C / D) < 64 ? 64 : ((N * C / D) > 1024 ? 1024 : (N * C / D));
 }
 
-// ---- column pass (Y-fwd, Y-inv): in-place FFT along an axis with element stride `estride` ----------
-// grid: (ntile, nouter, batch).  Tile = C consecutive innermost (kz) columns.
-template <int N, int C, bool INV>
+// ---- peer-aware global I/O of the slab decomposition -------------------------------------------------
+// y-transformed element (y, c) of x plane `xg` goes to the rank that owns y: AT[xg][y % ly][kz] there
+struct ScatterYIO {
+  static constexpr bool kSmem = false;
+  const Slab* sl;
+  long long xoff;   // xg * ly * nzc + kz0
+  __device__ __forceinline__ void operator()(int n, int c, float2 v) const {
+    const int d = n / sl->ly, yl = n - d * sl->ly;
+    __stcs(sl->at[d] + xoff + (long long)yl * sl->nzc + c, v);
+  }
+};
+// x-inverse-transformed element (x, c) of row yg goes to the rank that owns x: B[comp][x % lx][yg][kz] there
+struct ScatterXIO {
+  static constexpr bool kSmem = false;
+  const Slab* sl;
+  long long off;    // comp * lx * ny * nzc + yg * nzc + kz0
+  __device__ __forceinline__ void operator()(int n, int c, float2 v) const {
+    const int d = n / sl->lx, xl = n - d * sl->lx;
+    __stcs(sl->b3[d] + off + (long long)xl * sl->ny * sl->nzc + c, v);
+  }
+};
+
+// ---- Y-fwd: FFT along y of the local x planes, result transposed onto the y-owning ranks ---------------
+// grid: (ntile, lx).  in: A_loc = B3[2] region of this rank [lx][ny][nzc]; out: AT[nx][ly][nzc] of every rank.
+template <int N, int C>
 __global__ void __launch_bounds__(threads_for<N, C>())
-cols_kernel(float2* __restrict__ a, long long batch_stride, long long outer_stride, long long estride, int nzh,
-            const float2* __restrict__ twg) {
+yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg) {
   constexpr int NT = threads_for<N, C>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   for (int i = threadIdx.x; i < N; i += NT) tw[i] = twg[i];
-  const int kz0 = blockIdx.x * C;
-  const int ncol = min(C, nzh - kz0);
-  GlobalIO g{a + blockIdx.z * batch_stride + blockIdx.y * outer_stride + kz0, estride};
-  run_stages<N, C, NT, INV, false, false, false, LayCols<C>, 0>(s, tw, ncol, g, g, nullptr);
+  const int kz0 = blockIdx.x * C, xl = blockIdx.y;
+  const int ncol = min(C, sl.nzh - kz0);
+  const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
+  GlobalIO gin{sl.b3[sl.rank] + 2 * cs + (long long)xl * sl.ny * sl.nzc + kz0, sl.nzc};
+  ScatterYIO gout{&sl, (long long)(sl.rank * sl.lx + xl) * sl.ly * sl.nzc + kz0};
+  run_stages<N, C, NT, false, false, false, false, LayCols<C>, 0>(s, tw, ncol, gin, gout, nullptr);
 }
 
 // ---- X-fused pass ---------------------------------------------------------------------------------
-// grid: (ntile, ny).  Forward FFT along x, Green's function times the gradient for the three
-// components (same operation order as kspace_kernel<0> of plan.cu), three inverse FFTs along x.
+// grid: (ntile, ly).  Forward FFT along x; delta_k stays in registers and is scaled by norm * G(k) / k^2
+// (operation order of kspace_kernel<0>, plan.cu); then TWO inverse FFTs along x:
+//   T0 = IFFT_x(i a_x(kx) g delta)  -> B[0]   (x force; a_y, a_z do not depend on kx, so the y and z
+//   T1 = IFFT_x(g delta)            -> B[1]    forces share T1: their factors are applied in Y-inv / Z-inv)
 template <int N, int C>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
-xfused_kernel(const float2* __restrict__ a, float2* __restrict__ b3, long long comp_stride, long long xstride,
-              long long ystride, int nzh, const float2* __restrict__ twg, const float* __restrict__ wx,
+xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
               const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
-              const float* __restrict__ ay, const float* __restrict__ az, float norm, float r_split2,
-              const float* __restrict__ ftab, int ntab, float fscale) {
+              float norm, float r_split2, const float* __restrict__ ftab, int ntab, float fscale) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int L = radix_count(N);
   constexpr int RL = radix_at(N, L - 1, false);        // radix of the last forward == first inverse stage
@@ -238,23 +262,19 @@ xfused_kernel(const float2* __restrict__ a, float2* __restrict__ b3, long long c
   float* sax = swx + N;                               // [N] gradient table
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; swx[i] = wx[i]; sax[i] = ax[i]; }
   const int kz0 = blockIdx.x * C;
-  const int ncol = min(C, nzh - kz0);
-  const int y = blockIdx.y;
-  const long long off = (long long)y * ystride + kz0;
-  GlobalIO gin{const_cast<float2*>(a) + off, xstride};
+  const int ncol = min(C, sl.nzh - kz0);
+  const int yl = blockIdx.y, yg = sl.rank * sl.ly + yl;
+  GlobalIO gin{sl.at[sl.rank] + (long long)yl * sl.nzc + kz0, (long long)sl.ly * sl.nzc};
   float2 keep[TPT][8];
   run_stages<N, C, NT, false, false, false, true, LayCols<C>, 0>(s, tw, ncol, gin, NullIO{}, keep);
-  // delta_k(kx = j + r N/RL, y, kz0 + c) is in keep[i][r]; scale it by norm * G(k) / k^2 in place
-  const float ky = wy[y], a1 = ay[y];
-  float a2[TPT];
+  // delta_k(kx = j + r N/RL, yg, kz0 + c) is in keep[i][r]; scale it by norm * G(k) / k^2 in place
+  const float ky = wy[yg];
 #pragma unroll
   for (int i = 0; i < TPT; ++i) {
     const int task = threadIdx.x + i * NT;
     const int c = task % C, j = task / C;
-    a2[i] = 0.f;
     if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
       const float kz = wz[kz0 + c];
-      a2[i] = az[kz0 + c];
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
         const float kx = swx[j + r * (N / RL)];
@@ -274,8 +294,9 @@ xfused_kernel(const float2* __restrict__ a, float2* __restrict__ b3, long long c
       }
     }
   }
+  const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
 #pragma unroll 1
-  for (int d = 0; d < 3; ++d) {
+  for (int d = 0; d < 2; ++d) {
     float2 w[TPT][8];
 #pragma unroll
     for (int i = 0; i < TPT; ++i) {
@@ -283,39 +304,101 @@ xfused_kernel(const float2* __restrict__ a, float2* __restrict__ b3, long long c
       const int j = task / C;
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
-        const float ad = (d == 0) ? sax[(j + r * (N / RL)) & (N - 1)] : ((d == 1) ? a1 : a2[i]);
-        w[i][r] = make_float2(-ad * keep[i][r].y, ad * keep[i][r].x);   // i a_d (g delta)
+        if (d == 0) {
+          const float ad = sax[(j + r * (N / RL)) & (N - 1)];
+          w[i][r] = make_float2(-ad * keep[i][r].y, ad * keep[i][r].x);   // i a_x (g delta)
+        } else {
+          w[i][r] = keep[i][r];
+        }
       }
     }
-    GlobalIO gout{b3 + d * comp_stride + off, xstride};
+    ScatterXIO gout{&sl, d * cs + (long long)yg * sl.nzc + kz0};
     run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
   }
 }
 
+// ---- Y-inv: inverse FFT along y of the local x planes ---------------------------------------------------
+// grid: (ntile, lx).  B[0] = T0 -> F_x in place;  B[1] = T1 is read ONCE into registers and transformed twice:
+// as it is -> B[2] (F_z up to the factor i a_z(kz), applied by Z-inv) and times i a_y(ky) -> B[1] (F_y).
+template <int N, int C>
+__global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
+yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay) {
+  constexpr int NT = threads_for<N, C, 8>();
+  constexpr int R0 = radix_at(N, 0, false);           // first inverse stage (forward radix order)
+  constexpr int TASKS = (N / R0) * C;
+  constexpr int TPT = (TASKS + NT - 1) / NT;
+  extern __shared__ __align__(16) float2 sm[];
+  float2* tw = sm;            // [N]
+  float2* s = sm + N;         // [N][C]
+  float* say = reinterpret_cast<float*>(s + N * C);   // [N] gradient table along y
+  for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; say[i] = ay[i]; }
+  const int kz0 = blockIdx.x * C, xl = blockIdx.y;
+  const int ncol = min(C, sl.nzh - kz0);
+  const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
+  float2* base = sl.b3[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0;
+  GlobalIO g0{base, sl.nzc}, g1{base + cs, sl.nzc}, g2{base + 2 * cs, sl.nzc};
+  run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, g0, nullptr);
+  float2 keep[TPT][8];
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    const int task = threadIdx.x + i * NT;
+    const int c = task % C, j = task / C;
+    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+#pragma unroll
+      for (int r = 0; r < R0; ++r) keep[i][r] = g1(j + r * (N / R0), c);
+    }
+  }
+  __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
+  {
+    float2 w[TPT][8];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i)
+#pragma unroll
+      for (int r = 0; r < R0; ++r) w[i][r] = keep[i][r];
+    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g2, w);
+  }
+  {
+    float2 w[TPT][8];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int task = threadIdx.x + i * NT;
+      const int j = task / C;
+#pragma unroll
+      for (int r = 0; r < R0; ++r) {
+        const float a = say[(j + r * (N / R0)) & (N - 1)];
+        w[i][r] = make_float2(-a * keep[i][r].y, a * keep[i][r].x);       // i a_y T1
+      }
+    }
+    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g1, w);
+  }
+}
+
 // ---- Z-fwd: R2C along z of 16 rows, ghost zones folded while loading -------------------------------
-// grid: (ny / 16, nx).  density_p is [nxp][nyp][nzp] with G ghost cells per side.
+// grid: (ny / 16, lx).  Real arrays are [lx + 2 gx][nyp][nzp]: gx ghost planes per side in x (images of the
+// neighbour slabs; of this slab itself when P == 1), G ghost cells per side in y and z (periodic images).
 constexpr int kRows = 16;
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
-zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int ny, int nyp, int nzp, int G,
-            int nzc, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
+zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int x = blockIdx.y, y0 = blockIdx.x * kRows;
-  // periodic images of this x plane / these y rows inside the ghost zones (padded indices)
-  int xs[2] = {x + G, -1};
-  if (x < G) xs[1] = x + nx + G;
-  else if (x >= nx - G) xs[1] = x - nx + G;
+  const int xl = blockIdx.y, y0 = blockIdx.x * kRows;
+  const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp;
   const int GH = G / 2;       // ghost width in float2 units
+  // x planes that fold onto interior plane xl: this rank's own, the left neighbour's high ghost, the right
+  // neighbour's low ghost
+  const float* src[3] = {sl.dens[sl.rank] + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
+  if (xl < gx) src[1] = sl.dens[(sl.rank + sl.P - 1) % sl.P] + (long long)(gx + lx + xl) * nyp * nzp;
+  if (xl >= lx - gx) src[2] = sl.dens[(sl.rank + 1) % sl.P] + (long long)(xl - (lx - gx)) * nyp * nzp;
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
   // blocks away from the x / y faces have no periodic images to fold: branch-free loads, BATCH in flight
-  const bool interior = xs[1] < 0 && y0 >= G && y0 + kRows <= ny - G;
+  const bool interior = !src[1] && !src[2] && y0 >= G && y0 + kRows <= ny - G;
   if (interior) {
-    const float2* base = reinterpret_cast<const float2*>(dens + ((long long)xs[0] * nyp + (y0 + G)) * nzp) + GH;
+    const float2* base = reinterpret_cast<const float2*>(src[0] + (long long)(y0 + G) * nzp) + GH;
     const int rowp = nzp / 2;   // row pitch in float2
 #pragma unroll 1
     for (int b = 0; b < ITER; b += BATCH) {
@@ -337,6 +420,7 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
       }
     }
   } else {
+#pragma unroll 2
     for (int e = threadIdx.x; e < kRows * NH; e += NT) {
       const int r = e / NH, m = e - r * NH;
       const int y = y0 + r;
@@ -345,15 +429,15 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
       else if (y >= ny - G) ys[1] = y - ny + G;
       float2 acc = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int ix = 0; ix < 2; ++ix) {
-        if (xs[ix] < 0) continue;
+      for (int ix = 0; ix < 3; ++ix) {
+        if (!src[ix]) continue;
 #pragma unroll
         for (int iy = 0; iy < 2; ++iy) {
           if (ys[iy] < 0) continue;
-          const float2* row = reinterpret_cast<const float2*>(dens + ((long long)xs[ix] * nyp + ys[iy]) * nzp);
-          acc = cadd(acc, __ldcs(row + GH + m));
-          if (m < GH) acc = cadd(acc, __ldcs(row + NH + GH + m));
-          if (m >= NH - GH) acc = cadd(acc, __ldcs(row + m - (NH - GH)));
+          const float2* row = reinterpret_cast<const float2*>(src[ix] + (long long)ys[iy] * nzp);
+          acc = cadd(acc, row[GH + m]);
+          if (m < GH) acc = cadd(acc, row[NH + GH + m]);
+          if (m >= NH - GH) acc = cadd(acc, row[m - (NH - GH)]);
         }
       }
       s[LayRows<NH>::idx(m, r)] = acc;
@@ -362,7 +446,8 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
   __syncthreads();
   SmemIO<LayRows<NH>> io{s};
   run_stages<NH, kRows, NT, false, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
-  // untangle: X[k] = (Z[k] + conj Z[NH-k]) / 2 + W_NZ^k (Z[k] - conj Z[NH-k]) / (2i)
+  // untangle: X[k] = (Z[k] + conj Z[NH-k]) / 2 + W_NZ^k (Z[k] - conj Z[NH-k]) / (2i)   -> A_loc (= B[2] region)
+  float2* aloc = sl.b3[sl.rank] + 2ll * sl.lx * ny * sl.nzc + ((long long)xl * ny + y0) * sl.nzc;
   for (int e = threadIdx.x; e < kRows * NH; e += NT) {
     const int r = e / NH, k = e - r * NH;
     const float2 zk = s[LayRows<NH>::idx(k, r)];
@@ -371,26 +456,28 @@ zfwd_kernel(const float* __restrict__ dens, float2* __restrict__ a, int nx, int 
     const float2 df = csub(zk, zc);
     const float2 od = make_float2(0.5f * df.y, -0.5f * df.x);       // (zk - zc) / (2i)
     const float2 w = __ldg(twfull + k);
-    float2* dst = a + ((long long)x * ny + (y0 + r)) * nzc;
+    float2* dst = aloc + (long long)r * sl.nzc;
     __stcs(dst + k, cadd(ev, cmul(w, od)));
     if (k == 0) __stcs(dst + NH, make_float2(zk.x - zk.y, 0.f));
   }
 }
 
 // ---- Z-inv: C2R along z of 16 rows, ghost zones filled while storing -------------------------------
-// grid: (ny / 16, nx, 3).  Output is unnormalised (the 1/Nc lives in the k-space factor).
+// grid: (ny / 16, lx, 3).  Output is unnormalised (the 1/Nc lives in the k-space factor).  Component 2
+// still carries the factor i a_z(kz) (see X-fused / Y-inv).  Every row is written to this rank's interior
+// plane, to its y / z ghost images and to the x ghost planes of the neighbour slabs that image it.
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
-zinv_kernel(const float2* __restrict__ b3, long long comp_stride, float* __restrict__ f3p, long long fcomp_stride,
-            int nx, int ny, int nyp, int nzp, int G, int nzc, const float2* __restrict__ twh,
-            const float2* __restrict__ twfull) {
+zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull,
+            const float* __restrict__ az) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int x = blockIdx.y, y0 = blockIdx.x * kRows;
-  const float2* src = b3 + blockIdx.z * comp_stride + ((long long)x * ny + y0) * nzc;
+  const int xl = blockIdx.y, y0 = blockIdx.x * kRows, comp = blockIdx.z;
+  const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp, nzc = sl.nzc;
+  const float2* src = sl.b3[sl.rank] + (long long)comp * lx * ny * nzc + ((long long)xl * ny + y0) * nzc;
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
 #pragma unroll 1
@@ -406,10 +493,21 @@ zinv_kernel(const float2* __restrict__ b3, long long comp_stride, float* __restr
     for (int i = 0; i < BATCH; ++i) {
       const int e = threadIdx.x + (b + i) * NT;
       const int r = e / NH, k = e - r * NH;
+      if (comp == 2) {
+        const float a = __ldg(az + k);
+        v[i] = make_float2(-a * v[i].y, a * v[i].x);
+      }
       s[LayRows<NH>::idx(k, r)] = v[i];
     }
   }
-  if (threadIdx.x < kRows) s[LayRows<NH>::idx(NH, threadIdx.x)] = __ldcs(src + (long long)threadIdx.x * nzc + NH);
+  if (threadIdx.x < kRows) {
+    float2 v = __ldcs(src + (long long)threadIdx.x * nzc + NH);
+    if (comp == 2) {
+      const float a = __ldg(az + NH);
+      v = make_float2(-a * v.y, a * v.x);
+    }
+    s[LayRows<NH>::idx(NH, threadIdx.x)] = v;
+  }
   __syncthreads();
   // tangle pairs (k, NH - k): Z'[k] = (X[k] + conj X[NH-k]) + i conj(W^k) (X[k] - conj X[NH-k])
   for (int e = threadIdx.x; e < kRows * (NH / 2 + 1); e += NT) {
@@ -432,11 +530,12 @@ zinv_kernel(const float2* __restrict__ b3, long long comp_stride, float* __restr
   __syncthreads();
   SmemIO<LayRows<NH>> io{s};
   run_stages<NH, kRows, NT, true, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
-  int xs[2] = {x + G, -1};
-  if (x < G) xs[1] = x + nx + G;
-  else if (x >= nx - G) xs[1] = x - nx + G;
+  // destinations in x: own interior plane, left neighbour's high ghost, right neighbour's low ghost
+  const long long cofs = (long long)comp * sl.npad;
+  float* dstp[3] = {sl.force[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
+  if (xl < gx) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
+  if (xl >= lx - gx) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
   const int GH = G / 2;
-  float* dstc = f3p + blockIdx.z * fcomp_stride;
   for (int e = threadIdx.x; e < kRows * NH; e += NT) {
     const int r = e / NH, m = e - r * NH;
     const int y = y0 + r;
@@ -445,18 +544,44 @@ zinv_kernel(const float2* __restrict__ b3, long long comp_stride, float* __restr
     else if (y >= ny - G) ys[1] = y - ny + G;
     const float2 v = s[LayRows<NH>::idx(m, r)];
 #pragma unroll
-    for (int ix = 0; ix < 2; ++ix) {
-      if (xs[ix] < 0) continue;
+    for (int ix = 0; ix < 3; ++ix) {
+      if (!dstp[ix]) continue;
 #pragma unroll
       for (int iy = 0; iy < 2; ++iy) {
         if (ys[iy] < 0) continue;
-        float2* row = reinterpret_cast<float2*>(dstc + ((long long)xs[ix] * nyp + ys[iy]) * nzp);
+        float2* row = reinterpret_cast<float2*>(dstp[ix] + (long long)ys[iy] * nzp);
         row[GH + m] = v;
         if (m < GH) row[NH + GH + m] = v;
         if (m >= NH - GH) row[m - (NH - GH)] = v;
       }
     }
   }
+}
+
+// ---- inter-GPU barrier over peer-mapped flags ------------------------------------------------------------
+// flags[r] (on every rank) has one slot per peer; rank `me` writes `epoch` into slot `me` of every peer and
+// waits until its own slots all reach `epoch`.  One CTA, one thread per peer.  A lost peer trips the
+// timeout (~4 s) and raises the error word instead of hanging the GPU.
+__global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch) {
+  const int t = threadIdx.x;
+  __threadfence_system();
+  if (t < sl.P) {
+    unsigned* remote = sl.flags[t] + sl.rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
+    const unsigned* mine = sl.flags[sl.rank] + t;
+    unsigned v;
+    long long t0 = clock64();
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 8000000000ll) {   // ~4 s at 2 GHz
+        sl.flags[sl.rank][64] = 1u;          // error word
+        break;
+      }
+    } while (true);
+  }
+  __syncthreads();
+  __threadfence_system();
 }
 
 static void make_twiddles(int n, int count, std::vector<float2>& out) {
@@ -479,8 +604,8 @@ template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C
 template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
 template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
 
-constexpr int kColsC = 16;   // kz columns per tile of the Y passes (128-byte segments)
-constexpr int kXC = 8;       // ... of the X-fused pass (64-byte segments; delta_k held in registers)
+constexpr int kColsC = 16;   // kz columns per tile of the Y-fwd pass (128-byte segments)
+constexpr int kXC = 8;       // ... of the X-fused and Y-inv passes (64-byte segments; data held in registers)
 
 #define JPM_FFT_SWITCH(n, MACRO)          \
   switch (n) {                            \
@@ -494,111 +619,134 @@ constexpr int kXC = 8;       // ... of the X-fused pass (64-byte segments; delta
     default: set_error("pmfft: unsupported size %d", n); return JPM_ERR_INVALID; \
   }
 
-static int32_t set_attrs(jpm_plan* p) {
+static int32_t set_attrs(const Slab& sl) {
 #define ATTR_Y(N_)                                                                                              \
-  JPM_CUDA(cudaFuncSetAttribute(cols_kernel<N_, kColsC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+  JPM_CUDA(cudaFuncSetAttribute(yfwd_kernel<N_, kColsC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
                                 (int)cols_smem<N_, kColsC>()));                                                 \
-  JPM_CUDA(cudaFuncSetAttribute(cols_kernel<N_, kColsC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                (int)cols_smem<N_, kColsC>()));
-  JPM_FFT_SWITCH(p->ny, ATTR_Y)
+  JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
+                                (int)xfused_smem<N_, kXC>()));
+  JPM_FFT_SWITCH(sl.ny, ATTR_Y)
 #undef ATTR_Y
 #define ATTR_X(N_)                                                                                              \
   JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
                                 (int)xfused_smem<N_, kXC>()));
-  JPM_FFT_SWITCH(p->nx, ATTR_X)
+  JPM_FFT_SWITCH(sl.nx, ATTR_X)
 #undef ATTR_X
 #define ATTR_Z(N_)                                                                                              \
   JPM_CUDA(cudaFuncSetAttribute(zfwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>())); \
   JPM_CUDA(cudaFuncSetAttribute(zinv_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>()));
-  JPM_FFT_SWITCH(p->nz, ATTR_Z)
+  JPM_FFT_SWITCH(sl.nz, ATTR_Z)
 #undef ATTR_Z
   return JPM_OK;
 }
 
 }  // namespace fft
 
-bool pmfft_supported(const jpm_plan* p) {
-  return fft::pow2_in_range(p->nx) && fft::pow2_in_range(p->ny) && fft::pow2_in_range(p->nz) && p->G > 0 &&
-         (p->G % 2) == 0;
+bool pmfft_shape_ok(int nx, int ny, int nz) {
+  return fft::pow2_in_range(nx) && fft::pow2_in_range(ny) && fft::pow2_in_range(nz);
 }
 
-int32_t pmfft_enable(jpm_plan* p) {
-  if (p->fft_a) return JPM_OK;
-  if (!pmfft_supported(p)) return JPM_OK;
-  p->nzc = (p->nzh + 7) & ~7;
-  const long long na = (long long)p->nx * p->ny * p->nzc;
+// Twiddle tables + kernel attributes for the slab geometry in p->slab (arrays already allocated).
+int32_t pmfft_setup(jpm_plan* p) {
+  const Slab& sl = p->slab;
   std::vector<float2> t;
   int32_t rc;
-  fft::make_twiddles(p->nx, p->nx, t);
+  fft::make_twiddles(sl.nx, sl.nx, t);
   if ((rc = fft::upload2(&p->tw_x, t))) return rc;
-  fft::make_twiddles(p->ny, p->ny, t);
+  fft::make_twiddles(sl.ny, sl.ny, t);
   if ((rc = fft::upload2(&p->tw_y, t))) return rc;
-  fft::make_twiddles(p->nz / 2, p->nz / 2, t);
+  fft::make_twiddles(sl.nz / 2, sl.nz / 2, t);
   if ((rc = fft::upload2(&p->tw_zh, t))) return rc;
-  fft::make_twiddles(p->nz, p->nz / 2 + 1, t);
+  fft::make_twiddles(sl.nz, sl.nz / 2 + 1, t);
   if ((rc = fft::upload2(&p->tw_zfull, t))) return rc;
-  if ((rc = fft::set_attrs(p))) return rc;
-  JPM_CUDA(cudaMalloc(&p->fft_a, na * sizeof(float2)));
+  return fft::set_attrs(sl);
+}
+
+// Single-GPU plan: allocate AT / B3 and describe the plan's ghost-zone meshes as a one-rank slab.
+int32_t pmfft_enable(jpm_plan* p) {
+  if (p->fft_on) return JPM_OK;
+  if (!(pmfft_shape_ok(p->nx, p->ny, p->nz) && p->G > 0 && (p->G % 2) == 0)) return JPM_OK;
+  Slab& sl = p->slab;
+  memset(&sl, 0, sizeof(sl));
+  sl.P = 1; sl.rank = 0;
+  sl.nx = p->nx; sl.ny = p->ny; sl.nz = p->nz;
+  sl.lx = p->nx; sl.ly = p->ny; sl.gx = p->G; sl.G = p->G;
+  sl.nxp = p->nxp; sl.nyp = p->nyp; sl.nzp = p->nzp; sl.npad = p->npad;
+  sl.nzh = p->nzh; sl.nzc = (p->nzh + 7) & ~7;
+  const long long na = (long long)sl.nx * sl.ny * sl.nzc;
+  JPM_CUDA(cudaMalloc(&p->fft_at, na * sizeof(float2)));
   JPM_CUDA(cudaMalloc(&p->fft_b3, 3 * na * sizeof(float2)));
-  JPM_CUDA(cudaMemset(p->fft_a, 0, na * sizeof(float2)));
+  JPM_CUDA(cudaMemset(p->fft_at, 0, na * sizeof(float2)));
   JPM_CUDA(cudaMemset(p->fft_b3, 0, 3 * na * sizeof(float2)));
+  sl.dens[0] = p->density_p; sl.force[0] = p->force3_p; sl.at[0] = p->fft_at; sl.b3[0] = p->fft_b3;
+  int32_t rc = pmfft_setup(p);
+  if (rc) return rc;
+  p->fft_on = true;
   return JPM_OK;
 }
 
 void pmfft_destroy(jpm_plan* p) {
-  void* bufs[] = {p->fft_a, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
+  void* bufs[] = {p->fft_at, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
   for (void* b : bufs)
     if (b) cudaFree(b);
-  p->fft_a = nullptr;
+  p->fft_at = nullptr; p->fft_b3 = nullptr;
+  p->fft_on = false;
 }
 
-// density_p (painted, ghosts NOT folded) -> force3_p (ghosts filled); five kernels on `st`.
+int32_t slab_barrier(jpm_plan* p, cudaStream_t st) {
+  if (p->slab.P == 1) return JPM_OK;
+  fft::slab_barrier_kernel<<<1, 32, 0, st>>>(p->slab, ++p->epoch);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+// density_p (painted, ghosts NOT folded) -> force3_p (ghosts filled).  P == 1: five kernels on `st`;
+// P > 1: the same five kernels, each rank on its own stream, with four flag barriers between them.
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
                      float filter_kmax) {
   using namespace fft;
-  JPM_CHECK_ARG(p->fft_a, "pmfft not enabled for this plan");
-  const int nx = p->nx, ny = p->ny, nz = p->nz, nzh = p->nzh, nzc = p->nzc, G = p->G;
-  const long long na = (long long)nx * ny * nzc;
-  const float norm = 1.0f / (float)p->ncell;
+  JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
+  const Slab& sl = p->slab;
+  const int nzh = sl.nzh;
+  const float norm = 1.0f / ((float)sl.nx * (float)sl.ny * (float)sl.nz);
   const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
-  const dim3 gz(ny / kRows, nx, 1), gz3(ny / kRows, nx, 3);
+  const dim3 gz(sl.ny / kRows, sl.lx, 1), gz3(sl.ny / kRows, sl.lx, 3);
+  int32_t rc;
+  if ((rc = slab_barrier(p, st))) return rc;      // every rank has painted: neighbours' ghost planes are final
 #define RUN_ZF(N_)                                                                                             \
-  zfwd_kernel<N_><<<gz, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(p->density_p, p->fft_a, nx, ny, p->nyp, \
-                                                                         p->nzp, G, nzc, p->tw_zh, p->tw_zfull);
-  JPM_FFT_SWITCH(nz, RUN_ZF)
+  zfwd_kernel<N_><<<gz, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(sl, p->tw_zh, p->tw_zfull);
+  JPM_FFT_SWITCH(sl.nz, RUN_ZF)
 #undef RUN_ZF
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "fft_z_r2c+ghost_fold");
   const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
 #define RUN_YF(N_)                                                                                             \
-  cols_kernel<N_, kColsC, false><<<dim3(nty, nx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
-      p->fft_a, na, (long long)ny * nzc, nzc, nzh, p->tw_y);
-  JPM_FFT_SWITCH(ny, RUN_YF)
+  yfwd_kernel<N_, kColsC><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>(sl, p->tw_y);
+  JPM_FFT_SWITCH(sl.ny, RUN_YF)
 #undef RUN_YF
   JPM_LAUNCH_CHECK();
-  if (p->timer) p->timer->mark(st, "fft_y_fwd");
+  if ((rc = slab_barrier(p, st))) return rc;      // AT complete on every rank
+  if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
 #define RUN_X(N_)                                                                                              \
-  xfused_kernel<N_, kXC><<<dim3(ntx, ny, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(            \
-      p->fft_a, p->fft_b3, na, (long long)ny * nzc, nzc, nzh, p->tw_x, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, \
-      norm, r_split * r_split, filter_tab, n_tab, fscale);
-  JPM_FFT_SWITCH(nx, RUN_X)
+  xfused_kernel<N_, kXC><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(      \
+      sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale);
+  JPM_FFT_SWITCH(sl.nx, RUN_X)
 #undef RUN_X
   JPM_LAUNCH_CHECK();
-  if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x3");
+  if ((rc = slab_barrier(p, st))) return rc;      // B[0], B[1] complete on every rank
+  if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x2+transpose");
 #define RUN_YI(N_)                                                                                             \
-  cols_kernel<N_, kColsC, true><<<dim3(nty, nx, 3), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>(  \
-      p->fft_b3, na, (long long)ny * nzc, nzc, nzh, p->tw_y);
-  JPM_FFT_SWITCH(ny, RUN_YI)
+  yinv_kernel<N_, kXC><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(sl, p->tw_y, p->ay);
+  JPM_FFT_SWITCH(sl.ny, RUN_YI)
 #undef RUN_YI
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "ifft_y_x3");
 #define RUN_ZI(N_)                                                                                             \
-  zinv_kernel<N_><<<gz3, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(p->fft_b3, na, p->force3_p, p->npad, nx, \
-                                                                          ny, p->nyp, p->nzp, G, nzc, p->tw_zh,  \
-                                                                          p->tw_zfull);
-  JPM_FFT_SWITCH(nz, RUN_ZI)
+  zinv_kernel<N_><<<gz3, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(sl, p->tw_zh, p->tw_zfull, p->az);
+  JPM_FFT_SWITCH(sl.nz, RUN_ZI)
 #undef RUN_ZI
   JPM_LAUNCH_CHECK();
+  if ((rc = slab_barrier(p, st))) return rc;      // force ghost planes written by the neighbours are final
   if (p->timer) p->timer->mark(st, "ifft_z_c2r_x3+ghost_fill");
   return JPM_OK;
 }
