@@ -38,8 +38,9 @@ def run_multi(args, world, rank, dev):
     torch.cuda.empty_cache()
     n_pre, d, k = schedule(cosmo, args, kick_drift_coefficients)
     ops.axpby(1.0, disp, d[0], vel, out=disp)
-    stepper = halo.ShardedStepper(disp, vel, h, sh, resident=not args.no_resident, tile=args.tile,
-                                  margin=args.margin)
+    stepper = halo.make_stepper(disp, vel, h, sh, resident=not args.no_resident, tile=args.tile,
+                                margin=args.margin, fused=not args.nccl)
+    fused = type(stepper).__name__ == "SlabStepper"
 
     def step(n):
         stepper.step(k[n], d[n + 1] if n + 1 < n_pre + K else 0.0)
@@ -100,11 +101,15 @@ def run_multi(args, world, rank, dev):
                                    f"drift-kick steps to a=1 (relative mode), Planck15, L={N} Mpc/h; timed = the "
                                    f"last {K} steps, {n_pre} untimed before",
                        "l2": "inputs larger than L2", "parallelism": f"slab pdims={pdims}, halo={h}",
-                       "resident": not args.no_resident},
+                       "resident": not args.no_resident,
+                       "exchange": ("halo reduce / FFT transposes / halo fill inside the FFT kernels over NVLink peer "
+                                    "memory (slab.py), 4 flag barriers per step, no NCCL on the data path") if fused
+                       else "NCCL send/recv halos + all-to-all FFT transposes (halo.py, pfft.py)"},
             "roofline": {"bound": "hbm", "kernel": "whole step (per-GPU share of 124 B/particle-step)",
                          "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": step_alg_bytes * K / t_dev / 1e9 / world / peak, "traffic": None},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
             "timing": stepper.timing_summary(),
         }))
+    stepper.close()
     dist.destroy_process_group()

@@ -212,6 +212,34 @@ int32_t jpm_pm_step_host_f32(jpm_plan* plan, void* stream, float* pos_host, floa
                              int32_t relative);
 
 /* ------------------------------------------------------------------------
+ * multi-GPU x-slab plan: the fused FFT chain + halo protocol over NVLink peer memory
+ *   replaces, for pdims = (P, 1): [ext] jaxdecomp.pfft3d / pifft3d (jaxpm/distributed.py:37-42) and
+ *   halo_exchange + slice_unpad (jaxpm/distributed.py:45-85, painting.py:192-215, :239-260)
+ * ---------------------------------------------------------------------- */
+/* Host call, one per rank (= GPU of the box, <= 8).  Global mesh [nx][ny][nz] (powers of two); rank r owns
+ * x planes [r nx/P, (r+1) nx/P) plus gx ghost planes per side (the reference's halo; gx <= nx/P).
+ * Allocates ONE device block holding the rank's density / force / spectrum buffers and barrier flags. */
+int32_t jpm_slab_create(jpm_plan** plan, int32_t nx, int32_t ny, int32_t nz, int32_t nranks, int32_t rank,
+                        int32_t gx);
+/* cudaIpcMemHandle_t (64 bytes) of the rank's block: gather them over the ranks (any transport), then */
+int32_t jpm_slab_ipc_handle(jpm_plan* plan, void* handle_out, int32_t handle_bytes);
+/* map every peer's block: handles[nranks][64] in rank order (other processes, cudaIpcOpenMemHandle) ... */
+int32_t jpm_slab_attach_ipc(jpm_plan* plan, const void* handles, int32_t nranks);
+/* ... or bases[nranks] = device pointers valid in THIS process (ranks sharing a process / a device). */
+int32_t jpm_slab_attach_ptrs(jpm_plan* plan, void* const* bases, int32_t nranks);
+int32_t jpm_slab_base(jpm_plan* plan, void** base_out, int64_t* bytes_out);
+/* interior [nx/P][ny][nz] of this rank: which = 0 density, 1..3 force component -> dst (compact) */
+int32_t jpm_slab_get_interior_f32(jpm_plan* plan, void* stream, int32_t which, float* dst);
+/* compact local density block -> the rank's density mesh (ghosts zero) */
+int32_t jpm_slab_set_density_f32(jpm_plan* plan, void* stream, const float* src);
+/* COLLECTIVE (every rank must call, each on its own stream): density with unfolded ghosts -> the three
+ * force meshes with ghosts filled (jaxpm/pm.py:41-56).  Kernels only enqueue; ranks meet in four
+ * in-stream flag barriers over peer memory. */
+int32_t jpm_slab_forces(jpm_plan* plan, void* stream, float r_split);
+/* Synchronises `stream`; error if one of this rank's flag barriers timed out (peer lost). */
+int32_t jpm_slab_check(jpm_plan* plan, void* stream);
+
+/* ------------------------------------------------------------------------
  * tile-sorted resident particle state (the fast path for many steps)
  * ---------------------------------------------------------------------- */
 typedef struct jpm_sim jpm_sim; /* opaque; owns a tile-sorted copy of (pos, vel) */

@@ -42,6 +42,8 @@ struct jpm_plan {
   StageTimer* timer = nullptr;
   Slab slab;                  // valid when fft_on
   bool fft_on = false;        // pmfft chain available (power-of-two shape)
+  bool is_slab = false;       // created by jpm_slab_create: one rank of a multi-GPU x-slab decomposition
+  bool ipc_peers = false;     // peer_base[] opened with cudaIpcOpenMemHandle (else borrowed pointers)
   unsigned epoch = 0;         // barrier epoch (P > 1)
   void* sym_base = nullptr;   // P > 1: the IPC-shared allocation every array of `slab` lives in
   void* peer_base[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

@@ -39,7 +39,7 @@ struct SimGeom {
   // storage of the mesh the kernels address directly (fallback atomics / gathers, non-TMA rows):
   // element (i, j, k) lives at ((i + mo) * msx + (j + mo) * msy + (k + mo)); batch stride mb
   long long msx, msy, mb;
-  int mo;
+  int mo, mox;               // storage offset of cell 0 along y/z (mo) and along x (mox)
 };
 
 struct jpm_sim {
@@ -344,7 +344,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, int c0,
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 __device__ __forceinline__ long long mesh_index(const SimGeom& g, int i, int j, int k) {
-  return (long long)(i + g.mo) * g.msx + (long long)(j + g.mo) * g.msy + (k + g.mo);
+  return (long long)(i + g.mox) * g.msx + (long long)(j + g.mo) * g.msy + (k + g.mo);
 }
 
 // ---- paint -------------------------------------------------------------------------------------
@@ -489,7 +489,7 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
     }
     fence_async_smem();
     __syncthreads();
-    if (threadIdx.x == 0) tma_reduce_add_3d(&tm, oz + g.mo, oy + g.mo, ox + g.mo, lo);
+    if (threadIdx.x == 0) tma_reduce_add_3d(&tm, oz + g.mo, oy + g.mo, ox + g.mox, lo);
     return;
   }
   // flush: two box rows per warp pass, one z-pair per lane (8-byte vector reductions when the pair
@@ -548,7 +548,7 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
       mbar_init(&mbar, 1);
       fence_async_smem();
       mbar_expect_tx(&mbar, 3u * NBOX * (unsigned)sizeof(float));
-      tma_load_4d(box, &tm, oz + g.mo, oy + g.mo, ox + g.mo, 0, &mbar);
+      tma_load_4d(box, &tm, oz + g.mo, oy + g.mo, ox + g.mox, 0, &mbar);
     }
   } else {
     // stage the three force boxes with cp.async (LDGSTS): one box row (B contiguous floats) per
@@ -722,7 +722,7 @@ static SimGeom make_geom(int nx, int ny, int nz, int pny, int pnz, int hx, int h
   g.ntx = (nx + g.T - 1) / g.T; g.nty = (ny + g.T - 1) / g.T; g.ntz = (nz + g.T - 1) / g.T;
   g.nt = g.ntx * g.nty * g.ntz;
   g.BX = g.BY = g.BZ = g.T + 2 * m + 1;
-  g.msx = (long long)ny * nz; g.msy = nz; g.mb = (long long)nx * ny * nz; g.mo = 0;   // compact mesh
+  g.msx = (long long)ny * nz; g.msy = nz; g.mb = (long long)nx * ny * nz; g.mo = 0; g.mox = 0;   // compact mesh
   return g;
 }
 
@@ -785,6 +785,7 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
       if ((rc = encode_tensor_map(&s->tm_f3, plan->force3_p, 4, d4, st4, b4))) return rc;
       s->gp = s->g;
       s->gp.msx = (long long)plan->nyp * plan->nzp; s->gp.msy = plan->nzp; s->gp.mb = plan->npad; s->gp.mo = plan->G;
+      s->gp.mox = plan->G;
       s->tma = true;
 #define SET_ATTR_TMA(TS_, M_)                                                                              \
   {                                                                                                         \
@@ -961,6 +962,7 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
     if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
     return rc;
   }
+  JPM_CHECK_ARG(!p->is_slab, "slab plan: the tile/margin pair must be one the TMA path supports");
   JPM_CUDA(cudaMemsetAsync(p->density, 0, p->ncell * sizeof(float), st));
   if (tm) tm->mark(st, "mesh_memset");
   if ((rc = sim_paint_impl(s, st, p->density, false))) return rc;

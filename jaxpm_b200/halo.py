@@ -210,9 +210,11 @@ class ShardedStepper:
       both) with the inner h//2 of the pad filled — identical to the reference for every particle
       within its halo reach (max|disp| < h//2, the reference's own validity limit)."""
 
-    def __init__(self, disp, vel, halo_size, sh, resident=True, tile=None, margin=2):
+    def __init__(self, disp, vel, halo_size, sh, resident=True, tile=None, margin=2, halos=None):
         self.sh, self.halo_size = sh, halo_size
-        self.hx, self.hy = _halos(halo_size, sh)
+        # `halos` overrides the reference's rule "no halo on an axis that is not split" (tests: a (1, 1)
+        # process grid where every rank is its own neighbour)
+        self.hx, self.hy = halos if halos is not None else _halos(halo_size, sh)
         self.disp, self.vel = disp, vel
         self.lshape = tuple(disp.shape[:3])
         self.resident = resident
@@ -238,7 +240,10 @@ class ShardedStepper:
     def step(self, kick, drift):
         sh, hx, hy = self.sh, self.hx, self.hy
         if self.sim is None:
-            rho = cic_paint_dx(self.disp, 1.0, self.halo_size, sh)
+            lx, ly, nz = self.lshape
+            padded = torch.zeros((lx + 2 * hx, ly + 2 * hy, nz), dtype=torch.float32, device=self.disp.device)
+            ops.cic_paint_dx_(padded, self.disp, 1.0, (hx, hy))
+            rho = halo_reduce_(padded, hx, hy, sh)
             f3p = halo_fill(force_meshes(rho, sh), hx // 2, hy // 2, sh)
             ops.read3_kick_drift_(f3p, self.disp, self.vel, kick, drift, True, halo=(hx // 2, hy // 2))
             return
@@ -251,10 +256,28 @@ class ShardedStepper:
     def timing_summary(self):
         return None
 
+    def close(self):
+        self.sim = None
 
-def nbody_kick_drift(disp, vel, d, k, mesh_shape, halo_size, sh, callback=None, resident=True):
+
+def make_stepper(disp, vel, halo_size, sh, resident=True, tile=None, margin=None, fused=True):
+    """The fastest stepper that serves this decomposition: the peer-memory slab stepper (slab.py: halo
+    reduce / FFT transposes / halo fill inside the FFT kernels, no NCCL on the data path) for a (P, 1)
+    process grid on power-of-two meshes, else the NCCL stepper above."""
+    from . import slab
+    hx, _ = _halos(halo_size, sh)
+    gshape = sh.global_shape(tuple(disp.shape[:3]))
+    # the slab stepper's ghost planes play the role of the reference's halo; its validity limit is the
+    # reference's (|displacement| < halo // 2 is exchanged, painting.py:192-215)
+    if fused and resident and slab.slab_supported(gshape, sh.pdims, hx):
+        return slab.SlabStepper(disp, vel, hx, sh.size, sh.rank, group=sh.group, tile=tile,
+                                margin=1 if margin is None else margin)
+    return ShardedStepper(disp, vel, halo_size, sh, resident=resident, tile=tile, margin=2 if margin is None else margin)
+
+
+def nbody_kick_drift(disp, vel, d, k, mesh_shape, halo_size, sh, callback=None, resident=True, fused=True):
     """Sharded drift-kick loop (the first drift has already been applied by the caller)."""
-    st = ShardedStepper(disp, vel, halo_size, sh, resident=resident)
+    st = make_stepper(disp, vel, halo_size, sh, resident=resident, fused=fused)
     nsteps = len(k)
     for n in range(nsteps):
         st.step(k[n], d[n + 1] if n + 1 < nsteps else 0.0)
@@ -262,6 +285,7 @@ def nbody_kick_drift(disp, vel, d, k, mesh_shape, halo_size, sh, callback=None, 
             st.store(disp, vel)
             callback(n, disp, vel)
     st.store(disp, vel)
+    st.close()
     return disp, vel
 
 

@@ -153,7 +153,7 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
     ops.axpby(1.0, pos, d[0], vel, out=pos)
     if not _single(sharding):
         from . import halo
-        return halo.nbody_kick_drift(pos, vel, d, k, mesh_shape, halo_size, sharding, callback)
+        return halo.nbody_kick_drift(pos, vel, d, k, mesh_shape, halo_size, sharding, callback, resident=resident)
     if not resident:
         plan = ops.get_plan(mesh_shape, pos.device)
         for n in range(nsteps):

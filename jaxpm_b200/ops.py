@@ -290,14 +290,15 @@ class Sim:
     """Tile-sorted resident particle state (jpm_sim): load once, step many times, store back."""
 
     def __init__(self, mesh_shape, particle_shape, relative, device, halo=(0, 0), tile=None, margin=2,
-                 with_plan=True):
+                 with_plan=True, plan=None):
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.pshape = tuple(int(s) for s in particle_shape)
         self.relative, self.device, self.halo = bool(relative), device, halo
         if tile is None:
             tile = 16 if min(self.mesh_shape) >= 64 else 8
         self.tile, self.margin = tile, margin
-        self.plan = get_plan(self.mesh_shape, device) if with_plan else None
+        # `plan`: any object with a jpm_plan `.handle` (ops.Plan, slab.SlabPlan); kept alive by the sim
+        self.plan = plan if plan is not None else (get_plan(self.mesh_shape, device) if with_plan else None)
         h = C.c_void_p()
         with torch.cuda.device(device):
             call("jpm_sim_create", C.byref(h), self.plan.handle if self.plan else None, *self.mesh_shape,

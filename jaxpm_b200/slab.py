@@ -1,0 +1,159 @@
+"""Multi-GPU x-slab force loop over NVLink peer memory (pdims = (P, 1), one process per GPU).
+
+What the reference does with three library collectives per force evaluation — halo_exchange after the
+paint, [ext] jaxdecomp.pfft3d / pifft3d all-to-alls, halo_exchange before the read
+(/root/reference/jaxpm/distributed.py:37-85, painting.py:192-215, :239-260, pm.py:41-56) — is done
+here INSIDE the FFT kernels of csrc/pmfft.cu: the z pass folds the neighbours' density ghost planes
+while it loads, the y and x passes store their results straight into the buffer of the rank that owns
+the row (the transposes), the last pass writes the neighbours' force ghost planes.  Ranks meet in
+four in-stream flag barriers per step; no NCCL call, no pack/unpack kernel, no staging copy.
+
+`torch.distributed` is only used once, to gather the 64-byte CUDA IPC handles of the ranks' blocks.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib, ops
+from ._lib import as_f32, call, ptr, stream
+
+_HANDLE_BYTES = 64
+
+
+def slab_supported(global_shape, pdims, halo_x):
+    """True when the fused slab path can serve this decomposition."""
+    nx, ny, nz = (int(s) for s in global_shape)
+    px, py = pdims
+    pow2 = lambda n: 16 <= n <= 1024 and (n & (n - 1)) == 0
+    if py != 1 or px < 1 or px > 8 or not (pow2(nx) and pow2(ny) and pow2(nz)):
+        return False
+    if nx % px or ny % px:
+        return False
+    lx = nx // px
+    return 1 <= halo_x <= lx and lx + 2 * halo_x >= 16
+
+
+class SlabPlan:
+    """One rank's jpm_plan of the slab decomposition (buffers + peer mappings)."""
+
+    def __init__(self, global_shape, nranks, rank, gx, device):
+        self.global_shape = tuple(int(s) for s in global_shape)
+        self.nranks, self.rank, self.gx, self.device = int(nranks), int(rank), int(gx), torch.device(device)
+        nx, ny, nz = self.global_shape
+        self.lx = nx // self.nranks
+        self.local_shape = (self.lx, ny, nz)
+        self.mesh_shape = (self.lx + 2 * self.gx, ny, nz)     # what the particle kernels see
+        h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            call("jpm_slab_create", C.byref(h), nx, ny, nz, self.nranks, self.rank, self.gx)
+        self.handle = h
+        self.attached = False
+
+    def ipc_handle(self):
+        buf = (C.c_ubyte * _HANDLE_BYTES)()
+        call("jpm_slab_ipc_handle", self.handle, buf, _HANDLE_BYTES)
+        return bytes(buf)
+
+    def base(self):
+        b, n = C.c_void_p(), C.c_int64()
+        call("jpm_slab_base", self.handle, C.byref(b), C.byref(n))
+        return b.value
+
+    def attach_ipc(self, handles):
+        """handles: list of nranks 64-byte strings in rank order (from every rank's ipc_handle())."""
+        blob = b"".join(handles)
+        assert len(blob) == _HANDLE_BYTES * self.nranks
+        buf = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        with torch.cuda.device(self.device):
+            call("jpm_slab_attach_ipc", self.handle, buf, self.nranks)
+        self.attached = True
+
+    def attach_local(self, plans):
+        """Peers living in this process (tests: several ranks on one device, or one process driving
+        several peer-enabled devices)."""
+        arr = (C.c_void_p * self.nranks)(*[p.base() for p in plans])
+        with torch.cuda.device(self.device):
+            call("jpm_slab_attach_ptrs", self.handle, arr, self.nranks)
+        self.attached = True
+
+    def set_density(self, rho_local):
+        call("jpm_slab_set_density_f32", self.handle, stream(), ptr(as_f32(rho_local), torch.float32))
+
+    def forces(self, r_split=0.0):
+        """COLLECTIVE: every rank calls it on its own stream."""
+        call("jpm_slab_forces", self.handle, stream(), float(r_split))
+
+    def interior(self, which):
+        out = torch.empty(self.local_shape, dtype=torch.float32, device=self.device)
+        call("jpm_slab_get_interior_f32", self.handle, stream(), int(which), ptr(out))
+        return out
+
+    def check(self):
+        call("jpm_slab_check", self.handle, stream())
+
+    def destroy(self):
+        if self.handle:
+            _lib.load().jpm_plan_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
+def connect(plan, group=None):
+    """Exchange the IPC handles of every rank's block over `torch.distributed` and map the peers."""
+    import torch.distributed as dist
+    handles = [None] * plan.nranks
+    dist.all_gather_object(handles, plan.ipc_handle(), group=group)
+    plan.attach_ipc(handles)
+    dist.barrier(group=group)
+    return plan
+
+
+class SlabStepper:
+    """Per-rank resident state of the slab drift-kick loop: tile-sorted particles (csrc/sim.cu) on the
+    rank's ghost-zone mesh + the fused peer-memory FFT chain.  Same contract as halo.ShardedStepper:
+    identical to the reference for every particle within its halo reach (|disp_x| < gx)."""
+
+    def __init__(self, disp, vel, gx, nranks, rank, group=None, tile=None, margin=1, plan=None):
+        d = as_f32(disp)
+        lx, ny, nz = d.shape[:3]
+        self.device = d.device
+        self.group = group
+        self.plan = plan if plan is not None else SlabPlan((lx * nranks, ny, nz), nranks, rank, gx, d.device)
+        if not self.plan.attached and plan is None:
+            connect(self.plan, group)
+        ms = self.plan.mesh_shape
+        if tile is None:
+            tile = 16 if min(ms) >= 64 else 8
+        self.sim = ops.Sim(ms, (lx, ny, nz), True, d.device, halo=(gx, 0), tile=tile, margin=margin,
+                           plan=self.plan)
+        self.sim.load(d, as_f32(vel))
+
+    def load(self, disp, vel):
+        self.sim.load(as_f32(disp), as_f32(vel))
+
+    def store(self, disp, vel):
+        self.sim.store(disp, vel)
+        self.plan.check()
+
+    def step(self, kick, drift):
+        self.sim.step(kick, drift)
+
+    def step_profile(self, kick, drift):
+        return self.sim.step_profile(kick, drift)
+
+    def timing_summary(self):
+        return None
+
+    def close(self, barrier=True):
+        """Ranks must have finished using each other's memory before any block is freed."""
+        import torch.distributed as dist
+        torch.cuda.synchronize(self.device)
+        if barrier and self.plan.nranks > 1 and dist.is_available() and dist.is_initialized():
+            dist.barrier(group=self.group)
+        self.sim = None
+        self.plan.destroy()

@@ -1,0 +1,132 @@
+"""The multi-GPU paths exercised on ONE device, so that the round-end single-GPU box covers them:
+
+* the slab decomposition over peer memory (jaxpm_b200/slab.py, csrc/pmfft.cu) with P ranks living in
+  this process, each on its own stream, their blocks attached by pointer instead of by CUDA IPC handle;
+* the NCCL halo protocol of jaxpm_b200/halo.py with a (1, 1) process grid, where every rank is its own
+  neighbour (the send/recv degenerates to a copy, the pack/unpack/accumulate logic is the same).
+
+Reference behaviour: sharded == unsharded (/root/reference/tests/test_distributed_pm.py:37-179).
+The real multi-process runs are tests/test_multi_gpu.py (needs >= 2 GPUs)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import displaced, rel_err
+
+pytestmark = pytest.mark.gpu
+
+FIELD_TOL = 1e-5
+
+
+def T(x, dev):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(dev)
+
+
+def _make_plans(shape, P, gx, dev):
+    from jaxpm_b200.slab import SlabPlan
+    plans = [SlabPlan(shape, P, r, gx, dev) for r in range(P)]
+    for p in plans:
+        p.attach_local(plans)
+    return plans
+
+
+@pytest.mark.parametrize("shape,P,gx", [((32, 32, 32), 1, 4), ((32, 32, 32), 2, 8), ((32, 32, 32), 2, 16),
+                                        ((64, 32, 16), 4, 5), ((64, 64, 64), 8, 8), ((128, 32, 64), 2, 7)])
+def test_slab_forces_equal_single_gpu(cuda, shape, P, gx):
+    """density block per rank -> fused peer-memory FFT chain -> force blocks == the single-GPU chain."""
+    from jaxpm_b200 import ops
+    rng = np.random.default_rng(5)
+    rho = rng.standard_normal(shape).astype(np.float32)
+    ref = ops.force_meshes_from_density(T(rho, cuda), ops.get_plan(shape, cuda)).cpu().numpy()
+    plans = _make_plans(shape, P, gx, cuda)
+    streams = [torch.cuda.Stream(cuda) for _ in range(P)]
+    lx = shape[0] // P
+    torch.cuda.synchronize()
+    for rep in range(2):      # twice: the barrier epochs and buffer reuse of a second evaluation
+        for r, (p, s) in enumerate(zip(plans, streams)):
+            with torch.cuda.stream(s):
+                p.set_density(T(rho[r * lx:(r + 1) * lx], cuda))
+        for p, s in zip(plans, streams):
+            with torch.cuda.stream(s):
+                p.forces()
+        for r, (p, s) in enumerate(zip(plans, streams)):
+            with torch.cuda.stream(s):
+                p.check()
+                for d in range(3):
+                    got = p.interior(1 + d).cpu().numpy()
+                    err = np.abs(got - ref[d][r * lx:(r + 1) * lx]).max() / np.abs(ref[d]).max()
+                    assert err < FIELD_TOL, (rep, r, d, err)
+    torch.cuda.synchronize()
+    for p in plans:
+        p.destroy()
+
+
+@pytest.mark.parametrize("shape,P,gx,tile", [((32, 32, 32), 2, 8, 8), ((64, 64, 64), 2, 16, 16), ((64, 32, 32), 4, 8, 8),
+                                             ((32, 32, 32), 1, 8, 8)])
+def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile):
+    """K drift-kick steps of the slab stepper (ghost-fold / transposes / ghost-fill inside the FFT kernels)
+    == the single-GPU resident stepper on the same particles."""
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.ode import kick_drift_coefficients, nbody_kick_drift
+    from jaxpm_b200.slab import SlabStepper
+    from jaxpm_b200 import ops
+    _, disp = displaced(shape, 1.0)
+    disp = np.clip(disp, -gx / 2 + 0.5, gx / 2 - 0.5).astype(np.float32)
+    vel = (0.2 * np.random.default_rng(9).standard_normal(disp.shape)).astype(np.float32)
+    cosmo = Planck15()
+    K = 3
+    rp, rv = nbody_kick_drift(cosmo, T(disp, cuda), T(vel, cuda), 0.5, 0.8, K, paint_absolute_pos=False,
+                              resident=True, tile=tile, margin=1)
+    d, k = kick_drift_coefficients(cosmo, 0.5, 0.8, K, "symplectic")
+    lx = shape[0] // P
+    plans = _make_plans(shape, P, gx, cuda)
+    streams = [torch.cuda.Stream(cuda) for _ in range(P)]
+    dl = [T(disp[r * lx:(r + 1) * lx], cuda) for r in range(P)]
+    vl = [T(vel[r * lx:(r + 1) * lx], cuda) for r in range(P)]
+    for r in range(P):
+        ops.axpby(1.0, dl[r], d[0], vl[r], out=dl[r])
+    torch.cuda.synchronize()
+    steppers = []
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            steppers.append(SlabStepper(dl[r], vl[r], gx, P, r, tile=tile, margin=1, plan=plans[r]))
+    for n in range(K):
+        for r in range(P):
+            with torch.cuda.stream(streams[r]):
+                steppers[r].step(k[n], d[n + 1] if n + 1 < K else 0.0)
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            steppers[r].store(dl[r], vl[r])
+    torch.cuda.synchronize()
+    p = torch.cat(dl).cpu().numpy()
+    v = torch.cat(vl).cpu().numpy()
+    assert np.abs(p - rp.cpu().numpy()).max() < 2e-4
+    assert rel_err(v, rv.cpu().numpy()) < 1e-4
+    for s in steppers:
+        s.close(barrier=False)
+
+
+@pytest.mark.parametrize("resident", [False, True])
+def test_halo_protocol_self_neighbour(cuda, resident):
+    """halo.ShardedStepper on a (1, 1) process grid with halo 8: pad / paint / halo reduce / halo fill /
+    read run exactly as on a real process grid, the neighbour being the rank itself."""
+    from jaxpm_b200 import halo, ops
+    from jaxpm_b200.cosmology import Planck15
+    from jaxpm_b200.distributed import Sharding
+    from jaxpm_b200.ode import kick_drift_coefficients, nbody_kick_drift
+    shape, h, K = (32, 32, 24), 8, 3
+    _, disp = displaced(shape, 1.0)
+    disp = np.clip(disp, -h / 2 + 0.5, h / 2 - 0.5).astype(np.float32)
+    vel = (0.2 * np.random.default_rng(9).standard_normal(disp.shape)).astype(np.float32)
+    cosmo = Planck15()
+    rp, rv = nbody_kick_drift(cosmo, T(disp, cuda), T(vel, cuda), 0.5, 0.8, K, paint_absolute_pos=False, resident=False)
+    d, k = kick_drift_coefficients(cosmo, 0.5, 0.8, K, "symplectic")
+    sh = Sharding((1, 1), rank=0)
+    p, v = T(disp, cuda), T(vel, cuda)
+    ops.axpby(1.0, p, d[0], v, out=p)
+    st = halo.ShardedStepper(p, v, h, sh, resident=resident, halos=(h, h))
+    for n in range(K):
+        st.step(k[n], d[n + 1] if n + 1 < K else 0.0)
+    st.store(p, v)
+    assert np.abs(p.cpu().numpy() - rp.cpu().numpy()).max() < 2e-4
+    assert rel_err(v.cpu().numpy(), rv.cpu().numpy()) < 1e-4
