@@ -90,6 +90,19 @@ def run_multi(args, world, rank, dev):
     e2e = {"value": npart * e2e_steps / float(te), "unit": UNIT, "h2d_bytes_per_step": bytes_state,
            "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
            "entry": "per-rank pinned host state -> sharded PM step -> host state (all ranks concurrently)"}
+    # per-stage durations of one more step (CUDA events at the stage boundaries of this rank's stream; a stage
+    # ends with the flag barrier that follows it, so waiting for the slowest rank is inside), max over ranks
+    timing = None
+    if fused:
+        acc, reps = {}, 5
+        for _ in range(reps):
+            for name, ms in stepper.step_profile(0.0, 0.0):
+                acc[name] = acc.get(name, 0.0) + ms / reps
+        names = list(acc)
+        tt = torch.tensor([acc[n] for n in names], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        timing = {"stage_ms_max_over_ranks": {n: round(float(v), 4) for n, v in zip(names, tt)},
+                  "ghost_planes_used": stepper.plan.ghost_width(), "ghost_planes_allocated": h}
     peak, peak_kind = _peaks()
     step_alg_bytes = (60 + 64) * npart
     if rank == 0:
@@ -109,7 +122,7 @@ def run_multi(args, world, rank, dev):
                          "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": step_alg_bytes * K / t_dev / 1e9 / world / peak, "traffic": None},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "timing": stepper.timing_summary(),
+            "timing": timing,
         }))
     stepper.close()
     dist.destroy_process_group()

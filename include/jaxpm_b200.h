@@ -211,6 +211,11 @@ int32_t jpm_pm_step_host_f32(jpm_plan* plan, void* stream, float* pos_host, floa
                              float* pos_dev, float* vel_dev, float kick_coef, float drift_coef,
                              int32_t relative);
 
+/* Test / debug access to the ghost-zone meshes the resident step (jpm_sim_step) works on: which = 0 the
+ * painted density (ghosts not folded), 1..3 a force component (ghosts filled).  dims3 (nullable) receives the
+ * padded extents; dst (nullable) the whole padded array [dims3[0]][dims3[1]][dims3[2]]. */
+int32_t jpm_plan_padded_get_f32(jpm_plan* plan, void* stream, int32_t which, float* dst, int32_t* dims3);
+
 /* ------------------------------------------------------------------------
  * multi-GPU x-slab plan: the fused FFT chain + halo protocol over NVLink peer memory
  *   replaces, for pdims = (P, 1): [ext] jaxdecomp.pfft3d / pifft3d (jaxpm/distributed.py:37-42) and
@@ -238,6 +243,9 @@ int32_t jpm_slab_set_density_f32(jpm_plan* plan, void* stream, const float* src)
 int32_t jpm_slab_forces(jpm_plan* plan, void* stream, float r_split);
 /* Synchronises `stream`; error if one of this rank's flag barriers timed out (peer lost). */
 int32_t jpm_slab_check(jpm_plan* plan, void* stream);
+/* Ghost planes per side the last force evaluation exchanged: gx, or - when the density was painted by a
+ * jpm_sim bound to this plan - the maximum over the ranks of what their particles actually reach. */
+int32_t jpm_slab_ghost_width(jpm_plan* plan, void* stream, int32_t* out);
 
 /* ------------------------------------------------------------------------
  * tile-sorted resident particle state (the fast path for many steps)

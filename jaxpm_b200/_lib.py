@@ -42,6 +42,7 @@ SIGNATURES = {
     "jpm_density_to_force_meshes_fused": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_pm_step_f32": ([vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_pm_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32, i32], i32),
+    "jpm_plan_padded_get_f32": ([vp, vp, i32, vp, C.POINTER(i32)], i32),
     "jpm_slab_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
     "jpm_slab_ipc_handle": ([vp, vp, i32], i32),
     "jpm_slab_attach_ipc": ([vp, vp, i32], i32),
@@ -51,6 +52,7 @@ SIGNATURES = {
     "jpm_slab_set_density_f32": ([vp, vp, vp], i32),
     "jpm_slab_forces": ([vp, vp, f32], i32),
     "jpm_slab_check": ([vp, vp], i32),
+    "jpm_slab_ghost_width": ([vp, vp, C.POINTER(i32)], i32),
     "jpm_sim_create": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
     "jpm_sim_destroy": ([vp], i32),
     "jpm_sim_load": ([vp, vp, vp, vp], i32),

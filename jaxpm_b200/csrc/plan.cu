@@ -650,8 +650,12 @@ extern "C" int32_t jpm_slab_create(jpm_plan** out, int32_t nx, int32_t ny, int32
   p->sym_bytes = L.total;
   JPM_CUDA(cudaMalloc(&p->sym_base, L.total));
   JPM_CUDA(cudaMemset(p->sym_base, 0, L.total));
-  JPM_CUDA(cudaDeviceSynchronize());
   slab_point(sl, rank, p->sym_base);
+  {
+    const int init[3] = {0x7fffffff, (int)0x80000000, gx};   // touched x range unknown, ghost width = all of it
+    JPM_CUDA(cudaMemcpy(sl.flags[rank] + kFlagXmin, init, sizeof(init), cudaMemcpyHostToDevice));
+  }
+  JPM_CUDA(cudaDeviceSynchronize());
   p->density_p = (float*)((char*)p->sym_base + L.dens);
   p->force3_p = (float*)((char*)p->sym_base + L.force);
   *out = p;
@@ -729,6 +733,8 @@ extern "C" int32_t jpm_slab_set_density_f32(jpm_plan* p, void* stream, const flo
   const Slab& sl = p->slab;
   cudaStream_t st = (cudaStream_t)stream;
   JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+  JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagXmin, 0x7f, sizeof(int), st));   // 0x7f7f7f7f > any plane: unknown
+  JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagXmax, 0x80, sizeof(int), st));   // 0x80808080 < 0
   float* dstp = p->density_p + (long long)sl.gx * sl.nyp * sl.nzp;
   const long long total = (long long)sl.lx * sl.ny * sl.nz / 4;
   const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
@@ -749,10 +755,33 @@ extern "C" int32_t jpm_slab_check(jpm_plan* p, void* stream) {
   JPM_CHECK_ARG(p && p->is_slab, "not a slab plan");
   unsigned err = 0;
   JPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  JPM_CUDA(cudaMemcpy(&err, p->slab.flags[p->slab.rank] + 64, sizeof(err), cudaMemcpyDeviceToHost));
+  JPM_CUDA(cudaMemcpy(&err, p->slab.flags[p->slab.rank] + kFlagErr, sizeof(err), cudaMemcpyDeviceToHost));
   if (err) {
     set_error("slab barrier timed out on rank %d (epoch %u): a peer did not arrive", p->slab.rank, p->epoch);
     return JPM_ERR_CUDA;
   }
+  return JPM_OK;
+}
+
+// Ghost planes per side the last force evaluation used (<= gx; adaptive when the density was painted by a
+// jpm_sim).  Synchronises `stream`.
+extern "C" int32_t jpm_slab_ghost_width(jpm_plan* p, void* stream, int32_t* out) {
+  JPM_CHECK_ARG(p && p->is_slab && out, "not a slab plan");
+  int v = 0;
+  JPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  JPM_CUDA(cudaMemcpy(&v, p->slab.flags[p->slab.rank] + kFlagGe, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = p->slab.P == 1 ? p->slab.gx : v;
+  return JPM_OK;
+}
+
+// Debug / test access to the ghost-zone meshes of a plan: which = 0 the painted density (ghosts NOT folded),
+// 1..3 a force component (ghosts filled); dst receives the whole padded array [nxp][nyp][nzp].
+extern "C" int32_t jpm_plan_padded_get_f32(jpm_plan* p, void* stream, int32_t which, float* dst, int32_t* dims3) {
+  JPM_CHECK_ARG(p && which >= 0 && which <= 3, "bad arguments");
+  JPM_CHECK_ARG(p->G > 0 && p->density_p, "plan has no ghost-zone meshes (no resident sim stepped on it yet)");
+  if (dims3) { dims3[0] = p->nxp; dims3[1] = p->nyp; dims3[2] = p->nzp; }
+  if (!dst) return JPM_OK;
+  const float* src = which == 0 ? p->density_p : p->force3_p + (long long)(which - 1) * p->npad;
+  JPM_CUDA(cudaMemcpyAsync(dst, src, p->npad * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
   return JPM_OK;
 }

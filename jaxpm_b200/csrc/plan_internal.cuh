@@ -38,6 +38,13 @@ struct Slab {
   unsigned* flags[8];    // [65] barrier slots (one per peer) + error word
 };
 
+// word offsets inside a rank's flag block (flags[r], 256 unsigned words)
+constexpr int kFlagErr = 64;       // barrier timeout marker
+constexpr int kFlagXmin = 96;      // int: lowest / highest local x plane touched by the last paint (atomicMin / Max by
+constexpr int kFlagXmax = 97;      //      sim_paint_kernel; INT_MAX / INT_MIN = unknown)
+constexpr int kFlagGe = 98;        // int: ghost planes per side in use this step = max over ranks of what each needs
+constexpr int kFlagGeSlots = 128;  // [P] the ranks' needs, written by the peers in the first barrier of a step
+
 struct jpm_plan {
   StageTimer* timer = nullptr;
   Slab slab;                  // valid when fft_on
@@ -89,7 +96,7 @@ int32_t plan_padded_forces(jpm_plan* p, cudaStream_t stream, float r_split, cons
 int32_t pmfft_enable(jpm_plan* p);
 int32_t pmfft_setup(jpm_plan* p);
 bool pmfft_shape_ok(int nx, int ny, int nz);
-int32_t slab_barrier(jpm_plan* p, cudaStream_t stream);
+int32_t slab_barrier(jpm_plan* p, cudaStream_t stream, bool exchange_ghost_width = false);
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
                      float filter_kmax);
 void pmfft_destroy(jpm_plan* p);

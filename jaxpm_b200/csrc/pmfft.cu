@@ -377,6 +377,7 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // grid: (ny / 16, lx).  Real arrays are [lx + 2 gx][nyp][nzp]: gx ghost planes per side in x (images of the
 // neighbour slabs; of this slab itself when P == 1), G ghost cells per side in y and z (periodic images).
 constexpr int kRows = 16;
+__device__ __forceinline__ int ghost_width(const Slab& sl);
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
@@ -391,8 +392,9 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   // x planes that fold onto interior plane xl: this rank's own, the left neighbour's high ghost, the right
   // neighbour's low ghost
   const float* src[3] = {sl.dens[sl.rank] + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
-  if (xl < gx) src[1] = sl.dens[(sl.rank + sl.P - 1) % sl.P] + (long long)(gx + lx + xl) * nyp * nzp;
-  if (xl >= lx - gx) src[2] = sl.dens[(sl.rank + 1) % sl.P] + (long long)(xl - (lx - gx)) * nyp * nzp;
+  const int ge = ghost_width(sl);   // planes xl < ge / xl >= lx - ge receive neighbour ghosts
+  if (xl < ge) src[1] = sl.dens[(sl.rank + sl.P - 1) % sl.P] + (long long)(gx + lx + xl) * nyp * nzp;
+  if (xl >= lx - ge) src[2] = sl.dens[(sl.rank + 1) % sl.P] + (long long)(xl - (lx - gx)) * nyp * nzp;
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
   // blocks away from the x / y faces have no periodic images to fold: branch-free loads, BATCH in flight
@@ -533,8 +535,9 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   // destinations in x: own interior plane, left neighbour's high ghost, right neighbour's low ghost
   const long long cofs = (long long)comp * sl.npad;
   float* dstp[3] = {sl.force[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
-  if (xl < gx) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
-  if (xl >= lx - gx) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
+  const int ge = ghost_width(sl);
+  if (xl < ge) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
+  if (xl >= lx - ge) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
   const int GH = G / 2;
   for (int e = threadIdx.x; e < kRows * NH; e += NT) {
     const int r = e / NH, m = e - r * NH;
@@ -562,10 +565,20 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 // flags[r] (on every rank) has one slot per peer; rank `me` writes `epoch` into slot `me` of every peer and
 // waits until its own slots all reach `epoch`.  One CTA, one thread per peer.  A lost peer trips the
 // timeout (~4 s) and raises the error word instead of hanging the GPU.
+template <bool GHOSTW>
 __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch) {
   const int t = threadIdx.x;
   __threadfence_system();
   if (t < sl.P) {
+    if (GHOSTW) {
+      // ghost planes this rank's particles reach (sim_paint_kernel recorded the touched x range); every
+      // peer gets the number, the step then uses the maximum over the ranks.  Unknown range -> all gx.
+      const int* mine = reinterpret_cast<const int*>(sl.flags[sl.rank]);
+      const int xmin = mine[kFlagXmin], xmax = mine[kFlagXmax];
+      int need = sl.gx;
+      if (xmin <= xmax) need = min(sl.gx, max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.lx - 1))));
+      asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sl.flags[t] + kFlagGeSlots + sl.rank), "r"(need) : "memory");
+    }
     unsigned* remote = sl.flags[t] + sl.rank;
     asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(remote), "r"(epoch) : "memory");
     const unsigned* mine = sl.flags[sl.rank] + t;
@@ -575,13 +588,31 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int)(v - epoch) >= 0) break;
       if (clock64() - t0 > 8000000000ll) {   // ~4 s at 2 GHz
-        sl.flags[sl.rank][64] = 1u;          // error word
+        sl.flags[sl.rank][kFlagErr] = 1u;    // error word
         break;
       }
     } while (true);
   }
   __syncthreads();
+  if (GHOSTW && t == 0) {
+    int ge = 0;
+    for (int r = 0; r < sl.P; ++r) {
+      unsigned v;
+      asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(sl.flags[sl.rank] + kFlagGeSlots + r) : "memory");
+      ge = max(ge, (int)v);
+    }
+    int* mine = reinterpret_cast<int*>(sl.flags[sl.rank]);
+    mine[kFlagGe] = min(ge, sl.gx);
+    mine[kFlagXmin] = 0x7fffffff;          // the next paint starts a new range
+    mine[kFlagXmax] = (int)0x80000000;
+  }
   __threadfence_system();
+}
+
+// ghost planes per side in use this step (see slab_barrier_kernel); P == 1: the periodic images, always gx
+__device__ __forceinline__ int ghost_width(const Slab& sl) {
+  if (sl.P == 1) return sl.gx;
+  return min(sl.gx, reinterpret_cast<const int*>(sl.flags[sl.rank])[kFlagGe]);
 }
 
 static void make_twiddles(int n, int count, std::vector<float2>& out) {
@@ -659,6 +690,12 @@ int32_t pmfft_setup(jpm_plan* p) {
   if ((rc = fft::upload2(&p->tw_zh, t))) return rc;
   fft::make_twiddles(sl.nz, sl.nz / 2 + 1, t);
   if ((rc = fft::upload2(&p->tw_zfull, t))) return rc;
+  // load both barrier kernels NOW: with lazy module loading the first launch of a kernel can block the host
+  // until the device is idle, which never happens while this rank's previous barrier is still spinning for a
+  // peer driven by the same host thread (several ranks in one process)
+  cudaFuncAttributes fa;
+  JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<true>));
+  JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<false>));
   return fft::set_attrs(sl);
 }
 
@@ -693,9 +730,10 @@ void pmfft_destroy(jpm_plan* p) {
   p->fft_on = false;
 }
 
-int32_t slab_barrier(jpm_plan* p, cudaStream_t st) {
+int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width) {
   if (p->slab.P == 1) return JPM_OK;
-  fft::slab_barrier_kernel<<<1, 32, 0, st>>>(p->slab, ++p->epoch);
+  if (exchange_ghost_width) fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch);
+  else fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }
@@ -712,7 +750,8 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
   const dim3 gz(sl.ny / kRows, sl.lx, 1), gz3(sl.ny / kRows, sl.lx, 3);
   int32_t rc;
-  if ((rc = slab_barrier(p, st))) return rc;      // every rank has painted: neighbours' ghost planes are final
+  // every rank has painted: neighbours' ghost planes are final; agree on the ghost width of this step
+  if ((rc = slab_barrier(p, st, true))) return rc;
 #define RUN_ZF(N_)                                                                                             \
   zfwd_kernel<N_><<<gz, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(sl, p->tw_zh, p->tw_zfull);
   JPM_FFT_SWITCH(sl.nz, RUN_ZF)

@@ -250,30 +250,25 @@ __device__ __forceinline__ void make_corners(const SimGeom& g, const Cic1& cx, c
 //   relative (painting_utils.py:48-65): pp = base + d; corner c: r = pp + c (in [0, L), no mod),
 //       idx = floor(r), nd = pp - idx (|nd| <= 1 < L/4, no rint correction), w = 1 - |nd|;
 //   absolute (painting.py:22-37): idx = floor(p) + c, w = 1 - |p - idx|, 0 <= idx < n (no mod).
-// Lanes at the periodic edge run the generic rule for that axis only.
+// Lanes at the periodic edge of an axis take the generic path for the whole particle.
 template <bool REL>
 __device__ __forceinline__ bool axis_fast(int base, float v, int n, int& i0, float& w0, float& w1) {
+  // straight-line code, one predicate out: lanes that fail (periodic edge, dropped corner, huge / NaN
+  // coordinate) are re-done by the caller with the generic rules of common.cuh
   if (REL) {
     const float pp = (float)base + v;
     const float x1 = pp + 1.0f;
-    if (pp >= 0.0f && x1 < (float)n) {
-      const float f0 = floorf(pp), f1 = floorf(x1);
-      w0 = 1.0f - fabsf(pp - f0);
-      w1 = 1.0f - fabsf(pp - f1);
-      i0 = (int)f0;
-      return f1 == f0 + 1.0f;
-    }
-    const Cic1 c = cic_rel<false>(base, v, n);
-    i0 = c.i0; w0 = c.w0; w1 = c.w1;
-    return c.i0 >= 0 && c.i1 >= 0 && (c.i1 == c.i0 + 1 || (c.i0 == n - 1 && c.i1 == 0));
+    const float f0 = floorf(pp), f1 = floorf(x1);
+    w0 = 1.0f - fabsf(pp - f0);
+    w1 = 1.0f - fabsf(pp - f1);
+    i0 = (int)f0;
+    return pp >= 0.0f && x1 < (float)n && f1 == f0 + 1.0f;
   } else {
     const float f = floorf(v);
     w0 = 1.0f - fabsf(v - f);
     w1 = 1.0f - fabsf(v - (f + 1.0f));
     i0 = (int)f;
-    if ((unsigned)i0 < (unsigned)(n - 1)) return true;
-    i0 = pymod(i0, n);                      // i1 = pymod((int)(f + 1)) is its periodic neighbour
-    return fabsf(f) < 1.0e9f;               // int conversion exact
+    return (unsigned)i0 < (unsigned)(n - 1) && fabsf(f) < 1.0e9f;
   }
 }
 
@@ -290,8 +285,26 @@ struct FastStencil {
   float wx0, wx1, wy0, wy1, wz0, wz1;
 };
 
+// One axis by the generic rules of common.cuh (periodic edge).  Out of line and returning BY VALUE: the fast
+// path's stencil must stay in registers (an address-taken struct would live in local memory).
+struct AxisG { int i0; float w0, w1; int ok; };
 template <bool REL>
-__device__ __forceinline__ bool stencil_fast(const SimGeom& g, const float4& p, FastStencil& s) {
+__device__ __noinline__ AxisG axis_generic(int base, float v, int n) {
+  const Cic1 c = cic_1d<REL, false>(base, v, n);
+  AxisG r;
+  r.i0 = c.i0; r.w0 = c.w0; r.w1 = c.w1;
+  // "the two corners are periodic neighbours and neither is dropped"
+  r.ok = c.i0 >= 0 && c.i1 >= 0 && (c.i1 == c.i0 + 1 || (c.i0 == n - 1 && c.i1 == 0));
+  return r;
+}
+
+// Stencil of one particle relative to the box starting at (ox, oy, oz): straight-line code for all three axes,
+// then - only in warps that hold a lane at a periodic edge (~2 % of the particles late in a run: relative
+// coordinates base + disp are not wrapped) - the generic rule for the axes that need it.  Returns whether the
+// 8 corners are (lx..lx+1, ly..ly+1, lz..lz+1) inside the box; s.i0/j0/k0 = wrapped cell of corner 0.
+template <bool REL, int BX, int BY, int BZ>
+__device__ __forceinline__ bool stencil_box(const SimGeom& g, const float4& p, int ox, int oy, int oz,
+                                            FastStencil& s, int& lx, int& ly, int& lz) {
   int bi = 0, bj = 0, bk = 0;
   if (REL) {
     const int w = __float_as_int(p.w);
@@ -299,10 +312,26 @@ __device__ __forceinline__ bool stencil_fast(const SimGeom& g, const float4& p, 
     bj = ((w >> 10) & 1023) + g.hy;
     bi = (w >> 20) + g.hx;
   }
-  const bool fx = axis_fast<REL>(bi, p.x, g.nx, s.i0, s.wx0, s.wx1);
-  const bool fy = axis_fast<REL>(bj, p.y, g.ny, s.j0, s.wy0, s.wy1);
-  const bool fz = axis_fast<REL>(bk, p.z, g.nz, s.k0, s.wz0, s.wz1);
-  return fx && fy && fz;
+  bool fx = axis_fast<REL>(bi, p.x, g.nx, s.i0, s.wx0, s.wx1);
+  bool fy = axis_fast<REL>(bj, p.y, g.ny, s.j0, s.wy0, s.wy1);
+  bool fz = axis_fast<REL>(bk, p.z, g.nz, s.k0, s.wz0, s.wz1);
+  lx = s.i0 - ox; ly = s.j0 - oy; lz = s.k0 - oz;
+  if (!(fx & fy & fz)) {
+    if (!fx) {
+      const AxisG a = axis_generic<REL>(bi, p.x, g.nx);
+      s.i0 = a.i0; s.wx0 = a.w0; s.wx1 = a.w1; fx = a.ok; lx = local_wrap(max(a.i0, 0), ox, g.nx);
+    }
+    if (!fy) {
+      const AxisG a = axis_generic<REL>(bj, p.y, g.ny);
+      s.j0 = a.i0; s.wy0 = a.w0; s.wy1 = a.w1; fy = a.ok; ly = local_wrap(max(a.i0, 0), oy, g.ny);
+    }
+    if (!fz) {
+      const AxisG a = axis_generic<REL>(bk, p.z, g.nz);
+      s.k0 = a.i0; s.wz0 = a.w0; s.wz1 = a.w1; fz = a.ok; lz = local_wrap(max(a.i0, 0), oz, g.nz);
+    }
+  }
+  return fx & fy & fz & ((unsigned)lx < (unsigned)(BX - 1)) & ((unsigned)ly < (unsigned)(BY - 1)) &
+         ((unsigned)lz < (unsigned)(BZ - 1));
 }
 
 // ---- TMA / mbarrier helpers (sm_90+ PTX; SASS: UTMALDG / UTMAREDG, SYNCS) ------------------------
@@ -339,7 +368,10 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, int c0,
                ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  // wait for the reduction to be PERFORMED, not only for the box to be read (.read): the next kernel on the
+  // stream reads the mesh through the generic proxy, and a CTA that exits with the reduce still in flight
+  // was observed to lose (part of) its box for that reader on sm_100 (tests: 64^3 clustered state)
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -374,7 +406,7 @@ template <bool REL, int TS, int M, bool TMA>
 __global__ void __launch_bounds__(256, 3)
 sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
                  const int* __restrict__ start, float* __restrict__ mesh, int* __restrict__ count,
-                 unsigned long long* __restrict__ stats) {
+                 unsigned long long* __restrict__ stats, int* __restrict__ xrange) {
   // TMA boxes must start on a 16-byte boundary of the innermost (z) axis (misaligned coordinates raise
   // "illegal instruction", tools/tma_probe.cu): the z margin below the tile is kTmaMz = 4 cells there.
   constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
@@ -385,6 +417,8 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
   unsigned* const lo = sbox;
   unsigned* const hi = sbox + NBOX;
   __shared__ int scnt[28];                             // 27 neighbour tiles + generic-stencil count
+  __shared__ int sxr[2];                               // lowest / highest x plane touched (slab plans: ghost width)
+  int xlo = 0x7fffffff, xhi = (int)0x80000000;
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
@@ -399,8 +433,13 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
   float4 p = make_float4(0.f, 0.f, 0.f, 0.f), pn = p;
   if (q < end) p = __ldcs(spos + q);
   if (q + (int)blockDim.x < end) pn = __ldcs(spos + q + blockDim.x);
-  for (int i = threadIdx.x; i < NBOX + NBOX / 2; i += blockDim.x) sbox[i] = 0u;
+  constexpr int NW = NBOX + NBOX / 2, NW4 = NW / 4;
+  for (int i = threadIdx.x; i < NW4; i += blockDim.x) reinterpret_cast<uint4*>(sbox)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if constexpr (NW > 4 * NW4) {
+    if (threadIdx.x < NW - 4 * NW4) sbox[4 * NW4 + threadIdx.x] = 0u;
+  }
   if (threadIdx.x < 28) scnt[threadIdx.x] = 0;
+  if (threadIdx.x < 2) sxr[threadIdx.x] = threadIdx.x ? (int)0x80000000 : 0x7fffffff;
   __syncthreads();
   for (int qb = beg + (threadIdx.x & ~31); qb < end; qb += blockDim.x) {   // warp-uniform trip count
     const bool valid = q < end;
@@ -410,26 +449,33 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
     int ti = 0, tj = 0, tk = 0;            // tile the particle is in now (next ordering)
     if (valid) {
       FastStencil s;
-      bool fast = stencil_fast<REL>(g, p, s);
-      const int lx = local_wrap(s.i0, ox, g.nx), ly = local_wrap(s.j0, oy, g.ny), lz = local_wrap(s.k0, oz, g.nz);
-      fast = fast && (unsigned)lx < (unsigned)(B - 1) && (unsigned)ly < (unsigned)(B - 1) &&
-             (unsigned)lz < (unsigned)(BZV - 1);
+      int lx, ly, lz;
+      const bool fast = stencil_box<REL, B, B, BZV>(g, p, ox, oy, oz, s, lx, ly, lz);
       if (fast) {
         const int o = lx * SX + ly * SY + lz;
         const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
         // reference order (kx*ky)*kz, weight 1; corner offsets are compile-time constants
-        const unsigned v[8] = {__float2uint_rn(w00 * s.wz0 * kFixScale), __float2uint_rn(w00 * s.wz1 * kFixScale),
-                               __float2uint_rn(w01 * s.wz0 * kFixScale), __float2uint_rn(w01 * s.wz1 * kFixScale),
-                               __float2uint_rn(w10 * s.wz0 * kFixScale), __float2uint_rn(w10 * s.wz1 * kFixScale),
-                               __float2uint_rn(w11 * s.wz0 * kFixScale), __float2uint_rn(w11 * s.wz1 * kFixScale)};
+        // (kx ky) kz 2^24: scaling kz by a power of two first gives the same bits as scaling the product
+        const float z0 = s.wz0 * kFixScale, z1 = s.wz1 * kFixScale;
+        const unsigned v[8] = {__float2uint_rn(w00 * z0), __float2uint_rn(w00 * z1), __float2uint_rn(w01 * z0),
+                               __float2uint_rn(w01 * z1), __float2uint_rn(w10 * z0), __float2uint_rn(w10 * z1),
+                               __float2uint_rn(w11 * z0), __float2uint_rn(w11 * z1)};
         constexpr int off[8] = {0, 1, SY, SY + 1, SX, SX + 1, SX + SY, SX + SY + 1};
         unsigned old[8];
 #pragma unroll
         for (int c = 0; c < 8; ++c) old[c] = atomicAdd(lo + o + off[c], v[c]);
+        // carries out of the low words are rare: count them with the carry flag, branch once
+        unsigned ncarry = 0;
 #pragma unroll
         for (int c = 0; c < 8; ++c)
-          if (old[c] + v[c] < old[c]) fixed_carry(hi, o + off[c]);
+          asm("{\n\t.reg .u32 t;\n\tadd.cc.u32 t, %1, %2;\n\taddc.u32 %0, %0, 0;\n\t}" : "+r"(ncarry) : "r"(old[c]), "r"(v[c]));
+        if (ncarry) {
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+            if (old[c] + v[c] < old[c]) fixed_carry(hi, o + off[c]);
+        }
         ti = s.i0 >> TS; tj = s.j0 >> TS; tk = s.k0 >> TS;
+        xlo = min(xlo, s.i0); xhi = max(xhi, s.i0 + 1);
       } else {
         Cic1 cx, cy, cz;
         sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
@@ -450,6 +496,8 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
           }
         }
         if (c.inside) ++nslow; else atomicAdd(stats, 1ull);
+        if (cx.i0 >= 0) { xlo = min(xlo, cx.i0); xhi = max(xhi, cx.i0); }
+        if (cx.i1 >= 0) { xlo = min(xlo, cx.i1); xhi = max(xhi, cx.i1); }
         ti = max(cx.i0, 0) >> TS; tj = max(cy.i0, 0) >> TS; tk = max(cz.i0, 0) >> TS;
       }
     }
@@ -473,19 +521,40 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
     q = qn;
   }
   if (nslow) atomicAdd(scnt + 27, nslow);
+  if (xrange) {
+    xlo = __reduce_min_sync(0xffffffffu, xlo);
+    xhi = __reduce_max_sync(0xffffffffu, xhi);
+    if (lane == 0) { atomicMin(sxr, xlo); atomicMax(sxr + 1, xhi); }
+  }
   __syncthreads();
+  if (xrange && threadIdx.x < 2) {
+    if (threadIdx.x == 0) atomicMin(xrange, sxr[0]);
+    else atomicMax(xrange + 1, sxr[1]);
+  }
   if (threadIdx.x == 27 && scnt[27]) atomicAdd(stats + 2, (unsigned long long)scnt[27]);
   if (threadIdx.x < 27 && scnt[threadIdx.x]) {
     const int dx = threadIdx.x / 9 - 1, dy = (threadIdx.x / 3) % 3 - 1, dz = threadIdx.x % 3 - 1;
     const int i0 = pymod(tx + dx, g.ntx), j0 = pymod(ty + dy, g.nty), k0 = pymod(tz + dz, g.ntz);
     atomicAdd(count + (i0 * g.nty + j0) * g.ntz + k0, scnt[threadIdx.x]);
   }
-  if (TMA) {
+  if constexpr (TMA) {
     // convert the fixed-point box to fp32 in place, then ONE tensor reduce-add moves it into the
     // ghost-zone mesh (the box never wraps there; cells past the array edge are clipped by the TMA unit)
-    for (int i = threadIdx.x; i < NBOX; i += blockDim.x) {
-      const unsigned h = (hi[i >> 1] >> ((i & 1) * 16)) & 0xffffu;
-      reinterpret_cast<float*>(lo)[i] = fixed_to_float(lo[i], h);
+    static_assert(NBOX % 4 == 0, "box rows are multiples of four cells in the TMA flavour");
+    for (int i = threadIdx.x; i < NBOX / 4; i += blockDim.x) {
+      const uint4 l = reinterpret_cast<const uint4*>(lo)[i];
+      const uint2 h = reinterpret_cast<const uint2*>(hi)[i];
+      float4 f;
+      if ((h.x | h.y) == 0u) {   // no cell of the four holds more than 256 particles (the usual case)
+        f = make_float4(__uint2float_rn(l.x) * kFixInv, __uint2float_rn(l.y) * kFixInv,
+                        __uint2float_rn(l.z) * kFixInv, __uint2float_rn(l.w) * kFixInv);
+      } else {
+        f.x = fixed_to_float(l.x, h.x & 0xffffu);
+        f.y = fixed_to_float(l.y, h.x >> 16);
+        f.z = fixed_to_float(l.z, h.y & 0xffffu);
+        f.w = fixed_to_float(l.w, h.y >> 16);
+      }
+      reinterpret_cast<float4*>(lo)[i] = f;
     }
     fence_async_smem();
     __syncthreads();
@@ -598,10 +667,7 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
     bool fast = false;
     FastStencil s;
     if (valid) {
-      fast = stencil_fast<REL>(g, p, s);
-      lx = local_wrap(s.i0, ox, g.nx); ly = local_wrap(s.j0, oy, g.ny); lz = local_wrap(s.k0, oz, g.nz);
-      fast = fast && (unsigned)lx < (unsigned)(B - 1) && (unsigned)ly < (unsigned)(B - 1) &&
-             (unsigned)lz < (unsigned)(BZ - 1);
+      fast = stencil_box<REL, B, B, BZ>(g, p, ox, oy, oz, s, lx, ly, lz);
       if (fast) {
         tt = ((s.i0 >> TS) * g.nty + (s.j0 >> TS)) * g.ntz + (s.k0 >> TS);
       } else {
@@ -877,14 +943,17 @@ static int32_t sim_paint_impl(jpm_sim* s, cudaStream_t st, float* mesh, bool tma
   JPM_CUDA(cudaMemsetAsync(s->count, 0, s->g.nt * sizeof(int), st));
   const int ts = s->g.tshift, m = s->g.m;
   const SimGeom& g = tma ? s->gp : s->g;
+  // slab plans: record the x planes the particles touch, the first barrier of the step turns it into the ghost width
+  int* xrange = (tma && s->plan && s->plan->is_slab && s->plan->slab.P > 1)
+                    ? reinterpret_cast<int*>(s->plan->slab.flags[s->plan->slab.rank]) + kFlagXmin : nullptr;
 #define LAUNCH_PAINT_T(TS_, M_, TMA_)                                                                    \
   {                                                                                                      \
     if (s->relative)                                                                                     \
       sim_paint_kernel<true, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(             \
-          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                     \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange);             \
     else                                                                                                 \
       sim_paint_kernel<false, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(            \
-          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats);                     \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange);             \
   }
 #define LAUNCH_PAINT(TS_, M_) LAUNCH_PAINT_T(TS_, M_, false)
 #define LAUNCH_PAINT_TMA(TS_, M_) LAUNCH_PAINT_T(TS_, M_, true)

@@ -91,6 +91,11 @@ class SlabPlan:
     def check(self):
         call("jpm_slab_check", self.handle, stream())
 
+    def ghost_width(self):
+        v = C.c_int32(0)
+        call("jpm_slab_ghost_width", self.handle, stream(), C.byref(v))
+        return int(v.value)
+
     def destroy(self):
         if self.handle:
             _lib.load().jpm_plan_destroy(self.handle)
