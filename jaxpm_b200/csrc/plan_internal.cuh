@@ -45,6 +45,9 @@ constexpr int kFlagXmax = 97;      //      sim_paint_kernel; INT_MAX / INT_MIN =
 constexpr int kFlagGe = 98;        // int: ghost planes per side in use this step = max over ranks of what each needs
 constexpr int kFlagGeSlots = 128;  // [P] the ranks' needs, written by the peers in the first barrier of a step
 
+// one tensor map per destination rank (TMA stores of the transposing FFT passes)
+struct alignas(64) TmapPack { CUtensorMap m[8]; };
+
 struct jpm_plan {
   StageTimer* timer = nullptr;
   Slab slab;                  // valid when fft_on
@@ -82,6 +85,12 @@ struct jpm_plan {
   float2* fft_at = nullptr;   // P == 1: the AT buffer   [nx][ny][nzc]
   float2* fft_b3 = nullptr;   // P == 1: the B3 buffer   [3][nx][ny][nzc]
   float2 *tw_x = nullptr, *tw_y = nullptr, *tw_zh = nullptr, *tw_zfull = nullptr;   // exp(-2 pi i k / n) tables
+  // TMA-store flavour of the transposing passes: finished tiles leave shared memory as cp.async.bulk.tensor
+  // stores (one box per destination rank), so remote (NVLink) stores do not stall the SM
+  bool fft_tma_store = false;
+  int fft_xc = 8;               // kz columns per tile of the X-fused pass: 8 (64-byte rows), or 16 (128-byte rows: NVLink)
+  TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
+  TmapPack* tm_b3 = nullptr;    // [d]: B3 of rank d as {2 nzc, ny, lx, 3}, box {16, 1, min(lx,256), 1}
 };
 
 namespace jpm {

@@ -21,6 +21,8 @@
 // 4 shared-memory passes instead of 8.  Row passes (z) stage 16 rows with a pitch of N/2+1 complex, lanes
 // across rows: conflict-free for every stage permutation.
 #include <cmath>
+#include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -200,6 +202,21 @@ __host__ __device__ constexpr int threads_for() {
   return (N * C / D) < 64 ? 64 : ((N * C / D) > 1024 ? 1024 : (N * C / D));
 }
 
+// ---- TMA stores (shared -> global tensor tile; SASS UTMASTG) ------------------------------------------
+__device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, int c0, int c1, int c2, const void* src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];"
+               ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_addr(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* tm, int c0, int c1, int c2, int c3, const void* src) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+               ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(smem_addr(src)) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// the shared-memory sources of all committed stores have been read (the buffers may be reused / the CTA may exit)
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+
 // ---- peer-aware global I/O of the slab decomposition -------------------------------------------------
 // y-transformed element (y, c) of x plane `xg` goes to the rank that owns y: AT[xg][y % ly][kz] there
 struct ScatterYIO {
@@ -224,11 +241,11 @@ struct ScatterXIO {
 
 // ---- Y-fwd: FFT along y of the local x planes, result transposed onto the y-owning ranks ---------------
 // grid: (ntile, lx).  in: A_loc = B3[2] region of this rank [lx][ny][nzc]; out: AT[nx][ly][nzc] of every rank.
-template <int N, int C>
+template <int N, int C, bool TMAST>
 __global__ void __launch_bounds__(threads_for<N, C>())
-yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg) {
+yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const __grid_constant__ TmapPack tp) {
   constexpr int NT = threads_for<N, C>();
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   for (int i = threadIdx.x; i < N; i += NT) tw[i] = twg[i];
@@ -236,8 +253,26 @@ yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg) {
   const int ncol = min(C, sl.nzh - kz0);
   const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
   GlobalIO gin{sl.b3[sl.rank] + 2 * cs + (long long)xl * sl.ny * sl.nzc + kz0, sl.nzc};
-  ScatterYIO gout{&sl, (long long)(sl.rank * sl.lx + xl) * sl.ly * sl.nzc + kz0};
-  run_stages<N, C, NT, false, false, false, false, LayCols<C>, 0>(s, tw, ncol, gin, gout, nullptr);
+  const int xg = sl.rank * sl.lx + xl;
+  if constexpr (TMAST) {
+    // the finished tile stays in shared memory; rows [d ly, (d+1) ly) leave as one tensor store per
+    // destination rank (<= 256 rows per box)
+    SmemIO<LayCols<C>> so{s};
+    run_stages<N, C, NT, false, false, false, false, LayCols<C>, 0>(s, tw, ncol, gin, so, nullptr);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int rows = min(sl.ly, 256);
+      for (int d = 0; d < sl.P; ++d)
+        for (int r0 = 0; r0 < sl.ly; r0 += rows)
+          tma_store_3d(&tp.m[d], 2 * kz0, r0, xg, s + (size_t)(d * sl.ly + r0) * C);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  } else {
+    ScatterYIO gout{&sl, (long long)xg * sl.ly * sl.nzc + kz0};
+    run_stages<N, C, NT, false, false, false, false, LayCols<C>, 0>(s, tw, ncol, gin, gout, nullptr);
+  }
 }
 
 // ---- X-fused pass ---------------------------------------------------------------------------------
@@ -245,21 +280,23 @@ yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg) {
 // (operation order of kspace_kernel<0>, plan.cu); then TWO inverse FFTs along x:
 //   T0 = IFFT_x(i a_x(kx) g delta)  -> B[0]   (x force; a_y, a_z do not depend on kx, so the y and z
 //   T1 = IFFT_x(g delta)            -> B[1]    forces share T1: their factors are applied in Y-inv / Z-inv)
-template <int N, int C>
+template <int N, int C, bool TMAST>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
 xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
               const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
-              float norm, float r_split2, const float* __restrict__ ftab, int ntab, float fscale) {
+              float norm, float r_split2, const float* __restrict__ ftab, int ntab, float fscale,
+              const __grid_constant__ TmapPack tp) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int L = radix_count(N);
   constexpr int RL = radix_at(N, L - 1, false);        // radix of the last forward == first inverse stage
   constexpr int TASKS = (N / RL) * C;
   constexpr int TPT = (TASKS + NT - 1) / NT;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   float* swx = reinterpret_cast<float*>(s + N * C);   // [N] k_x table
   float* sax = swx + N;                               // [N] gradient table
+  float2* s2 = reinterpret_cast<float2*>(sax + N);    // [N][C] second tile (TMAST: T1 is built while T0 drains)
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; swx[i] = wx[i]; sax[i] = ax[i]; }
   const int kz0 = blockIdx.x * C;
   const int ncol = min(C, sl.nzh - kz0);
@@ -312,8 +349,26 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
         }
       }
     }
-    ScatterXIO gout{&sl, d * cs + (long long)yg * sl.nzc + kz0};
-    run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
+    if constexpr (TMAST) {
+      float2* sb = d == 0 ? s : s2;
+      SmemIO<LayCols<C>> so{sb};
+      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(sb, tw, ncol, NullIO{}, so, w);
+      fence_async_smem();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int rows = min(sl.lx, 256);
+        for (int dst = 0; dst < sl.P; ++dst)
+          for (int r0 = 0; r0 < sl.lx; r0 += rows)
+            tma_store_4d(&tp.m[dst], 2 * kz0, yg, r0, d, sb + (size_t)(dst * sl.lx + r0) * C);
+        tma_store_commit();
+      }
+    } else {
+      ScatterXIO gout{&sl, d * cs + (long long)yg * sl.nzc + kz0};
+      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
+    }
+  }
+  if constexpr (TMAST) {
+    if (threadIdx.x == 0) tma_store_wait_read();
   }
 }
 
@@ -378,6 +433,12 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // neighbour slabs; of this slab itself when P == 1), G ghost cells per side in y and z (periodic images).
 constexpr int kRows = 16;
 __device__ __forceinline__ int ghost_width(const Slab& sl);
+// x plane of a z-pass block.  P > 1: planes next to the slab faces exchange ghosts with the neighbours over
+// NVLink; an odd stride (lx is a power of two) spreads them over the whole launch, so that at any time most
+// resident CTAs run at HBM speed while a few wait on the link, instead of one NVLink-bound phase.
+__device__ __forceinline__ int z_pass_plane(const Slab& sl, int by) {
+  return (sl.P > 1 && sl.lx >= 16) ? ((by * 37) & (sl.lx - 1)) : by;
+}
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
@@ -386,7 +447,7 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int xl = blockIdx.y, y0 = blockIdx.x * kRows;
+  const int xl = z_pass_plane(sl, blockIdx.y), y0 = blockIdx.x * kRows;
   const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp;
   const int GH = G / 2;       // ghost width in float2 units
   // x planes that fold onto interior plane xl: this rank's own, the left neighbour's high ghost, the right
@@ -477,7 +538,7 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int xl = blockIdx.y, y0 = blockIdx.x * kRows, comp = blockIdx.z;
+  const int xl = z_pass_plane(sl, blockIdx.y), y0 = blockIdx.x * kRows, comp = blockIdx.z;
   const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp, nzc = sl.nzc;
   const float2* src = sl.b3[sl.rank] + (long long)comp * lx * ny * nzc + ((long long)xl * ny + y0) * nzc;
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
@@ -633,6 +694,7 @@ static bool pow2_in_range(int n) { return n >= 16 && n <= 1024 && (n & (n - 1)) 
 
 template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C) * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
+template <int N, int C> constexpr size_t xfused_smem_tma() { return xfused_smem<N, C>() + (size_t)N * C * sizeof(float2); }
 template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
 
 constexpr int kColsC = 16;   // kz columns per tile of the Y-fwd pass (128-byte segments)
@@ -652,15 +714,23 @@ constexpr int kXC = 8;       // ... of the X-fused and Y-inv passes (64-byte seg
 
 static int32_t set_attrs(const Slab& sl) {
 #define ATTR_Y(N_)                                                                                              \
-  JPM_CUDA(cudaFuncSetAttribute(yfwd_kernel<N_, kColsC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+  JPM_CUDA(cudaFuncSetAttribute(yfwd_kernel<N_, kColsC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
+                                (int)cols_smem<N_, kColsC>()));                                                 \
+  JPM_CUDA(cudaFuncSetAttribute(yfwd_kernel<N_, kColsC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                 (int)cols_smem<N_, kColsC>()));                                                 \
   JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
                                 (int)xfused_smem<N_, kXC>()));
   JPM_FFT_SWITCH(sl.ny, ATTR_Y)
 #undef ATTR_Y
 #define ATTR_X(N_)                                                                                              \
-  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,            \
-                                (int)xfused_smem<N_, kXC>()));
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                (int)xfused_smem<N_, kXC>()));                                                  \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                (int)xfused_smem_tma<N_, kXC>()));                                              \
+  if constexpr (N_ <= 512) {                                                                                    \
+    JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)xfused_smem_tma<N_, 16>()));                                             \
+  }
   JPM_FFT_SWITCH(sl.nx, ATTR_X)
 #undef ATTR_X
 #define ATTR_Z(N_)                                                                                              \
@@ -693,6 +763,33 @@ int32_t pmfft_setup(jpm_plan* p) {
   // load both barrier kernels NOW: with lazy module loading the first launch of a kernel can block the host
   // until the device is idle, which never happens while this rank's previous barrier is still spinning for a
   // peer driven by the same host thread (several ranks in one process)
+  // tensor maps of every rank's AT / B3 for the TMA-store flavour (JPM_FFT_TMASTORE=0 keeps plain stores)
+  {
+    const char* env = getenv("JPM_FFT_TMASTORE");
+    p->fft_tma_store = !(env && env[0] == '0') && sl.lx >= 2 && sl.ly >= 2 &&
+                       (sl.lx <= 256 || sl.lx % 256 == 0) && (sl.ly <= 256 || sl.ly % 256 == 0);
+    // 128-byte rows for the x pass when its output crosses NVLink (64-byte writes reach about half the link
+    // rate); JPM_FFT_XC=8|16 overrides
+    p->fft_xc = (sl.P > 1 && sl.nx <= 512) ? 16 : 8;
+    if (const char* e = getenv("JPM_FFT_XC")) p->fft_xc = (atoi(e) == 16 && sl.nx <= 512) ? 16 : 8;
+    if (p->fft_tma_store) {
+      if (!p->tm_at) p->tm_at = new TmapPack();
+      if (!p->tm_b3) p->tm_b3 = new TmapPack();
+      memset(p->tm_at, 0, sizeof(TmapPack));
+      memset(p->tm_b3, 0, sizeof(TmapPack));
+      const unsigned long long row = (unsigned long long)sl.nzc * sizeof(float2);
+      for (int d = 0; d < sl.P; ++d) {
+        const unsigned long long da[3] = {2ull * sl.nzc, (unsigned long long)sl.ly, (unsigned long long)sl.nx};
+        const unsigned long long sa[2] = {row, row * sl.ly};
+        const unsigned ba[3] = {2u * fft::kColsC, (unsigned)std::min(sl.ly, 256), 1u};
+        if ((rc = encode_tensor_map(&p->tm_at->m[d], reinterpret_cast<float*>(sl.at[d]), 3, da, sa, ba))) return rc;
+        const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
+        const unsigned long long sb[3] = {row, row * sl.ny, row * sl.ny * sl.lx};
+        const unsigned bb[4] = {2u * (unsigned)p->fft_xc, 1u, (unsigned)std::min(sl.lx, 256), 1u};
+        if ((rc = encode_tensor_map(&p->tm_b3->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bb))) return rc;
+      }
+    }
+  }
   cudaFuncAttributes fa;
   JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<true>));
   JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<false>));
@@ -723,6 +820,8 @@ int32_t pmfft_enable(jpm_plan* p) {
 }
 
 void pmfft_destroy(jpm_plan* p) {
+  delete p->tm_at; p->tm_at = nullptr;
+  delete p->tm_b3; p->tm_b3 = nullptr;
   void* bufs[] = {p->fft_at, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -759,16 +858,36 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "fft_z_r2c+ghost_fold");
   const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
+  static const TmapPack kNoMaps{};
+  const TmapPack& tat = p->fft_tma_store ? *p->tm_at : kNoMaps;
+  const TmapPack& tb3 = p->fft_tma_store ? *p->tm_b3 : kNoMaps;
 #define RUN_YF(N_)                                                                                             \
-  yfwd_kernel<N_, kColsC><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>(sl, p->tw_y);
+  if (p->fft_tma_store)                                                                                        \
+    yfwd_kernel<N_, kColsC, true><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat);                                                                                     \
+  else                                                                                                         \
+    yfwd_kernel<N_, kColsC, false><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat);
   JPM_FFT_SWITCH(sl.ny, RUN_YF)
 #undef RUN_YF
   JPM_LAUNCH_CHECK();
   if ((rc = slab_barrier(p, st))) return rc;      // AT complete on every rank
   if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
 #define RUN_X(N_)                                                                                              \
-  xfused_kernel<N_, kXC><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(      \
-      sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale);
+  if constexpr (N_ <= 512) {                                                                                   \
+    if (p->fft_tma_store && p->fft_xc == 16) {                                                                 \
+      xfused_kernel<N_, 16, true><<<dim3((nzh + 15) / 16, sl.ly, 1), threads_for<N_, 16, 8>(),                 \
+                                    xfused_smem_tma<N_, 16>(), st>>>(                                          \
+          sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);   \
+      break;                                                                                                   \
+    }                                                                                                          \
+  }                                                                                                            \
+  if (p->fft_tma_store)                                                                                        \
+    xfused_kernel<N_, kXC, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+  else                                                                                                         \
+    xfused_kernel<N_, kXC, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);
   JPM_FFT_SWITCH(sl.nx, RUN_X)
 #undef RUN_X
   JPM_LAUNCH_CHECK();

@@ -368,10 +368,7 @@ __device__ __forceinline__ void tma_reduce_add_3d(const CUtensorMap* tm, int c0,
                ::"l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(src))
                : "memory");
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-  // wait for the reduction to be PERFORMED, not only for the box to be read (.read): the next kernel on the
-  // stream reads the mesh through the generic proxy, and a CTA that exits with the reduce still in flight
-  // was observed to lose (part of) its box for that reader on sm_100 (tests: 64^3 clustered state)
-  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
