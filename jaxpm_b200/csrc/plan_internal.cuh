@@ -88,8 +88,10 @@ struct jpm_plan {
   // TMA-store flavour of the transposing passes: finished tiles leave shared memory as cp.async.bulk.tensor
   // stores (one box per destination rank), so remote (NVLink) stores do not stall the SM
   bool fft_tma_store = false;
+  bool fft_yinv_tma = false;    // Y-inv pass through TMA stores too (measured slower on one GPU: off unless JPM_FFT_YINV_TMA=1)
   int fft_xc = 8;               // kz columns per tile of the X-fused pass: 8 (64-byte rows), or 16 (128-byte rows: NVLink)
   TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
+  TmapPack* tm_b3y = nullptr;   // [0]: this rank's B3 with a box along y {16, min(ny,256), 1, 1} (Y-inv pass)
   TmapPack* tm_b3 = nullptr;    // [d]: B3 of rank d as {2 nzc, ny, lx, 3}, box {16, 1, min(lx,256), 1}
 };
 

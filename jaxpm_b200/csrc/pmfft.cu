@@ -375,24 +375,43 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
 // ---- Y-inv: inverse FFT along y of the local x planes ---------------------------------------------------
 // grid: (ntile, lx).  B[0] = T0 -> F_x in place;  B[1] = T1 is read ONCE into registers and transformed twice:
 // as it is -> B[2] (F_z up to the factor i a_z(kz), applied by Z-inv) and times i a_y(ky) -> B[1] (F_y).
-template <int N, int C>
+template <int N, int C, bool TMAST>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
-yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay) {
+yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay,
+            const __grid_constant__ TmapPack tp) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int R0 = radix_at(N, 0, false);           // first inverse stage (forward radix order)
   constexpr int TASKS = (N / R0) * C;
   constexpr int TPT = (TASKS + NT - 1) / NT;
-  extern __shared__ __align__(16) float2 sm[];
+  extern __shared__ __align__(128) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   float* say = reinterpret_cast<float*>(s + N * C);   // [N] gradient table along y
+  float2* s2 = reinterpret_cast<float2*>(say + 2 * N);   // TMAST: tiles of the second and third transform
+  float2* s3 = s2 + N * C;
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; say[i] = ay[i]; }
   const int kz0 = blockIdx.x * C, xl = blockIdx.y;
   const int ncol = min(C, sl.nzh - kz0);
   const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
   float2* base = sl.b3[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0;
   GlobalIO g0{base, sl.nzc}, g1{base + cs, sl.nzc}, g2{base + 2 * cs, sl.nzc};
-  run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, g0, nullptr);
+  // TMAST: a finished tile leaves shared memory as tensor stores (<= 256 rows per box) while the next transform runs
+  auto drain = [&](const float2* tile, int comp) {
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int rows = min(N, 256);
+      for (int r0 = 0; r0 < N; r0 += rows) tma_store_4d(&tp.m[0], 2 * kz0, r0, xl, comp, tile + (size_t)r0 * C);
+      tma_store_commit();
+    }
+  };
+  if constexpr (TMAST) {
+    SmemIO<LayCols<C>> so{s};
+    run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, so, nullptr);
+    drain(s, 0);
+  } else {
+    run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, g0, nullptr);
+  }
   float2 keep[TPT][8];
 #pragma unroll
   for (int i = 0; i < TPT; ++i) {
@@ -403,14 +422,20 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
       for (int r = 0; r < R0; ++r) keep[i][r] = g1(j + r * (N / R0), c);
     }
   }
-  __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
+  if constexpr (!TMAST) __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
   {
     float2 w[TPT][8];
 #pragma unroll
     for (int i = 0; i < TPT; ++i)
 #pragma unroll
       for (int r = 0; r < R0; ++r) w[i][r] = keep[i][r];
-    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g2, w);
+    if constexpr (TMAST) {
+      SmemIO<LayCols<C>> so{s2};
+      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s2, tw, ncol, NullIO{}, so, w);
+      drain(s2, 2);
+    } else {
+      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g2, w);
+    }
   }
   {
     float2 w[TPT][8];
@@ -424,7 +449,14 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
         w[i][r] = make_float2(-a * keep[i][r].y, a * keep[i][r].x);       // i a_y T1
       }
     }
-    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g1, w);
+    if constexpr (TMAST) {
+      SmemIO<LayCols<C>> so{s3};
+      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s3, tw, ncol, NullIO{}, so, w);
+      drain(s3, 1);
+      if (threadIdx.x == 0) tma_store_wait_read();
+    } else {
+      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g1, w);
+    }
   }
 }
 
@@ -458,28 +490,37 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   if (xl >= lx - ge) src[2] = sl.dens[(sl.rank + 1) % sl.P] + (long long)(xl - (lx - gx)) * nyp * nzp;
   constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
-  // blocks away from the x / y faces have no periodic images to fold: branch-free loads, BATCH in flight
-  const bool interior = !src[1] && !src[2] && y0 >= G && y0 + kRows <= ny - G;
-  if (interior) {
-    const float2* base = reinterpret_cast<const float2*>(src[0] + (long long)(y0 + G) * nzp) + GH;
+  // blocks away from the y faces: per source plane (own, left neighbour's high ghost, right neighbour's low
+  // ghost) branch-free loads with BATCH in flight per thread - the neighbour planes are NVLink reads with
+  // ~2 us latency, so the number of loads in flight is what sets their rate.  Every thread owns the same
+  // elements in every pass: the accumulation into the tile needs no barrier.
+  const bool y_interior = y0 >= G && y0 + kRows <= ny - G;
+  if (y_interior) {
     const int rowp = nzp / 2;   // row pitch in float2
+#pragma unroll
+    for (int ix = 0; ix < 3; ++ix) {
+      if (!src[ix]) continue;
+      const float2* base = reinterpret_cast<const float2*>(src[ix] + (long long)(y0 + G) * nzp) + GH;
 #pragma unroll 1
-    for (int b = 0; b < ITER; b += BATCH) {
-      float2 acc[BATCH], lo[BATCH], hi[BATCH];
+      for (int b = 0; b < ITER; b += BATCH) {
+        float2 acc[BATCH], lo[BATCH], hi[BATCH];
 #pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int e = threadIdx.x + (b + i) * NT;
-        const int r = e / NH, m = e - r * NH;
-        const float2* q = base + r * rowp + m;
-        acc[i] = __ldcs(q);
-        hi[i] = (m < GH) ? __ldcs(q + NH) : make_float2(0.f, 0.f);          // high ghost -> first cells
-        lo[i] = (m >= NH - GH) ? __ldcs(q - NH) : make_float2(0.f, 0.f);    // low ghost -> last cells
-      }
+        for (int i = 0; i < BATCH; ++i) {
+          const int e = threadIdx.x + (b + i) * NT;
+          const int r = e / NH, m = e - r * NH;
+          const float2* q = base + r * rowp + m;
+          acc[i] = __ldcs(q);
+          hi[i] = (m < GH) ? __ldcs(q + NH) : make_float2(0.f, 0.f);          // high ghost -> first cells
+          lo[i] = (m >= NH - GH) ? __ldcs(q - NH) : make_float2(0.f, 0.f);    // low ghost -> last cells
+        }
 #pragma unroll
-      for (int i = 0; i < BATCH; ++i) {
-        const int e = threadIdx.x + (b + i) * NT;
-        const int r = e / NH, m = e - r * NH;
-        s[LayRows<NH>::idx(m, r)] = cadd(cadd(acc[i], hi[i]), lo[i]);
+        for (int i = 0; i < BATCH; ++i) {
+          const int e = threadIdx.x + (b + i) * NT;
+          const int r = e / NH, m = e - r * NH;
+          float2 v = cadd(cadd(acc[i], hi[i]), lo[i]);
+          if (ix > 0) v = cadd(v, s[LayRows<NH>::idx(m, r)]);
+          s[LayRows<NH>::idx(m, r)] = v;
+        }
       }
     }
   } else {
@@ -694,6 +735,7 @@ static bool pow2_in_range(int n) { return n >= 16 && n <= 1024 && (n & (n - 1)) 
 
 template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C) * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
+template <int N, int C> constexpr size_t yinv_smem_tma() { return xfused_smem<N, C>() + 2 * (size_t)N * C * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem_tma() { return xfused_smem<N, C>() + (size_t)N * C * sizeof(float2); }
 template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
 
@@ -718,8 +760,10 @@ static int32_t set_attrs(const Slab& sl) {
                                 (int)cols_smem<N_, kColsC>()));                                                 \
   JPM_CUDA(cudaFuncSetAttribute(yfwd_kernel<N_, kColsC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
                                 (int)cols_smem<N_, kColsC>()));                                                 \
-  JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC>, cudaFuncAttributeMaxDynamicSharedMemorySize,              \
-                                (int)xfused_smem<N_, kXC>()));
+  JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                (int)xfused_smem<N_, kXC>()));                                                  \
+  JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                (int)yinv_smem_tma<N_, kXC>()));
   JPM_FFT_SWITCH(sl.ny, ATTR_Y)
 #undef ATTR_Y
 #define ATTR_X(N_)                                                                                              \
@@ -767,14 +811,25 @@ int32_t pmfft_setup(jpm_plan* p) {
   {
     const char* env = getenv("JPM_FFT_TMASTORE");
     p->fft_tma_store = !(env && env[0] == '0') && sl.lx >= 2 && sl.ly >= 2 &&
-                       (sl.lx <= 256 || sl.lx % 256 == 0) && (sl.ly <= 256 || sl.ly % 256 == 0);
+                       (sl.lx <= 256 || sl.lx % 256 == 0) && (sl.ly <= 256 || sl.ly % 256 == 0) &&
+                       (sl.ny <= 256 || sl.ny % 256 == 0);
     // 128-byte rows for the x pass when its output crosses NVLink (64-byte writes reach about half the link
     // rate); JPM_FFT_XC=8|16 overrides
     p->fft_xc = (sl.P > 1 && sl.nx <= 512) ? 16 : 8;
+    if (const char* e = getenv("JPM_FFT_YINV_TMA")) p->fft_yinv_tma = e[0] == '1';
     if (const char* e = getenv("JPM_FFT_XC")) p->fft_xc = (atoi(e) == 16 && sl.nx <= 512) ? 16 : 8;
     if (p->fft_tma_store) {
       if (!p->tm_at) p->tm_at = new TmapPack();
       if (!p->tm_b3) p->tm_b3 = new TmapPack();
+      if (!p->tm_b3y) p->tm_b3y = new TmapPack();
+      memset(p->tm_b3y, 0, sizeof(TmapPack));
+      {
+        const unsigned long long rw = (unsigned long long)sl.nzc * sizeof(float2);
+        const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
+        const unsigned long long sb[3] = {rw, rw * sl.ny, rw * sl.ny * sl.lx};
+        const unsigned bb[4] = {2u * fft::kXC, (unsigned)std::min(sl.ny, 256), 1u, 1u};
+        if ((rc = encode_tensor_map(&p->tm_b3y->m[0], reinterpret_cast<float*>(sl.b3[sl.rank]), 4, db, sb, bb))) return rc;
+      }
       memset(p->tm_at, 0, sizeof(TmapPack));
       memset(p->tm_b3, 0, sizeof(TmapPack));
       const unsigned long long row = (unsigned long long)sl.nzc * sizeof(float2);
@@ -822,6 +877,7 @@ int32_t pmfft_enable(jpm_plan* p) {
 void pmfft_destroy(jpm_plan* p) {
   delete p->tm_at; p->tm_at = nullptr;
   delete p->tm_b3; p->tm_b3 = nullptr;
+  delete p->tm_b3y; p->tm_b3y = nullptr;
   void* bufs[] = {p->fft_at, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -894,7 +950,12 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   if ((rc = slab_barrier(p, st))) return rc;      // B[0], B[1] complete on every rank
   if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x2+transpose");
 #define RUN_YI(N_)                                                                                             \
-  yinv_kernel<N_, kXC><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(sl, p->tw_y, p->ay);
+  if (p->fft_tma_store && p->fft_yinv_tma)                                                                     \
+    yinv_kernel<N_, kXC, true><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), yinv_smem_tma<N_, kXC>(), st>>>( \
+        sl, p->tw_y, p->ay, *p->tm_b3y);                                                                       \
+  else                                                                                                         \
+    yinv_kernel<N_, kXC, false><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
+        sl, p->tw_y, p->ay, kNoMaps);
   JPM_FFT_SWITCH(sl.ny, RUN_YI)
 #undef RUN_YI
   JPM_LAUNCH_CHECK();
