@@ -227,6 +227,7 @@ def run_gpu(args):
         "fft_z_r2c+ghost_fold": 8 * nc, "fft_y_fwd+transpose": 8 * nc,
         "fft_x_fwd+greens_grad+ifft_x_x2+transpose": 12 * nc, "ifft_y_x3": 20 * nc,
         "ifft_z_c2r_x3+ghost_fill": 24 * nc,
+        "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)": 16 * nc, "ifft_y_x3|ifft_z_c2r_x3 (chunked pairs)": 44 * nc,
         "ghost_fold": 0, "ghost_fill": 0, "fft_r2c(cuFFT)": 8 * nc, "greens_grad": 16 * nc,
         "ifft_c2r_x3(cuFFT)": 24 * nc,
     }

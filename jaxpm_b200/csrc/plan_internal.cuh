@@ -89,6 +89,10 @@ struct jpm_plan {
   // stores (one box per destination rank), so remote (NVLink) stores do not stall the SM
   bool fft_tma_store = false;
   bool fft_yinv_tma = false;    // Y-inv pass through TMA stores too (measured slower on one GPU: off unless JPM_FFT_YINV_TMA=1)
+  int fft_chunk = 0;            // P == 1: x planes per (z-fwd, y-fwd) / (y-inv, z-inv) launch pair, so that the second
+                                // pass of a pair finds the first one's output in L2 (0 = whole mesh per launch)
+  bool fft_yinv_prefetch = true;   // Y-inv: request T1 before transforming T0 (0.80 -> 0.68 ms at 512^3)
+  int fft_zvariant = 1;            // experiments on the z-inverse pass (JPM_FFT_ZVAR bit 0: batched plain epilogue)
   int fft_xc = 8;               // kz columns per tile of the X-fused pass: 8 (64-byte rows), or 16 (128-byte rows: NVLink)
   TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
   TmapPack* tm_b3y = nullptr;   // [0]: this rank's B3 with a box along y {16, min(ny,256), 1, 1} (Y-inv pass)

@@ -243,13 +243,14 @@ struct ScatterXIO {
 // grid: (ntile, lx).  in: A_loc = B3[2] region of this rank [lx][ny][nzc]; out: AT[nx][ly][nzc] of every rank.
 template <int N, int C, bool TMAST>
 __global__ void __launch_bounds__(threads_for<N, C>())
-yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const __grid_constant__ TmapPack tp) {
+yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const __grid_constant__ TmapPack tp,
+            int x0) {
   constexpr int NT = threads_for<N, C>();
   extern __shared__ __align__(128) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   for (int i = threadIdx.x; i < N; i += NT) tw[i] = twg[i];
-  const int kz0 = blockIdx.x * C, xl = blockIdx.y;
+  const int kz0 = blockIdx.x * C, xl = x0 + blockIdx.y;
   const int ncol = min(C, sl.nzh - kz0);
   const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
   GlobalIO gin{sl.b3[sl.rank] + 2 * cs + (long long)xl * sl.ny * sl.nzc + kz0, sl.nzc};
@@ -378,7 +379,7 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
 template <int N, int C, bool TMAST>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
 yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay,
-            const __grid_constant__ TmapPack tp) {
+            const __grid_constant__ TmapPack tp, int x0, int prefetch) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int R0 = radix_at(N, 0, false);           // first inverse stage (forward radix order)
   constexpr int TASKS = (N / R0) * C;
@@ -390,7 +391,7 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
   float2* s2 = reinterpret_cast<float2*>(say + 2 * N);   // TMAST: tiles of the second and third transform
   float2* s3 = s2 + N * C;
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; say[i] = ay[i]; }
-  const int kz0 = blockIdx.x * C, xl = blockIdx.y;
+  const int kz0 = blockIdx.x * C, xl = x0 + blockIdx.y;
   const int ncol = min(C, sl.nzh - kz0);
   const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
   float2* base = sl.b3[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0;
@@ -405,6 +406,20 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
       tma_store_commit();
     }
   };
+  float2 keep[TPT][8];
+  auto load_keep = [&]() {
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int task = threadIdx.x + i * NT;
+      const int c = task % C, j = task / C;
+      if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) keep[i][r] = g1(j + r * (N / R0), c);
+      }
+    }
+  };
+  // prefetch: T1 is requested before T0 is transformed, so its latency hides behind that transform
+  if (prefetch) load_keep();
   if constexpr (TMAST) {
     SmemIO<LayCols<C>> so{s};
     run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, so, nullptr);
@@ -412,16 +427,7 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
   } else {
     run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, g0, nullptr);
   }
-  float2 keep[TPT][8];
-#pragma unroll
-  for (int i = 0; i < TPT; ++i) {
-    const int task = threadIdx.x + i * NT;
-    const int c = task % C, j = task / C;
-    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
-#pragma unroll
-      for (int r = 0; r < R0; ++r) keep[i][r] = g1(j + r * (N / R0), c);
-    }
-  }
+  if (!prefetch) load_keep();
   if constexpr (!TMAST) __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
   {
     float2 w[TPT][8];
@@ -464,6 +470,10 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // grid: (ny / 16, lx).  Real arrays are [lx + 2 gx][nyp][nzp]: gx ghost planes per side in x (images of the
 // neighbour slabs; of this slab itself when P == 1), G ghost cells per side in y and z (periodic images).
 constexpr int kRows = 16;
+#ifndef JPM_ZINV_BATCH
+#define JPM_ZINV_BATCH 16
+#endif
+constexpr int kZinvBatch = JPM_ZINV_BATCH;   // spectrum loads in flight per thread in the z-inverse pass
 __device__ __forceinline__ int ghost_width(const Slab& sl);
 // x plane of a z-pass block.  P > 1: planes next to the slab faces exchange ghosts with the neighbours over
 // NVLink; an odd stride (lx is a power of two) spreads them over the whole launch, so that at any time most
@@ -473,13 +483,13 @@ __device__ __forceinline__ int z_pass_plane(const Slab& sl, int by) {
 }
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
-zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull) {
+zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull, int x0) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int xl = z_pass_plane(sl, blockIdx.y), y0 = blockIdx.x * kRows;
+  const int xl = z_pass_plane(sl, x0 + blockIdx.y), y0 = blockIdx.x * kRows;
   const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp;
   const int GH = G / 2;       // ghost width in float2 units
   // x planes that fold onto interior plane xl: this rank's own, the left neighbour's high ghost, the right
@@ -497,31 +507,45 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   const bool y_interior = y0 >= G && y0 + kRows <= ny - G;
   if (y_interior) {
     const int rowp = nzp / 2;   // row pitch in float2
+    constexpr int ZB = ITER < 16 ? ITER : 16;
+    static_assert(ITER % ZB == 0, "row tile must divide evenly over the load batches");
 #pragma unroll
     for (int ix = 0; ix < 3; ++ix) {
       if (!src[ix]) continue;
       const float2* base = reinterpret_cast<const float2*>(src[ix] + (long long)(y0 + G) * nzp) + GH;
 #pragma unroll 1
-      for (int b = 0; b < ITER; b += BATCH) {
-        float2 acc[BATCH], lo[BATCH], hi[BATCH];
+      for (int b = 0; b < ITER; b += ZB) {
+        float2 acc[ZB];
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
+        for (int i = 0; i < ZB; ++i) {
           const int e = threadIdx.x + (b + i) * NT;
           const int r = e / NH, m = e - r * NH;
-          const float2* q = base + r * rowp + m;
-          acc[i] = __ldcs(q);
-          hi[i] = (m < GH) ? __ldcs(q + NH) : make_float2(0.f, 0.f);          // high ghost -> first cells
-          lo[i] = (m >= NH - GH) ? __ldcs(q - NH) : make_float2(0.f, 0.f);    // low ghost -> last cells
+          acc[i] = __ldcs(base + r * rowp + m);
         }
 #pragma unroll
-        for (int i = 0; i < BATCH; ++i) {
+        for (int i = 0; i < ZB; ++i) {
           const int e = threadIdx.x + (b + i) * NT;
           const int r = e / NH, m = e - r * NH;
-          float2 v = cadd(cadd(acc[i], hi[i]), lo[i]);
+          float2 v = acc[i];
           if (ix > 0) v = cadd(v, s[LayRows<NH>::idx(m, r)]);
           s[LayRows<NH>::idx(m, r)] = v;
         }
       }
+    }
+    __syncthreads();
+    // z ghost cells of every source plane: high ghost -> first cells, low ghost -> last cells (2 GH pairs per row)
+    for (int e = threadIdx.x; e < kRows * 2 * GH; e += NT) {
+      const int r = e / (2 * GH), g = e - r * (2 * GH);
+      const int m = g < GH ? g : NH - 2 * GH + g;            // destination pair
+      const int off = g < GH ? NH : -NH;                      // its ghost image
+      float2 v = s[LayRows<NH>::idx(m, r)];
+#pragma unroll
+      for (int ix = 0; ix < 3; ++ix) {
+        if (!src[ix]) continue;
+        const float2* base = reinterpret_cast<const float2*>(src[ix] + (long long)(y0 + G) * nzp) + GH;
+        v = cadd(v, __ldcs(base + r * rowp + m + off));
+      }
+      s[LayRows<NH>::idx(m, r)] = v;
     }
   } else {
 #pragma unroll 2
@@ -573,16 +597,16 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull,
-            const float* __restrict__ az) {
+            const float* __restrict__ az, int x0, int variant) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
   float2* s = sm + NH;        // [16][NH + 1]
   for (int i = threadIdx.x; i < NH; i += NT) tw[i] = twh[i];
-  const int xl = z_pass_plane(sl, blockIdx.y), y0 = blockIdx.x * kRows, comp = blockIdx.z;
+  const int xl = z_pass_plane(sl, x0 + blockIdx.y), y0 = blockIdx.x * kRows, comp = blockIdx.z;
   const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp, nzc = sl.nzc;
   const float2* src = sl.b3[sl.rank] + (long long)comp * lx * ny * nzc + ((long long)xl * ny + y0) * nzc;
-  constexpr int ITER = kRows * NH / NT, BATCH = ITER < 8 ? ITER : 8;
+  constexpr int ITER = kRows * NH / NT, BATCH = ITER < kZinvBatch ? ITER : kZinvBatch;
   static_assert(kRows * NH % NT == 0 && ITER % BATCH == 0, "row tile must divide evenly over the threads");
 #pragma unroll 1
   for (int b = 0; b < ITER; b += BATCH) {
@@ -641,6 +665,27 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   if (xl < ge) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
   if (xl >= lx - ge) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
   const int GH = G / 2;
+  if ((variant & 1) && !dstp[1] && !dstp[2] && y0 >= G && y0 + kRows <= ny - G) {
+    // block without x / y images to write: straight-line, 8 shared-memory loads in flight, then 8 row stores
+    static_assert(NT % NH == 0, "threads per CTA must be a multiple of the row length");
+    constexpr int RPP = NT / NH, RPT = kRows / RPP, RB = RPT < 8 ? RPT : 8;
+    const int m = threadIdx.x % NH, rr = threadIdx.x / NH;
+    const bool zhi = m < GH, zlo = m >= NH - GH;
+#pragma unroll 1
+    for (int b = 0; b < RPT; b += RB) {
+      float2 v[RB];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) v[i] = s[LayRows<NH>::idx(m, rr + (b + i) * RPP)];
+#pragma unroll
+      for (int i = 0; i < RB; ++i) {
+        float2* row = reinterpret_cast<float2*>(dstp[0] + (long long)(y0 + rr + (b + i) * RPP + G) * nzp);
+        row[GH + m] = v[i];
+        if (zhi) row[NH + GH + m] = v[i];
+        if (zlo) row[m - (NH - GH)] = v[i];
+      }
+    }
+    return;
+  }
   for (int e = threadIdx.x; e < kRows * NH; e += NT) {
     const int r = e / NH, m = e - r * NH;
     const int y = y0 + r;
@@ -817,6 +862,9 @@ int32_t pmfft_setup(jpm_plan* p) {
     // rate); JPM_FFT_XC=8|16 overrides
     p->fft_xc = (sl.P > 1 && sl.nx <= 512) ? 16 : 8;
     if (const char* e = getenv("JPM_FFT_YINV_TMA")) p->fft_yinv_tma = e[0] == '1';
+    if (const char* e = getenv("JPM_FFT_CHUNK")) p->fft_chunk = atoi(e);
+    if (const char* e = getenv("JPM_FFT_ZVAR")) p->fft_zvariant = atoi(e);
+    if (const char* e = getenv("JPM_FFT_YINV_PREFETCH")) p->fft_yinv_prefetch = e[0] == '1';
     if (const char* e = getenv("JPM_FFT_XC")) p->fft_xc = (atoi(e) == 16 && sl.nx <= 512) ? 16 : 8;
     if (p->fft_tma_store) {
       if (!p->tm_at) p->tm_at = new TmapPack();
@@ -903,32 +951,39 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   const int nzh = sl.nzh;
   const float norm = 1.0f / ((float)sl.nx * (float)sl.ny * (float)sl.nz);
   const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
-  const dim3 gz(sl.ny / kRows, sl.lx, 1), gz3(sl.ny / kRows, sl.lx, 3);
-  int32_t rc;
-  // every rank has painted: neighbours' ghost planes are final; agree on the ghost width of this step
-  if ((rc = slab_barrier(p, st, true))) return rc;
-#define RUN_ZF(N_)                                                                                             \
-  zfwd_kernel<N_><<<gz, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(sl, p->tw_zh, p->tw_zfull);
-  JPM_FFT_SWITCH(sl.nz, RUN_ZF)
-#undef RUN_ZF
-  JPM_LAUNCH_CHECK();
-  if (p->timer) p->timer->mark(st, "fft_z_r2c+ghost_fold");
   const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
   static const TmapPack kNoMaps{};
   const TmapPack& tat = p->fft_tma_store ? *p->tm_at : kNoMaps;
   const TmapPack& tb3 = p->fft_tma_store ? *p->tm_b3 : kNoMaps;
+  // P == 1: the passes that hand x planes to each other (z-fwd -> y-fwd, y-inv -> z-inv) can run as launch pairs
+  // over chunks of planes, so that the consumer finds the producer's output in L2 (126 MB) instead of HBM
+  const bool chunked = sl.P == 1 && p->fft_chunk > 0 && p->fft_chunk < sl.lx;
+  const int cx = chunked ? p->fft_chunk : sl.lx;
+  int32_t rc;
+  // every rank has painted: neighbours' ghost planes are final; agree on the ghost width of this step
+  if ((rc = slab_barrier(p, st, true))) return rc;
+  for (int x0 = 0; x0 < sl.lx; x0 += cx) {
+    const int nxl = std::min(cx, sl.lx - x0);
+#define RUN_ZF(N_)                                                                                             \
+  zfwd_kernel<N_><<<dim3(sl.ny / kRows, nxl, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
+      sl, p->tw_zh, p->tw_zfull, x0);
+    JPM_FFT_SWITCH(sl.nz, RUN_ZF)
+#undef RUN_ZF
+    JPM_LAUNCH_CHECK();
+    if (p->timer && !chunked) p->timer->mark(st, "fft_z_r2c+ghost_fold");
 #define RUN_YF(N_)                                                                                             \
   if (p->fft_tma_store)                                                                                        \
-    yfwd_kernel<N_, kColsC, true><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
-        sl, p->tw_y, tat);                                                                                     \
+    yfwd_kernel<N_, kColsC, true><<<dim3(nty, nxl, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat, x0);                                                                                 \
   else                                                                                                         \
-    yfwd_kernel<N_, kColsC, false><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
-        sl, p->tw_y, tat);
-  JPM_FFT_SWITCH(sl.ny, RUN_YF)
+    yfwd_kernel<N_, kColsC, false><<<dim3(nty, nxl, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat, x0);
+    JPM_FFT_SWITCH(sl.ny, RUN_YF)
 #undef RUN_YF
-  JPM_LAUNCH_CHECK();
+    JPM_LAUNCH_CHECK();
+  }
   if ((rc = slab_barrier(p, st))) return rc;      // AT complete on every rank
-  if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
+  if (p->timer) p->timer->mark(st, chunked ? "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)" : "fft_y_fwd+transpose");
 #define RUN_X(N_)                                                                                              \
   if constexpr (N_ <= 512) {                                                                                   \
     if (p->fft_tma_store && p->fft_xc == 16) {                                                                 \
@@ -949,24 +1004,29 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   JPM_LAUNCH_CHECK();
   if ((rc = slab_barrier(p, st))) return rc;      // B[0], B[1] complete on every rank
   if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x2+transpose");
+  const int pf = p->fft_yinv_prefetch ? 1 : 0;
+  for (int x0 = 0; x0 < sl.lx; x0 += cx) {
+    const int nxl = std::min(cx, sl.lx - x0);
 #define RUN_YI(N_)                                                                                             \
   if (p->fft_tma_store && p->fft_yinv_tma)                                                                     \
-    yinv_kernel<N_, kXC, true><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), yinv_smem_tma<N_, kXC>(), st>>>( \
-        sl, p->tw_y, p->ay, *p->tm_b3y);                                                                       \
+    yinv_kernel<N_, kXC, true><<<dim3(ntx, nxl, 1), threads_for<N_, kXC, 8>(), yinv_smem_tma<N_, kXC>(), st>>>( \
+        sl, p->tw_y, p->ay, *p->tm_b3y, x0, pf);                                                               \
   else                                                                                                         \
-    yinv_kernel<N_, kXC, false><<<dim3(ntx, sl.lx, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
-        sl, p->tw_y, p->ay, kNoMaps);
-  JPM_FFT_SWITCH(sl.ny, RUN_YI)
+    yinv_kernel<N_, kXC, false><<<dim3(ntx, nxl, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
+        sl, p->tw_y, p->ay, kNoMaps, x0, pf);
+    JPM_FFT_SWITCH(sl.ny, RUN_YI)
 #undef RUN_YI
-  JPM_LAUNCH_CHECK();
-  if (p->timer) p->timer->mark(st, "ifft_y_x3");
+    JPM_LAUNCH_CHECK();
+    if (p->timer && !chunked) p->timer->mark(st, "ifft_y_x3");
 #define RUN_ZI(N_)                                                                                             \
-  zinv_kernel<N_><<<gz3, threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(sl, p->tw_zh, p->tw_zfull, p->az);
-  JPM_FFT_SWITCH(sl.nz, RUN_ZI)
+  zinv_kernel<N_><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
+      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant);
+    JPM_FFT_SWITCH(sl.nz, RUN_ZI)
 #undef RUN_ZI
-  JPM_LAUNCH_CHECK();
+    JPM_LAUNCH_CHECK();
+  }
   if ((rc = slab_barrier(p, st))) return rc;      // force ghost planes written by the neighbours are final
-  if (p->timer) p->timer->mark(st, "ifft_z_c2r_x3+ghost_fill");
+  if (p->timer) p->timer->mark(st, chunked ? "ifft_y_x3|ifft_z_c2r_x3 (chunked pairs)" : "ifft_z_c2r_x3+ghost_fill");
   return JPM_OK;
 }
 
