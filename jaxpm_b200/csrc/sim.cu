@@ -28,6 +28,8 @@
 //   TMA = true : the mesh is the plan's ghost-zone array (plan_internal.cuh), where no box ever wraps:
 //                the read box (3 force meshes) arrives as ONE cp.async.bulk.tensor.4d signalled on an
 //                mbarrier, the paint box leaves as ONE cp.reduce.async.bulk.tensor.3d (.add.f32).
+#include <cstdlib>
+
 #include "plan_internal.cuh"
 
 struct SimGeom {
@@ -62,6 +64,10 @@ struct jpm_sim {
 
 namespace jpm {
 
+#ifndef JPM_L2_AHEAD
+#define JPM_L2_AHEAD 2
+#endif
+constexpr int kL2Ahead = JPM_L2_AHEAD;   // iterations of particle stream requested from L2 ahead of the register prefetch
 constexpr int kTmaMz = 4;   // z margin below a tile in the TMA flavour (== kGhost: box z origin = tile origin in padded coordinates)
 static_assert(kTmaMz == kGhost, "TMA box z origin must coincide with a 16-byte aligned padded coordinate");
 
@@ -215,6 +221,9 @@ sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restric
   }
   if (threadIdx.x == 1023) start[nt] = run;   // the last warp's running total is the grand total
 }
+
+// pull a line of the particle stream into L2 ahead of its use (no register held, unlike a real load)
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 __device__ __forceinline__ void red_add_v2(float* addr, float a, float b) {
   asm volatile("red.global.add.v2.f32 [%0], {%1, %2};" ::"l"(addr), "f"(a), "f"(b) : "memory");
@@ -460,6 +469,7 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
         constexpr int off[8] = {0, 1, SY, SY + 1, SX, SX + 1, SX + SY, SX + SY + 1};
         unsigned old[8];
 #pragma unroll
+#pragma unroll
         for (int c = 0; c < 8; ++c) old[c] = atomicAdd(lo + o + off[c], v[c]);
         // carries out of the low words are rare: count them with the carry flag, branch once
         unsigned ncarry = 0;
@@ -657,6 +667,16 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
       pn = __ldcs(spos + qn);
 #pragma unroll
       for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
+    }
+    if (kL2Ahead > 0) {   // and ask L2 for the lines of the iterations after that
+      const int qf = qn + kL2Ahead * (int)blockDim.x;
+      if (qf < end) {
+        prefetch_l2(spos + qf);
+        if ((threadIdx.x & 3) == 0) {   // one request per 16 bytes of each velocity row is plenty
+#pragma unroll
+          for (int f = 0; f < 3; ++f) prefetch_l2(svel + f * np + qf);
+        }
+      }
     }
     // (1) stencil and destination tile; the slot claim (a global atomic with ~1 us round trip) is
     //     issued right away so that its latency is covered by the gather below
