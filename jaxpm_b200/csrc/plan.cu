@@ -416,7 +416,7 @@ extern "C" int32_t jpm_plan_destroy(jpm_plan* p) {
     if (p->ipc_peers)
       for (int r = 0; r < 8; ++r)
         if (p->peer_base[r]) cudaIpcCloseMemHandle(p->peer_base[r]);
-    p->fft_at = nullptr; p->fft_b3 = nullptr;
+    p->fft_at = nullptr; p->fft_b3 = nullptr; p->fft_t01 = nullptr;
     p->density_p = nullptr; p->force3_p = nullptr;
     if (p->sym_base) cudaFree(p->sym_base);
   }
@@ -577,7 +577,7 @@ extern "C" int32_t jpm_pm_step_host_f32(jpm_plan* p, void* stream, float* pos_ho
 // ---------------------------------------------------------------------------------
 namespace jpm {
 
-struct SlabLayout { size_t dens, force, at, b3, flags, total; };
+struct SlabLayout { size_t dens, force, at, b3, t01, flags, total; };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -588,6 +588,7 @@ static SlabLayout slab_layout(const Slab& sl) {
   L.force = o; o = align_up(o + 3 * (size_t)sl.npad * sizeof(float), 1024);
   L.at = o;    o = align_up(o + (size_t)sl.nx * sl.ly * sl.nzc * sizeof(float2), 1024);
   L.b3 = o;    o = align_up(o + 3 * (size_t)sl.lx * sl.ny * sl.nzc * sizeof(float2), 1024);
+  L.t01 = o;   o = align_up(o + (size_t)sl.lx * sl.ny * sl.nzc * sizeof(float4), 1024);
   L.flags = o; o = align_up(o + 256 * sizeof(unsigned), 1024);
   L.total = o;
   return L;
@@ -604,6 +605,7 @@ static void slab_point(Slab& sl, int r, void* base_v) {
   sl.force[r] = (float*)(base + L.force) + skip;
   sl.at[r] = (float2*)(base + L.at);
   sl.b3[r] = (float2*)(base + L.b3);
+  sl.t01[r] = (float4*)(base + L.t01);
   sl.flags[r] = (unsigned*)(base + L.flags);
 }
 

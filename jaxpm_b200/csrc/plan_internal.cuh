@@ -34,7 +34,10 @@ struct Slab {
   float* dens[8];        // [nxp][nyp][nzp]       density (painted into, ghosts not folded)
   float* force[8];       // [3][nxp][nyp][nzp]    force meshes, ghosts filled
   float2* at[8];         // [nx][ly][nzc]         z,y-transformed density, transposed: all x of the rank's y rows
-  float2* b3[8];         // [3][lx][ny][nzc]      x-inverse-transformed spectra of the rank's x planes
+  float2* b3[8];         // [3][lx][ny][nzc]      y-inverse-transformed spectra of the rank's x planes ([2] doubles as
+                         //                       the z-transformed density the forward y pass reads)
+  float4* t01[8];        // [lx][ny][nzc]         the two x-inverse-transformed spectra (T0, T1) of a mode side by side:
+                         //                       16 bytes per mode, 128-byte rows per 8-column tile (NVLink / DRAM friendly)
   unsigned* flags[8];    // [65] barrier slots (one per peer) + error word
 };
 
@@ -84,19 +87,17 @@ struct jpm_plan {
   // ---- pmfft (csrc/pmfft.cu): hand-written fused FFT chain on the padded meshes, power-of-two shapes --
   float2* fft_at = nullptr;   // P == 1: the AT buffer   [nx][ny][nzc]
   float2* fft_b3 = nullptr;   // P == 1: the B3 buffer   [3][nx][ny][nzc]
+  float4* fft_t01 = nullptr;  // P == 1: the T01 buffer  [nx][ny][nzc]
   float2 *tw_x = nullptr, *tw_y = nullptr, *tw_zh = nullptr, *tw_zfull = nullptr;   // exp(-2 pi i k / n) tables
   // TMA-store flavour of the transposing passes: finished tiles leave shared memory as cp.async.bulk.tensor
   // stores (one box per destination rank), so remote (NVLink) stores do not stall the SM
   bool fft_tma_store = false;
-  bool fft_yinv_tma = false;    // Y-inv pass through TMA stores too (measured slower on one GPU: off unless JPM_FFT_YINV_TMA=1)
+  bool fft_pair = false;         // x pass writes (T0, T1) interleaved into T01 (P > 1) instead of planar B[0], B[1]
   int fft_chunk = 0;            // P == 1: x planes per (z-fwd, y-fwd) / (y-inv, z-inv) launch pair, so that the second
                                 // pass of a pair finds the first one's output in L2 (0 = whole mesh per launch)
-  bool fft_yinv_prefetch = true;   // Y-inv: request T1 before transforming T0 (0.80 -> 0.68 ms at 512^3)
   int fft_zvariant = 1;            // experiments on the z-inverse pass (JPM_FFT_ZVAR bit 0: batched plain epilogue)
-  int fft_xc = 8;               // kz columns per tile of the X-fused pass: 8 (64-byte rows), or 16 (128-byte rows: NVLink)
   TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
-  TmapPack* tm_b3y = nullptr;   // [0]: this rank's B3 with a box along y {16, min(ny,256), 1, 1} (Y-inv pass)
-  TmapPack* tm_b3 = nullptr;    // [d]: B3 of rank d as {2 nzc, ny, lx, 3}, box {16, 1, min(lx,256), 1}
+  TmapPack* tm_t01 = nullptr;   // [d]: T01 of rank d as {4 nzc, ny, lx} floats, box {32, 1, min(lx,256)}
 };
 
 namespace jpm {

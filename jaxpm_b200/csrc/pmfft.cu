@@ -105,6 +105,11 @@ struct LayRows {   // element n of row c, pitch N + 1 (odd number of complex wor
   __device__ __forceinline__ static int idx(int n, int c) { return c * (N + 1) + n; }
 };
 
+template <int C>
+struct LayPair {   // element n of column c in a [N][C][2] tile (T0 and T1 of a mode side by side; base + 0 | 1)
+  __device__ __forceinline__ static int idx(int n, int c) { return (n * C + c) * 2; }
+};
+
 template <class LAY>
 struct SmemIO {
   static constexpr bool kSmem = true;
@@ -228,8 +233,19 @@ struct ScatterYIO {
     __stcs(sl->at[d] + xoff + (long long)yl * sl->nzc + c, v);
   }
 };
-// x-inverse-transformed element (x, c) of row yg goes to the rank that owns x: B[comp][x % lx][yg][kz] there
+// x-inverse-transformed element (x, c) of row yg goes to the rank that owns x: T01[x % lx][yg][kz][comp] there
 struct ScatterXIO {
+  static constexpr bool kSmem = false;
+  const Slab* sl;
+  long long off;    // 2 * (yg * nzc + kz0) + comp   (float2 units)
+  __device__ __forceinline__ void operator()(int n, int c, float2 v) const {
+    const int d = n / sl->lx, xl = n - d * sl->lx;
+    __stcs(reinterpret_cast<float2*>(sl->t01[d]) + off + 2 * ((long long)xl * sl->ny * sl->nzc + c), v);
+  }
+};
+
+// x-inverse-transformed element (x, c) of row yg goes to the rank that owns x: B[comp][x % lx][yg][kz] there
+struct ScatterXPlanarIO {
   static constexpr bool kSmem = false;
   const Slab* sl;
   long long off;    // comp * lx * ny * nzc + yg * nzc + kz0
@@ -281,7 +297,7 @@ yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // (operation order of kspace_kernel<0>, plan.cu); then TWO inverse FFTs along x:
 //   T0 = IFFT_x(i a_x(kx) g delta)  -> B[0]   (x force; a_y, a_z do not depend on kx, so the y and z
 //   T1 = IFFT_x(g delta)            -> B[1]    forces share T1: their factors are applied in Y-inv / Z-inv)
-template <int N, int C, bool TMAST>
+template <int N, int C, bool TMAST, bool PAIR>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
 xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
               const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
@@ -297,7 +313,7 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
   float2* s = sm + N;         // [N][C]
   float* swx = reinterpret_cast<float*>(s + N * C);   // [N] k_x table
   float* sax = swx + N;                               // [N] gradient table
-  float2* s2 = reinterpret_cast<float2*>(sax + N);    // [N][C] second tile (TMAST: T1 is built while T0 drains)
+  float2* so = reinterpret_cast<float2*>(sax + N);    // TMAST: [N][C][2] finished T0 | T1 of every mode, side by side
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; swx[i] = wx[i]; sax[i] = ax[i]; }
   const int kz0 = blockIdx.x * C;
   const int ncol = min(C, sl.nzh - kz0);
@@ -332,7 +348,6 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
       }
     }
   }
-  const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
 #pragma unroll 1
   for (int d = 0; d < 2; ++d) {
     float2 w[TPT][8];
@@ -350,10 +365,15 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
         }
       }
     }
-    if constexpr (TMAST) {
-      float2* sb = d == 0 ? s : s2;
-      SmemIO<LayCols<C>> so{sb};
-      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(sb, tw, ncol, NullIO{}, so, w);
+    if constexpr (TMAST && PAIR) {
+      // the last stage writes the finished column into its half of the pair tile
+      SmemIO<LayPair<C>> stp{so + d};
+      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, stp, w);
+    } else if constexpr (TMAST) {
+      // planar (one GPU): T0 -> B[0], T1 -> B[1]; each finished tile drains while the next one is built
+      float2* sb = d == 0 ? s : so;
+      SmemIO<LayCols<C>> stl{sb};
+      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(sb, tw, ncol, NullIO{}, stl, w);
       fence_async_smem();
       __syncthreads();
       if (threadIdx.x == 0) {
@@ -362,52 +382,73 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
           for (int r0 = 0; r0 < sl.lx; r0 += rows)
             tma_store_4d(&tp.m[dst], 2 * kz0, yg, r0, d, sb + (size_t)(dst * sl.lx + r0) * C);
         tma_store_commit();
+        if (d == 1) tma_store_wait_read();
       }
+    } else if constexpr (PAIR) {
+      ScatterXIO gout{&sl, 2 * ((long long)yg * sl.nzc + kz0) + d};
+      run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
     } else {
-      ScatterXIO gout{&sl, d * cs + (long long)yg * sl.nzc + kz0};
+      const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
+      ScatterXPlanarIO gout{&sl, d * cs + (long long)yg * sl.nzc + kz0};
       run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, w);
     }
   }
-  if constexpr (TMAST) {
-    if (threadIdx.x == 0) tma_store_wait_read();
+  if constexpr (TMAST && PAIR) {
+    // rows [dst lx, (dst+1) lx) of the pair tile (128 bytes each) leave as one tensor store per destination rank
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int rows = min(sl.lx, 256);
+      for (int dst = 0; dst < sl.P; ++dst)
+        for (int r0 = 0; r0 < sl.lx; r0 += rows)
+          tma_store_3d(&tp.m[dst], 4 * kz0, yg, r0, so + (size_t)(dst * sl.lx + r0) * C * 2);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
   }
 }
 
 // ---- Y-inv: inverse FFT along y of the local x planes ---------------------------------------------------
-// grid: (ntile, lx).  B[0] = T0 -> F_x in place;  B[1] = T1 is read ONCE into registers and transformed twice:
-// as it is -> B[2] (F_z up to the factor i a_z(kz), applied by Z-inv) and times i a_y(ky) -> B[1] (F_y).
-template <int N, int C, bool TMAST>
+// grid: (ntile, lx).  One 16-byte load per mode brings T0 and T1 (T01, written by X-fused); T0 -> F_x = B[0];
+// T1 is transformed twice: as it is -> B[2] (F_z up to the factor i a_z(kz), applied by Z-inv) and times
+// i a_y(ky) -> B[1] (F_y).  All loads of the tile are in flight before the first transform starts.
+template <int N, int C, bool PAIR>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
-yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay,
-            const __grid_constant__ TmapPack tp, int x0, int prefetch) {
+yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ ay, int x0) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int R0 = radix_at(N, 0, false);           // first inverse stage (forward radix order)
   constexpr int TASKS = (N / R0) * C;
   constexpr int TPT = (TASKS + NT - 1) / NT;
-  extern __shared__ __align__(128) float2 sm[];
+  extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [N]
   float2* s = sm + N;         // [N][C]
   float* say = reinterpret_cast<float*>(s + N * C);   // [N] gradient table along y
-  float2* s2 = reinterpret_cast<float2*>(say + 2 * N);   // TMAST: tiles of the second and third transform
-  float2* s3 = s2 + N * C;
   for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; say[i] = ay[i]; }
   const int kz0 = blockIdx.x * C, xl = x0 + blockIdx.y;
   const int ncol = min(C, sl.nzh - kz0);
   const long long cs = (long long)sl.lx * sl.ny * sl.nzc;
+  const float4* in = PAIR ? sl.t01[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0 : nullptr;
   float2* base = sl.b3[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0;
   GlobalIO g0{base, sl.nzc}, g1{base + cs, sl.nzc}, g2{base + 2 * cs, sl.nzc};
-  // TMAST: a finished tile leaves shared memory as tensor stores (<= 256 rows per box) while the next transform runs
-  auto drain = [&](const float2* tile, int comp) {
-    fence_async_smem();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      const int rows = min(N, 256);
-      for (int r0 = 0; r0 < N; r0 += rows) tma_store_4d(&tp.m[0], 2 * kz0, r0, xl, comp, tile + (size_t)r0 * C);
-      tma_store_commit();
-    }
-  };
   float2 keep[TPT][8];
-  auto load_keep = [&]() {
+  if constexpr (PAIR) {
+    float2 w[TPT][8];
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int task = threadIdx.x + i * NT;
+      const int c = task % C, j = task / C;
+      if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) {
+          const float4 v = __ldcs(in + (long long)(j + r * (N / R0)) * sl.nzc + c);
+          w[i][r] = make_float2(v.x, v.y);
+          keep[i][r] = make_float2(v.z, v.w);
+        }
+      }
+    }
+    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g0, w);
+  } else {
+    // planar (one GPU): T0 = B[0] is transformed in place, T1 = B[1] is requested BEFORE that transform starts
 #pragma unroll
     for (int i = 0; i < TPT; ++i) {
       const int task = threadIdx.x + i * NT;
@@ -417,32 +458,18 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
         for (int r = 0; r < R0; ++r) keep[i][r] = g1(j + r * (N / R0), c);
       }
     }
-  };
-  // prefetch: T1 is requested before T0 is transformed, so its latency hides behind that transform
-  if (prefetch) load_keep();
-  if constexpr (TMAST) {
-    SmemIO<LayCols<C>> so{s};
-    run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, so, nullptr);
-    drain(s, 0);
-  } else {
     run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, g0, g0, nullptr);
   }
-  if (!prefetch) load_keep();
-  if constexpr (!TMAST) __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
+  __syncthreads();   // the T0 transform is done with `s` (its last stage reads it)
   {
     float2 w[TPT][8];
 #pragma unroll
     for (int i = 0; i < TPT; ++i)
 #pragma unroll
       for (int r = 0; r < R0; ++r) w[i][r] = keep[i][r];
-    if constexpr (TMAST) {
-      SmemIO<LayCols<C>> so{s2};
-      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s2, tw, ncol, NullIO{}, so, w);
-      drain(s2, 2);
-    } else {
-      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g2, w);
-    }
+    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g2, w);
   }
+  __syncthreads();
   {
     float2 w[TPT][8];
 #pragma unroll
@@ -455,14 +482,7 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
         w[i][r] = make_float2(-a * keep[i][r].y, a * keep[i][r].x);       // i a_y T1
       }
     }
-    if constexpr (TMAST) {
-      SmemIO<LayCols<C>> so{s3};
-      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s3, tw, ncol, NullIO{}, so, w);
-      drain(s3, 1);
-      if (threadIdx.x == 0) tma_store_wait_read();
-    } else {
-      run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g1, w);
-    }
+    run_stages<N, C, NT, true, false, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, g1, w);
   }
 }
 
@@ -780,8 +800,8 @@ static bool pow2_in_range(int n) { return n >= 16 && n <= 1024 && (n & (n - 1)) 
 
 template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C) * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
-template <int N, int C> constexpr size_t yinv_smem_tma() { return xfused_smem<N, C>() + 2 * (size_t)N * C * sizeof(float2); }
-template <int N, int C> constexpr size_t xfused_smem_tma() { return xfused_smem<N, C>() + (size_t)N * C * sizeof(float2); }
+template <int N, int C> constexpr size_t xfused_smem_tma() { return xfused_smem<N, C>() + 2 * (size_t)N * C * sizeof(float2); }
+template <int N, int C> constexpr size_t xfused_smem_tma_planar() { return xfused_smem<N, C>() + (size_t)N * C * sizeof(float2); }
 template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
 
 constexpr int kColsC = 16;   // kz columns per tile of the Y-fwd pass (128-byte segments)
@@ -808,18 +828,18 @@ static int32_t set_attrs(const Slab& sl) {
   JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                 (int)xfused_smem<N_, kXC>()));                                                  \
   JPM_CUDA(cudaFuncSetAttribute(yinv_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
-                                (int)yinv_smem_tma<N_, kXC>()));
+                                (int)xfused_smem<N_, kXC>()));
   JPM_FFT_SWITCH(sl.ny, ATTR_Y)
 #undef ATTR_Y
 #define ATTR_X(N_)                                                                                              \
-  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)xfused_smem<N_, kXC>()));                                                  \
-  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
-                                (int)xfused_smem_tma<N_, kXC>()));                                              \
-  if constexpr (N_ <= 512) {                                                                                    \
-    JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
-                                  (int)xfused_smem_tma<N_, 16>()));                                             \
-  }
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)xfused_smem<N_, kXC>()));                                                  \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)xfused_smem_tma_planar<N_, kXC>()));                                              \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)xfused_smem_tma<N_, kXC>()));
   JPM_FFT_SWITCH(sl.nx, ATTR_X)
 #undef ATTR_X
 #define ATTR_Z(N_)                                                                                              \
@@ -856,40 +876,39 @@ int32_t pmfft_setup(jpm_plan* p) {
   {
     const char* env = getenv("JPM_FFT_TMASTORE");
     p->fft_tma_store = !(env && env[0] == '0') && sl.lx >= 2 && sl.ly >= 2 &&
-                       (sl.lx <= 256 || sl.lx % 256 == 0) && (sl.ly <= 256 || sl.ly % 256 == 0) &&
-                       (sl.ny <= 256 || sl.ny % 256 == 0);
-    // 128-byte rows for the x pass when its output crosses NVLink (64-byte writes reach about half the link
-    // rate); JPM_FFT_XC=8|16 overrides
-    p->fft_xc = (sl.P > 1 && sl.nx <= 512) ? 16 : 8;
-    if (const char* e = getenv("JPM_FFT_YINV_TMA")) p->fft_yinv_tma = e[0] == '1';
+                       (sl.lx <= 256 || sl.lx % 256 == 0) && (sl.ly <= 256 || sl.ly % 256 == 0);
+    // interleaved (T0, T1) output of the x pass when it crosses NVLink (128-byte rows, one store per mode pair);
+    // planar on one GPU, where the per-transform drain overlaps better (JPM_FFT_PAIR=0|1 overrides)
+    p->fft_pair = sl.P > 1;
+    if (const char* e = getenv("JPM_FFT_PAIR")) p->fft_pair = e[0] == '1';
+    if (p->fft_pair && !sl.t01[sl.rank]) {
+      set_error("pmfft: the pair layout needs the T01 buffer");
+      return JPM_ERR_INVALID;
+    }
     if (const char* e = getenv("JPM_FFT_CHUNK")) p->fft_chunk = atoi(e);
     if (const char* e = getenv("JPM_FFT_ZVAR")) p->fft_zvariant = atoi(e);
-    if (const char* e = getenv("JPM_FFT_YINV_PREFETCH")) p->fft_yinv_prefetch = e[0] == '1';
-    if (const char* e = getenv("JPM_FFT_XC")) p->fft_xc = (atoi(e) == 16 && sl.nx <= 512) ? 16 : 8;
     if (p->fft_tma_store) {
       if (!p->tm_at) p->tm_at = new TmapPack();
-      if (!p->tm_b3) p->tm_b3 = new TmapPack();
-      if (!p->tm_b3y) p->tm_b3y = new TmapPack();
-      memset(p->tm_b3y, 0, sizeof(TmapPack));
-      {
-        const unsigned long long rw = (unsigned long long)sl.nzc * sizeof(float2);
-        const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
-        const unsigned long long sb[3] = {rw, rw * sl.ny, rw * sl.ny * sl.lx};
-        const unsigned bb[4] = {2u * fft::kXC, (unsigned)std::min(sl.ny, 256), 1u, 1u};
-        if ((rc = encode_tensor_map(&p->tm_b3y->m[0], reinterpret_cast<float*>(sl.b3[sl.rank]), 4, db, sb, bb))) return rc;
-      }
+      if (!p->tm_t01) p->tm_t01 = new TmapPack();
       memset(p->tm_at, 0, sizeof(TmapPack));
-      memset(p->tm_b3, 0, sizeof(TmapPack));
+      memset(p->tm_t01, 0, sizeof(TmapPack));
       const unsigned long long row = (unsigned long long)sl.nzc * sizeof(float2);
       for (int d = 0; d < sl.P; ++d) {
         const unsigned long long da[3] = {2ull * sl.nzc, (unsigned long long)sl.ly, (unsigned long long)sl.nx};
         const unsigned long long sa[2] = {row, row * sl.ly};
         const unsigned ba[3] = {2u * fft::kColsC, (unsigned)std::min(sl.ly, 256), 1u};
         if ((rc = encode_tensor_map(&p->tm_at->m[d], reinterpret_cast<float*>(sl.at[d]), 3, da, sa, ba))) return rc;
-        const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
-        const unsigned long long sb[3] = {row, row * sl.ny, row * sl.ny * sl.lx};
-        const unsigned bb[4] = {2u * (unsigned)p->fft_xc, 1u, (unsigned)std::min(sl.lx, 256), 1u};
-        if ((rc = encode_tensor_map(&p->tm_b3->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bb))) return rc;
+        if (p->fft_pair) {
+          const unsigned long long dt[3] = {4ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx};
+          const unsigned long long st[2] = {2 * row, 2 * row * sl.ny};
+          const unsigned bt[3] = {4u * fft::kXC, 1u, (unsigned)std::min(sl.lx, 256)};
+          if ((rc = encode_tensor_map(&p->tm_t01->m[d], reinterpret_cast<float*>(sl.t01[d]), 3, dt, st, bt))) return rc;
+        } else {
+          const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
+          const unsigned long long sb[3] = {row, row * sl.ny, row * sl.ny * sl.lx};
+          const unsigned bb[4] = {2u * fft::kXC, 1u, (unsigned)std::min(sl.lx, 256), 1u};
+          if ((rc = encode_tensor_map(&p->tm_t01->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bb))) return rc;
+        }
       }
     }
   }
@@ -915,7 +934,14 @@ int32_t pmfft_enable(jpm_plan* p) {
   JPM_CUDA(cudaMalloc(&p->fft_b3, 3 * na * sizeof(float2)));
   JPM_CUDA(cudaMemset(p->fft_at, 0, na * sizeof(float2)));
   JPM_CUDA(cudaMemset(p->fft_b3, 0, 3 * na * sizeof(float2)));
-  sl.dens[0] = p->density_p; sl.force[0] = p->force3_p; sl.at[0] = p->fft_at; sl.b3[0] = p->fft_b3;
+  {
+    const char* e = getenv("JPM_FFT_PAIR");     // one GPU uses the planar layout unless asked otherwise
+    if (e && e[0] == '1') {
+      JPM_CUDA(cudaMalloc(&p->fft_t01, na * sizeof(float4)));
+      JPM_CUDA(cudaMemset(p->fft_t01, 0, na * sizeof(float4)));
+    }
+  }
+  sl.dens[0] = p->density_p; sl.force[0] = p->force3_p; sl.at[0] = p->fft_at; sl.b3[0] = p->fft_b3; sl.t01[0] = p->fft_t01;
   int32_t rc = pmfft_setup(p);
   if (rc) return rc;
   p->fft_on = true;
@@ -924,12 +950,11 @@ int32_t pmfft_enable(jpm_plan* p) {
 
 void pmfft_destroy(jpm_plan* p) {
   delete p->tm_at; p->tm_at = nullptr;
-  delete p->tm_b3; p->tm_b3 = nullptr;
-  delete p->tm_b3y; p->tm_b3y = nullptr;
-  void* bufs[] = {p->fft_at, p->fft_b3, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
+  delete p->tm_t01; p->tm_t01 = nullptr;
+  void* bufs[] = {p->fft_at, p->fft_b3, p->fft_t01, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
   for (void* b : bufs)
     if (b) cudaFree(b);
-  p->fft_at = nullptr; p->fft_b3 = nullptr;
+  p->fft_at = nullptr; p->fft_b3 = nullptr; p->fft_t01 = nullptr;
   p->fft_on = false;
 }
 
@@ -954,7 +979,8 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
   static const TmapPack kNoMaps{};
   const TmapPack& tat = p->fft_tma_store ? *p->tm_at : kNoMaps;
-  const TmapPack& tb3 = p->fft_tma_store ? *p->tm_b3 : kNoMaps;
+  const bool pair = p->fft_pair;
+  const TmapPack& tb3 = p->fft_tma_store ? *p->tm_t01 : kNoMaps;   // T01 maps (pair) or planar B3 maps
   // P == 1: the passes that hand x planes to each other (z-fwd -> y-fwd, y-inv -> z-inv) can run as launch pairs
   // over chunks of planes, so that the consumer finds the producer's output in L2 (126 MB) instead of HBM
   const bool chunked = sl.P == 1 && p->fft_chunk > 0 && p->fft_chunk < sl.lx;
@@ -985,35 +1011,32 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   if ((rc = slab_barrier(p, st))) return rc;      // AT complete on every rank
   if (p->timer) p->timer->mark(st, chunked ? "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)" : "fft_y_fwd+transpose");
 #define RUN_X(N_)                                                                                              \
-  if constexpr (N_ <= 512) {                                                                                   \
-    if (p->fft_tma_store && p->fft_xc == 16) {                                                                 \
-      xfused_kernel<N_, 16, true><<<dim3((nzh + 15) / 16, sl.ly, 1), threads_for<N_, 16, 8>(),                 \
-                                    xfused_smem_tma<N_, 16>(), st>>>(                                          \
-          sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);   \
-      break;                                                                                                   \
-    }                                                                                                          \
-  }                                                                                                            \
-  if (p->fft_tma_store)                                                                                        \
-    xfused_kernel<N_, kXC, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma<N_, kXC>(), st>>>( \
+  if (p->fft_tma_store && pair)                                                                                \
+    xfused_kernel<N_, kXC, true, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+  else if (p->fft_tma_store)                                                                                   \
+    xfused_kernel<N_, kXC, true, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma_planar<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+  else if (pair)                                                                                               \
+    xfused_kernel<N_, kXC, false, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
         sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
   else                                                                                                         \
-    xfused_kernel<N_, kXC, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
+    xfused_kernel<N_, kXC, false, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
         sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);
   JPM_FFT_SWITCH(sl.nx, RUN_X)
 #undef RUN_X
   JPM_LAUNCH_CHECK();
   if ((rc = slab_barrier(p, st))) return rc;      // B[0], B[1] complete on every rank
   if (p->timer) p->timer->mark(st, "fft_x_fwd+greens_grad+ifft_x_x2+transpose");
-  const int pf = p->fft_yinv_prefetch ? 1 : 0;
   for (int x0 = 0; x0 < sl.lx; x0 += cx) {
     const int nxl = std::min(cx, sl.lx - x0);
 #define RUN_YI(N_)                                                                                             \
-  if (p->fft_tma_store && p->fft_yinv_tma)                                                                     \
-    yinv_kernel<N_, kXC, true><<<dim3(ntx, nxl, 1), threads_for<N_, kXC, 8>(), yinv_smem_tma<N_, kXC>(), st>>>( \
-        sl, p->tw_y, p->ay, *p->tm_b3y, x0, pf);                                                               \
+  if (pair)                                                                                                    \
+    yinv_kernel<N_, kXC, true><<<dim3(ntx, nxl, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>(  \
+        sl, p->tw_y, p->ay, x0);                                                                               \
   else                                                                                                         \
     yinv_kernel<N_, kXC, false><<<dim3(ntx, nxl, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
-        sl, p->tw_y, p->ay, kNoMaps, x0, pf);
+        sl, p->tw_y, p->ay, x0);
     JPM_FFT_SWITCH(sl.ny, RUN_YI)
 #undef RUN_YI
     JPM_LAUNCH_CHECK();
