@@ -103,6 +103,23 @@ def run_multi(args, world, rank, dev):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         timing = {"stage_ms_max_over_ranks": {n: round(float(v), 4) for n, v in zip(names, tt)},
                   "ghost_planes_used": stepper.plan.ghost_width(), "ghost_planes_allocated": h}
+    # NVLink bytes this rank sends + receives per step on the slab path (remote stores of the two FFT transposes,
+    # ghost planes read for the halo reduce, ghost planes written for the halo fill), against the measured
+    # 770 GB/s per direction of /opt/skills/guides/B200_PROFILING.md
+    nvlink = None
+    if fused:
+        nzc = (N // 2 + 1 + 7) // 8 * 8
+        lxl = N // world
+        remote = (world - 1) / world
+        transposes = (lxl * N * nzc * 8) * remote * 3          # AT (1 spectrum) + T01 (2 spectra) leaving the rank
+        ge = timing["ghost_planes_used"]
+        plane = (N + 8) * (N + 8) * 4
+        ghosts_out = 3 * 2 * ge * plane                          # force ghost planes written to the two neighbours
+        ghosts_in = 2 * ge * plane                               # density ghost planes read from them
+        sent = transposes + ghosts_out
+        nvlink = {"sent_bytes_per_rank_per_step": int(sent), "read_bytes_per_rank_per_step": int(ghosts_in),
+                  "sent_GBps_over_whole_step": sent * K / t_dev / 1e9, "peak_GBps_per_direction": 770.0,
+                  "frac_of_link_if_not_overlapped": sent / 770e9 / (t_dev / K)}
     peak, peak_kind = _peaks()
     step_alg_bytes = (60 + 64) * npart
     if rank == 0:
@@ -122,7 +139,7 @@ def run_multi(args, world, rank, dev):
                          "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": step_alg_bytes * K / t_dev / 1e9 / world / peak, "traffic": None},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "timing": timing,
+            "timing": timing, "nvlink": nvlink,
         }))
     stepper.close()
     dist.destroy_process_group()

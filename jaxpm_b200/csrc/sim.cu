@@ -65,7 +65,7 @@ struct jpm_sim {
 namespace jpm {
 
 #ifndef JPM_L2_AHEAD
-#define JPM_L2_AHEAD 2
+#define JPM_L2_AHEAD 1
 #endif
 constexpr int kL2Ahead = JPM_L2_AHEAD;   // iterations of particle stream requested from L2 ahead of the register prefetch
 constexpr int kTmaMz = 4;   // z margin below a tile in the TMA flavour (== kGhost: box z origin = tile origin in padded coordinates)
@@ -606,7 +606,7 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
                 const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ f0,
                 const float* __restrict__ f1, const float* __restrict__ f2, float kick, float drift,
                 long long np, int* __restrict__ cursor, float4* __restrict__ npos,
-                float* __restrict__ nvel, unsigned long long* __restrict__ stats) {
+                float* __restrict__ nvel, unsigned long long* __restrict__ stats, int l2ahead) {
   constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
   constexpr int BZ = TMA ? ((T + MZ + M + 1 + 3) & ~3) : B, NBOX = B * B * BZ;
   extern __shared__ __align__(128) float box[];        // [3][B][B][BZ]
@@ -668,8 +668,8 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
 #pragma unroll
       for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
     }
-    if (kL2Ahead > 0) {   // and ask L2 for the lines of the iterations after that
-      const int qf = qn + kL2Ahead * (int)blockDim.x;
+    if (l2ahead > 0) {   // and ask L2 for the lines of the iterations after that
+      const int qf = qn + l2ahead * (int)blockDim.x;
       if (qf < end) {
         prefetch_l2(spos + qf);
         if ((threadIdx.x & 3) == 0) {   // one request per 16 bytes of each velocity row is plenty
@@ -991,16 +991,17 @@ static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const
   JPM_LAUNCH_CHECK();
   const int ts = s->g.tshift, m = s->g.m;
   const SimGeom& g = tma ? s->gp : s->g;
+  static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
 #define LAUNCH_READ_T(TS_, M_, TMA_)                                                                     \
   {                                                                                                      \
     if (s->relative)                                                                                     \
       sim_read_kernel<true, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(               \
           s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
-          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                             \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead);                    \
     else                                                                                                 \
       sim_read_kernel<false, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(              \
           s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
-          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats);                             \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead);                    \
   }
 #define LAUNCH_READ(TS_, M_) LAUNCH_READ_T(TS_, M_, false)
 #define LAUNCH_READ_TMA(TS_, M_) LAUNCH_READ_T(TS_, M_, true)

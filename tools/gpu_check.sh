@@ -30,9 +30,10 @@ if [[ $STAGES == *launches* ]]; then
   echo "launches rc=$?"
 fi
 if [[ $STAGES == *full* ]]; then
+  # one `ncu --set full` capture of every own kernel of one PM step (the 38th: 37 untimed steps before it)
   timeout 1200 ncu --set full --clock-control none --import-source on \
-      -k regex:'sim_paint_kernel|sim_read_kernel|kspace_kernel' -s 106 -c 3 -f -o $OUT/prof_sim \
-      python bench.py --no-cpu --e2e-steps 1 > $OUT/full_run.log 2>&1
+      -k regex:'sim_paint_kernel|sim_read_kernel|xfused_kernel|zinv_kernel|zfwd_kernel|yfwd_kernel|yinv_kernel' -s 266 -c 7 -f -o $OUT/prof_step \
+      python bench.py --no-cpu --e2e-steps 1 --steps 3 --warmup 3 > $OUT/full_run.log 2>&1
   echo "full rc=$?"
 fi
 ls -la $OUT
