@@ -256,12 +256,24 @@ def run_gpu(args):
     for v in kernels.values():
         v["GBps"] = v["alg_bytes"] / v["s"] / 1e9 if v["s"] > 0 else 0.0
         v["frac"] = v["GBps"] / peak
+    # DRAM traffic of each kernel from the committed `ncu --set full` capture of this workload (profiles/), per launch
+    traffic = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", f"traffic_{N}.json")) as f:
+            tj = json.load(f)["kernels"]
+        traffic = {"sim_paint": tj["sim_paint_kernel"]["traffic"], "tile_scan+sim_read3_kick_drift": tj["sim_read_kernel"]["traffic"],
+                   "fft_z_r2c+ghost_fold": tj["zfwd_kernel"]["traffic"], "fft_y_fwd+transpose": tj["yfwd_kernel"]["traffic"],
+                   "fft_x_fwd+greens_grad+ifft_x_x2+transpose": tj["xfused_kernel"]["traffic"],
+                   "ifft_y_x3": tj["yinv_kernel"]["traffic"], "ifft_z_c2r_x3+ghost_fill": tj["zinv_kernel"]["traffic"]}
+    except Exception:
+        pass
     own = {n: v for n, v in kernels.items() if "cuFFT" not in n and n != "mesh_memset" and "direct" not in n}
     dom_name = max(own, key=lambda n: own[n]["s"])
     dom = own[dom_name]
     step_alg_bytes = 60 * npart + 64 * nc
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak,
-                "peak_kind": peak_kind, "unit": "GB/s", "frac": dom["frac"], "traffic": None,
+                "peak_kind": peak_kind, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic.get(dom_name),
+                "alg_bytes": dom["alg_bytes"],
                 "step_achieved": step_alg_bytes * K / t_dev / 1e9,
                 "step_frac": step_alg_bytes * K / t_dev / 1e9 / peak,
                 "kernels": {n: {"ms": round(v["s"] * 1e3, 4), "GBps": round(v["GBps"], 1),
