@@ -334,7 +334,7 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
         const float kx = swx[j + r * (N / RL)];
         const float kxy2 = kx * kx + ky * ky;
         const float kk = kxy2 + kz * kz;
-        float g = (kk == 0.f) ? 0.f : (1.0f / kk);
+        float g = (kk == 0.f) ? 0.f : __frcp_rn(kk);   // correctly rounded, == 1.0f / kk
         g *= norm;
         if (r_split2 != 0.f) g *= expf(-kk * r_split2);
         if (ftab) {
