@@ -211,6 +211,26 @@ int32_t jpm_pm_step_host_f32(jpm_plan* plan, void* stream, float* pos_host, floa
                              float* pos_dev, float* vel_dev, float kick_coef, float drift_coef,
                              int32_t relative);
 
+/* ------------------------------------------------------------------------
+ * power-spectrum estimator on the R2C half-spectrum and its adjoint
+ *   replaces jaxpm/utils.py:14-73 (_initialize_pk) + :76-128 (power_spectrum)
+ * ---------------------------------------------------------------------- */
+/* spec_a (and spec_b for a cross spectrum, else NULL): complex64 half-spectra [nx][ny][nz/2+1] of UNNORMALISED
+ * forward transforms; norm = 1/(nx ny nz) gives the reference's 'ortho' convention.  kx[nx], ky[ny], kz[nz/2+1]:
+ * DEVICE float64 physical wavenumbers per axis ((2 pi m / l) fftfreq(m), utils.py:51-53); kedges[n_edges]: DEVICE
+ * float64 bin edges.  ells[n_ell] (HOST, each 0, 2 or 4) and los3 (HOST unit vector; may be NULL when all ells
+ * are 0).  out (DEVICE float64, zeroed here): [n_ell][nb] real sums | [n_ell][nb] imaginary sums |
+ * [nb] mode counts | [nb] sums of |k| (the last two only if want_counts), nb = n_edges + 1 bins of np.digitize. */
+int32_t jpm_pk_bin_c64(void* stream, const void* spec_a, const void* spec_b, int32_t nx, int32_t ny, int32_t nz,
+                       const double* kx, const double* ky, const double* kz, const double* kedges, int32_t n_edges,
+                       const int32_t* ells, int32_t n_ell, const float* los3, float norm, int32_t want_counts,
+                       double* out);
+/* Adjoint of the auto spectrum: out_k = spec_a_k * 2 norm sum_l wbin[l][bin(k)] (2l+1) L_l(mu_k); the unnormalised
+ * C2R of `out` is d(sum_lb g_lb pk_l[b]) / d mesh for wbin[l][b] = g_lb * cell volume / kcount[b] (DEVICE float64). */
+int32_t jpm_pk_weight_c64(void* stream, const void* spec_a, void* out, int32_t nx, int32_t ny, int32_t nz,
+                          const double* kx, const double* ky, const double* kz, const double* kedges, int32_t n_edges,
+                          const int32_t* ells, int32_t n_ell, const float* los3, const double* wbin, float norm);
+
 /* Test / debug access to the ghost-zone meshes the resident step (jpm_sim_step) works on: which = 0 the
  * painted density (ghosts not folded), 1..3 a force component (ghosts filled).  dims3 (nullable) receives the
  * padded extents; dst (nullable) the whole padded array [dims3[0]][dims3[1]][dims3[2]]. */
