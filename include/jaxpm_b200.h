@@ -231,6 +231,12 @@ int32_t jpm_pk_weight_c64(void* stream, const void* spec_a, void* out, int32_t n
                           const double* kx, const double* ky, const double* kz, const double* kedges, int32_t n_edges,
                           const int32_t* ells, int32_t n_ell, const float* los3, const double* wbin, float norm);
 
+/* Half-spectrum times a separable real filter: out_k = in_k * norm * tx[ix] ty[iy] tz[iz] (tables are DEVICE
+ * float32 of lengths nx, ny, nz/2+1; in place allowed).  compensate_cic of jaxpm/painting.py:263-275 is
+ * R2C -> this with t_d = sinc(k_d / 2 pi)^-2 (kernels.py:118-136) -> C2R. */
+int32_t jpm_kseparable_c64(void* stream, const void* in, void* out, const float* tx, const float* ty, const float* tz,
+                           int32_t nx, int32_t ny, int32_t nz, float norm);
+
 /* Test / debug access to the ghost-zone meshes the resident step (jpm_sim_step) works on: which = 0 the
  * painted density (ghosts not folded), 1..3 a force component (ghosts filled).  dims3 (nullable) receives the
  * padded extents; dst (nullable) the whole padded array [dims3[0]][dims3[1]][dims3[2]]. */

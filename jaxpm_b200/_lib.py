@@ -46,6 +46,7 @@ SIGNATURES = {
                         vp], i32),
     "jpm_pk_weight_c64": ([vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32), i32, C.POINTER(f32), vp,
                            f32], i32),
+    "jpm_kseparable_c64": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, f32], i32),
     "jpm_plan_padded_get_f32": ([vp, vp, i32, vp, C.POINTER(i32)], i32),
     "jpm_slab_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
     "jpm_slab_ipc_handle": ([vp, vp, i32], i32),

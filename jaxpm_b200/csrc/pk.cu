@@ -231,3 +231,34 @@ extern "C" int32_t jpm_pk_weight_c64(void* stream, const void* spec_a, void* out
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }
+
+// spectrum times a separable real filter: out_k = in_k * norm * tx[ix] ty[iy] tz[iz]  (one pass; in place allowed).
+//   used by compensate_cic (jaxpm/painting.py:263-275 with kernels.py:118-136: the filter of that function is
+//   prod_d sinc(k_d / 2 pi)^-2, a product of per-axis factors)
+namespace jpm {
+__global__ void __launch_bounds__(256)
+kseparable_kernel(const float2* __restrict__ in, float2* __restrict__ out, const float* __restrict__ tx,
+                  const float* __restrict__ ty, const float* __restrict__ tz, int nx, int ny, int nzh, float norm) {
+  const long long nrows = (long long)nx * ny;
+  for (long long row = blockIdx.x; row < nrows; row += gridDim.x) {
+    const float fxy = norm * (tx[row / ny] * ty[row % ny]);
+    for (int iz = threadIdx.x; iz < nzh; iz += blockDim.x) {
+      const long long o = row * nzh + iz;
+      const float f = fxy * tz[iz];
+      const float2 v = in[o];
+      out[o] = make_float2(f * v.x, f * v.y);
+    }
+  }
+}
+}  // namespace jpm
+
+extern "C" int32_t jpm_kseparable_c64(void* stream, const void* in, void* out, const float* tx, const float* ty,
+                                      const float* tz, int32_t nx, int32_t ny, int32_t nz, float norm) {
+  JPM_CHECK_ARG(in && out && tx && ty && tz && nx > 0 && ny > 0 && nz > 0, "bad arguments");
+  const long long rows = (long long)nx * ny;
+  const int blocks = (int)std::min<long long>(rows, (long long)jpm::kNumSMs * 8);
+  jpm::kseparable_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const float2*)in, (float2*)out, tx, ty, tz, nx, ny,
+                                                                  nz / 2 + 1, norm);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}

@@ -167,3 +167,38 @@ def cic_read_dx(grid_mesh, disp, halo_size=0, sharding=None):
         from . import distributed
         return distributed.sharded_cic_read_dx(grid_mesh, disp, halo_size, sharding)
     return _CicReadDx.apply(grid_mesh, disp, (0, 0))
+
+
+class _CompensateCic(torch.autograd.Function):
+    """R2C -> separable sinc^-2 filter -> C2R; a real symmetric linear operator, so it is its own adjoint."""
+
+    @staticmethod
+    def forward(ctx, field):
+        import numpy as np
+        from ._lib import call, ptr, stream
+        plan = ops.get_plan(tuple(field.shape), field.device)
+        nx, ny, nz = plan.shape
+        key = ("cic_comp", plan.shape, field.device.index or 0)
+        tabs = _tables.get(key)
+        if tabs is None:
+            # kernels.py:133-135: kwts_d = sinc(k_d / 2 pi) in float32 with k_d = 2 pi fftfreq(n_d); wts = (prod kwts)^-2
+            mk = lambda n, nh: torch.as_tensor((np.sinc(np.fft.fftfreq(n)[:nh].astype(np.float32)).astype(np.float32))**-2.0,
+                                               dtype=torch.float32).to(field.device)
+            tabs = _tables[key] = (mk(nx, nx), mk(ny, ny), mk(nz, nz // 2 + 1))
+        spec = ops.rfft3(field, plan)
+        call("jpm_kseparable_c64", stream(), ptr(spec), ptr(spec), ptr(tabs[0]), ptr(tabs[1]), ptr(tabs[2]), nx, ny, nz,
+             1.0 / plan.ncell)
+        return ops.irfft3_(spec, plan, batch=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _CompensateCic.apply(g.contiguous())
+
+
+_tables = {}
+
+
+def compensate_cic(field):
+    """Compensate for CIC painting (jaxpm/painting.py:263-275): divide the spectrum by the CIC window
+    prod_d sinc(k_d / 2 pi)^2 (kernels.py:118-136) and transform back."""
+    return _CompensateCic.apply(as_f32(field))
