@@ -164,3 +164,46 @@ def _halo_worker(rank, world, pdims, shape, h):
 @pytest.mark.parametrize("pdims", [(2, 1), (1, 2), (2, 2)])
 def test_halo_protocol(pdims):
     _run(_halo_worker, pdims[0] * pdims[1], pdims, (16, 16, 6), 4)
+
+
+# ---- slab path: host-side logic (the kernels are CUDA-only; the handle exchange and the routing rule are not) ----
+class _FakeSlabPlan:
+    """Stands in for slab.SlabPlan: a rank-tagged 64-byte 'IPC handle' and a record of what was attached."""
+
+    def __init__(self, nranks, rank):
+        self.nranks, self.rank, self.attached, self.got = nranks, rank, False, None
+
+    def ipc_handle(self):
+        return bytes([self.rank]) * 64
+
+    def attach_ipc(self, handles):
+        self.got, self.attached = list(handles), True
+
+
+def _slab_connect_worker(rank, world):
+    from jaxpm_b200 import slab
+    plan = _FakeSlabPlan(world, rank)
+    slab.connect(plan)
+    assert plan.attached and len(plan.got) == world
+    for r, h in enumerate(plan.got):          # rank order, every rank sees every handle
+        assert h == bytes([r]) * 64
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_slab_handle_exchange(world):
+    """slab.connect gathers the ranks' 64-byte handles in rank order (gloo here, NCCL on the box)."""
+    _run(_slab_connect_worker, world)
+
+
+def test_slab_routing_rule():
+    """Which decompositions take the fused peer-memory stepper (slab.slab_supported): (P, 1) grids on power-of-two
+    meshes with the halo inside one slab; everything else stays on the NCCL path."""
+    from jaxpm_b200.slab import slab_supported
+    assert slab_supported((512, 512, 512), (8, 1), 64)
+    assert slab_supported((1024, 1024, 1024), (8, 1), 64)
+    assert slab_supported((32, 32, 32), (2, 1), 8)
+    assert not slab_supported((512, 512, 512), (1, 8), 64)        # y slabs
+    assert not slab_supported((512, 512, 512), (4, 2), 64)        # pencils
+    assert not slab_supported((32, 32, 24), (2, 1), 8)            # not a power of two
+    assert not slab_supported((512, 512, 512), (8, 1), 65)        # halo wider than a slab
+    assert not slab_supported((64, 64, 64), (8, 1), 0)
