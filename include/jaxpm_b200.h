@@ -130,6 +130,11 @@ int32_t jpm_cic_readgrad_f32(void* stream, float* value, float* grad, const floa
                              float grad_scale_scalar, int64_t np, int32_t nx, int32_t ny,
                              int32_t nz, int32_t hx, int32_t hy, int32_t relative);
 
+/* 2-D CIC paint of projected particles (light-cone density planes): mesh[nx][ny] += paint(pos2[np][2]) * weight[np]
+ * (weight may be NULL = 1).  Replaces jaxpm/painting.py:131-158 (cic_paint_2d), same index / weight rule. */
+int32_t jpm_cic_paint_2d_f32(void* stream, float* mesh, const float* pos2, const float* weight, int64_t np,
+                             int32_t nx, int32_t ny);
+
 /* ------------------------------------------------------------------------
  * K2/K3/K4  FFT plan and the fused k-space pass
  * ---------------------------------------------------------------------- */

@@ -22,6 +22,7 @@ SIGNATURES = {
     "jpm_device_info": ([C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
     "jpm_cic_paint_f32": ([vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint_dx_f32": ([vp, vp, vp, vp, f32, i32, i32, i32, i32, i32], i32),
+    "jpm_cic_paint_2d_f32": ([vp, vp, vp, vp, i64, i32, i32], i32),
     "jpm_cic_cell_index_i32": ([vp, vp, vp, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_read_f32": ([vp, vp, vp, vp, i64, i32, i32, i32], i32),
     "jpm_cic_read_dx_f32": ([vp, vp, vp, vp, i32, i32, i32, i32, i32], i32),

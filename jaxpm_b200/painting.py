@@ -202,3 +202,17 @@ def compensate_cic(field):
     """Compensate for CIC painting (jaxpm/painting.py:263-275): divide the spectrum by the CIC window
     prod_d sinc(k_d / 2 pi)^2 (kernels.py:118-136) and transform back."""
     return _CompensateCic.apply(as_f32(field))
+
+
+def cic_paint_2d(mesh, positions, weight):
+    """Paints positions onto a 2-D mesh (jaxpm/painting.py:131-158): mesh [nx, ny], positions [npart, 2],
+    weight [npart] or None.  Returns the updated mesh (a new tensor, like the functional reference).
+    Forward only: the reference's lensing planes (lensing.py:11-44) are not differentiated through here."""
+    from ._lib import call, ptr, stream
+    out = as_f32(mesh).clone()
+    pos = as_f32(positions, out.device).reshape(-1, 2)
+    w = None if weight is None else as_f32(weight, out.device).reshape(-1)
+    if w is not None and w.numel() != pos.shape[0]:
+        raise ValueError("Weight shape must match particle shape")
+    call("jpm_cic_paint_2d_f32", stream(), ptr(out), ptr(pos), ptr(w), pos.shape[0], out.shape[0], out.shape[1])
+    return out

@@ -215,8 +215,27 @@ def gen_power_spectrum():
          pk_poles=pkl, k_cell=kc, pk_cell=pkc)
 
 
+def gen_widened():
+    """compensate_cic (painting.py:263-275) and cic_paint_2d (:131-158)."""
+    rng = np.random.default_rng(19)
+    shape = (8, 12, 16)
+    f = rng.standard_normal(shape).astype(np.float32)
+    comp = painting.compensate_cic(jnp.asarray(f))
+    pshape, n = (12, 10), 500
+    pos = rng.uniform(-3, 15, (n, 2)).astype(np.float32)
+    pos[0] = (-1e-7, 9.9999995)
+    w = rng.uniform(0.5, 1.5, n).astype(np.float32)
+    base = rng.standard_normal(pshape).astype(np.float32)
+    m_w = painting.cic_paint_2d(jnp.asarray(base), jnp.asarray(pos), jnp.asarray(w))
+    m_1 = painting.cic_paint_2d(jnp.zeros(pshape), jnp.asarray(pos), None)
+    save("widened", field=f, compensated=comp, pos2=pos, w2=w, base2=base, mesh2_weighted=m_w, mesh2_unit=m_1)
+
+
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for fn in (gen_paint_read_abs, gen_paint_read_rel, gen_kernels, gen_pm_forces, gen_lpt, gen_growth_ode,
-               gen_distributed, gen_power_spectrum):
+               gen_distributed, gen_power_spectrum, gen_widened):
+        if only and fn.__name__ not in only:
+            continue
         fn()
     print("golden fixtures written to", OUT)

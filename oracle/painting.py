@@ -193,3 +193,21 @@ def cic_paint_vjp(mesh_shape, positions, weight, cot):
     gpos = (vals[..., None] * g).sum(axis=1) * wt
     gw = (vals * w).sum(axis=1)
     return gpos.reshape(pos.shape).astype(cot.dtype), gw.astype(cot.dtype)
+
+
+def cic_paint_2d(mesh, positions, weight):
+    """painting.py:131-158: 2-D CIC, kernel = (1-|dx|)(1-|dy|) [* weight], int32 cast, python mod."""
+    mesh = np.asarray(mesh)
+    dt = mesh.dtype
+    pos = np.asarray(positions, dtype=dt).reshape(-1, 1, 2)
+    fl = np.floor(pos)
+    conn = np.array([[0, 0], [1., 0], [0., 1], [1., 1]], dtype=dt)
+    nc = fl + conn
+    k = (1. - np.abs(pos - nc)).astype(dt)
+    k = (k[..., 0] * k[..., 1]).astype(dt)
+    if weight is not None:
+        k = (k * np.asarray(weight, dtype=dt).reshape(-1, 1)).astype(dt)
+    idx = np.mod(nc.astype(np.int32), np.array(mesh.shape))
+    flat = idx[..., 0].astype(np.int64) * mesh.shape[1] + idx[..., 1]
+    acc = np.bincount(flat.ravel(), weights=k.ravel().astype(np.float64), minlength=mesh.size)
+    return (mesh.astype(np.float64) + acc.reshape(mesh.shape)).astype(dt)

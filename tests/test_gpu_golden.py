@@ -138,3 +138,27 @@ def test_golden_growth_and_ode_terms(cuda):
     assert rel_err(N(drift(a0, vel, None)), g["fpm_drift"]) < 3e-5     # growth-table (host scalar) tolerance
     assert rel_err(N(kick(a0, pos, None)), g["fpm_kick"]) < 3e-5
     assert rel_err(N(first(a0, pos, cosmo)), g["fpm_first_kick"]) < 3e-5
+
+
+def test_golden_power_spectrum_and_widened_rows(cuda):
+    """Device power_spectrum, compensate_cic and cic_paint_2d directly against what the reference's own source
+    produced (tests/golden/power_spectrum.npz, widened.npz)."""
+    from jaxpm_b200.painting import cic_paint_2d, compensate_cic
+    from jaxpm_b200.utils import power_spectrum
+    g = gold("power_spectrum")
+    box = tuple(float(b) for b in g["box"])
+    k, pk = power_spectrum(T(g["f1"], cuda), box_shape=box)
+    np.testing.assert_allclose(k, g["k"], rtol=1e-5)
+    np.testing.assert_allclose(N(pk), g["pk"], rtol=1e-4)
+    _, pkx = power_spectrum(T(g["f1"], cuda), T(g["f2"], cuda), box_shape=box)
+    np.testing.assert_allclose(N(pkx), g["pk_cross"], rtol=1e-4)
+    kp, pkl = power_spectrum(T(g["f1"], cuda), box_shape=box, multipoles=[0, 2], kedges=5)
+    np.testing.assert_allclose(kp, g["k_poles"], rtol=1e-5)
+    assert np.abs(N(pkl) - g["pk_poles"]).max() < 1e-4 * np.abs(g["pk_poles"][0]).max()
+    kc, pkc = power_spectrum(T(g["f1"], cuda))
+    np.testing.assert_allclose(N(pkc), g["pk_cell"], rtol=1e-4)
+    w = gold("widened")
+    assert rel_err(N(compensate_cic(T(w["field"], cuda))), w["compensated"]) < FIELD_TOL
+    assert rel_err(N(cic_paint_2d(T(w["base2"], cuda), T(w["pos2"], cuda), T(w["w2"], cuda))), w["mesh2_weighted"]) < FIELD_TOL
+    assert rel_err(N(cic_paint_2d(torch.zeros(tuple(w["base2"].shape), device=cuda), T(w["pos2"], cuda), None)),
+                   w["mesh2_unit"]) < FIELD_TOL

@@ -164,3 +164,16 @@ def test_power_spectrum():
     np.testing.assert_allclose(pkl, g["pk_poles"], rtol=2e-4, atol=1e-3 * np.abs(g["pk_poles"]).max())
     kc, pkc = U.power_spectrum(g["f1"])
     np.testing.assert_allclose(pkc, g["pk_cell"], rtol=2e-5)
+
+
+def test_widened_rows():
+    """SURVEY.md §8f rows 3-4 as computed by the reference's own source: compensate_cic, cic_paint_2d."""
+    from oracle import kernels as K2
+    from oracle import painting as P2
+    g = gold("widened")
+    dk = K2.fft3d(g["field"].astype(np.float64))
+    comp = K2.ifft3d(K2.cic_compensation(K2.fftk(dk)) * dk)
+    assert np.abs(comp - g["compensated"]).max() / np.abs(g["compensated"]).max() < 2e-6
+    for base, w, key in ((g["base2"], g["w2"], "mesh2_weighted"), (np.zeros_like(g["base2"]), None, "mesh2_unit")):
+        got = P2.cic_paint_2d(base, g["pos2"], w)
+        assert np.abs(got - g[key]).max() / np.abs(g[key]).max() < 2e-6
