@@ -277,6 +277,10 @@ int32_t jpm_slab_check(jpm_plan* plan, void* stream);
 /* Ghost planes per side the last force evaluation exchanged: gx, or - when the density was painted by a
  * jpm_sim bound to this plan - the maximum over the ranks of what their particles actually reach. */
 int32_t jpm_slab_ghost_width(jpm_plan* plan, void* stream, int32_t* out);
+/* *out = 1 if some step since creation saw particles of this rank on its outermost ghost plane: gx (the
+ * reference's halo_size) is too small for the displacement field; like in the reference those particles are then
+ * painted / read at wrapped positions, but here the condition is detectable. */
+int32_t jpm_slab_halo_exceeded(jpm_plan* plan, void* stream, int32_t* out);
 
 /* ------------------------------------------------------------------------
  * tile-sorted resident particle state (the fast path for many steps)

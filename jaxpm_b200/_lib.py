@@ -59,6 +59,7 @@ SIGNATURES = {
     "jpm_slab_forces": ([vp, vp, f32], i32),
     "jpm_slab_check": ([vp, vp], i32),
     "jpm_slab_ghost_width": ([vp, vp, C.POINTER(i32)], i32),
+    "jpm_slab_halo_exceeded": ([vp, vp, C.POINTER(i32)], i32),
     "jpm_sim_create": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
     "jpm_sim_destroy": ([vp], i32),
     "jpm_sim_load": ([vp, vp, vp, vp], i32),

@@ -776,6 +776,18 @@ extern "C" int32_t jpm_slab_ghost_width(jpm_plan* p, void* stream, int32_t* out)
   return JPM_OK;
 }
 
+// 1 if, since the plan was created, some step saw particles on the outermost ghost plane of this rank: the
+// halo (gx) is too small for the displacement field and - exactly like in the reference, whose halo_size has
+// the same role (painting.py:192-215) - those particles were painted / read at wrapped positions.
+extern "C" int32_t jpm_slab_halo_exceeded(jpm_plan* p, void* stream, int32_t* out) {
+  JPM_CHECK_ARG(p && p->is_slab && out, "not a slab plan");
+  unsigned v = 0;
+  JPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  JPM_CUDA(cudaMemcpy(&v, p->slab.flags[p->slab.rank] + kFlagReach, sizeof(v), cudaMemcpyDeviceToHost));
+  *out = (int32_t)v;
+  return JPM_OK;
+}
+
 // Debug / test access to the ghost-zone meshes of a plan: which = 0 the painted density (ghosts NOT folded),
 // 1..3 a force component (ghosts filled); dst receives the whole padded array [nxp][nyp][nzp].
 extern "C" int32_t jpm_plan_padded_get_f32(jpm_plan* p, void* stream, int32_t which, float* dst, int32_t* dims3) {

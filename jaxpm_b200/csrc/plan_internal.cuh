@@ -43,6 +43,7 @@ struct Slab {
 
 // word offsets inside a rank's flag block (flags[r], 256 unsigned words)
 constexpr int kFlagErr = 64;       // barrier timeout marker
+constexpr int kFlagReach = 65;     // set when a rank's particles touched its outermost ghost plane (halo too small)
 constexpr int kFlagXmin = 96;      // int: lowest / highest local x plane touched by the last paint (atomicMin / Max by
 constexpr int kFlagXmax = 97;      //      sim_paint_kernel; INT_MAX / INT_MIN = unknown)
 constexpr int kFlagGe = 98;        // int: ghost planes per side in use this step = max over ranks of what each needs

@@ -743,7 +743,12 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
       const int* mine = reinterpret_cast<const int*>(sl.flags[sl.rank]);
       const int xmin = mine[kFlagXmin], xmax = mine[kFlagXmax];
       int need = sl.gx;
-      if (xmin <= xmax) need = min(sl.gx, max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.lx - 1))));
+      if (xmin <= xmax) {
+        const int raw = max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.lx - 1)));
+        need = min(sl.gx, raw);
+        // the outermost ghost plane was touched: some particle is at (or wrapped past) the reach of the halo
+        if (raw >= sl.gx && t == 0) sl.flags[sl.rank][kFlagReach] = 1u;
+      }
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sl.flags[t] + kFlagGeSlots + sl.rank), "r"(need) : "memory");
     }
     unsigned* remote = sl.flags[t] + sl.rank;

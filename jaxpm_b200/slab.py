@@ -96,6 +96,11 @@ class SlabPlan:
         call("jpm_slab_ghost_width", self.handle, stream(), C.byref(v))
         return int(v.value)
 
+    def halo_exceeded(self):
+        v = C.c_int32(0)
+        call("jpm_slab_halo_exceeded", self.handle, stream(), C.byref(v))
+        return bool(v.value)
+
     def destroy(self):
         if self.handle:
             _lib.load().jpm_plan_destroy(self.handle)
@@ -144,6 +149,10 @@ class SlabStepper:
     def store(self, disp, vel):
         self.sim.store(disp, vel)
         self.plan.check()
+        if self.plan.halo_exceeded():
+            import warnings
+            warnings.warn(f"rank {self.plan.rank}: particles reached the outermost of the {self.plan.gx} ghost planes - "
+                          "halo_size is too small for this displacement field (the reference silently wraps them too)")
 
     def step(self, kick, drift):
         self.sim.step(kick, drift)

@@ -130,3 +130,38 @@ def test_halo_protocol_self_neighbour(cuda, resident):
     st.store(p, v)
     assert np.abs(p.cpu().numpy() - rp.cpu().numpy()).max() < 2e-4
     assert rel_err(v.cpu().numpy(), rv.cpu().numpy()) < 1e-4
+
+
+def test_slab_reports_halo_too_small(cuda):
+    """A displacement field that reaches the outermost ghost plane is flagged (the reference's halo_size has the same
+    validity limit but fails silently); a field inside the reach is not."""
+    import warnings
+    from jaxpm_b200.slab import SlabStepper
+    shape, P, gx = (32, 32, 32), 2, 4
+    lx = shape[0] // P
+    for amp, expect in ((1.0, False), (6.0, True)):
+        plans = _make_plans(shape, P, gx, cuda)
+        streams = [torch.cuda.Stream(cuda) for _ in range(P)]
+        disp = np.zeros((*shape, 3), np.float32)
+        disp[..., 0] = amp * np.sin(2 * np.pi * np.arange(shape[1]) / shape[1])[None, :, None]
+        vel = np.zeros_like(disp)
+        dl = [T(disp[r * lx:(r + 1) * lx], cuda) for r in range(P)]
+        vl = [T(vel[r * lx:(r + 1) * lx], cuda) for r in range(P)]
+        torch.cuda.synchronize()
+        st = []
+        for r in range(P):
+            with torch.cuda.stream(streams[r]):
+                st.append(SlabStepper(dl[r], vl[r], gx, P, r, tile=8, margin=1, plan=plans[r]))
+        for r in range(P):
+            with torch.cuda.stream(streams[r]):
+                st[r].step(0.0, 0.0)
+        flagged = False
+        for r in range(P):
+            with torch.cuda.stream(streams[r]), warnings.catch_warnings(record=True) as w:
+                warnings.simplefilter("always")
+                st[r].store(dl[r], vl[r])
+                flagged = flagged or any("halo_size is too small" in str(x.message) for x in w)
+        torch.cuda.synchronize()
+        assert flagged == expect, (amp, flagged)
+        for s_ in st:
+            s_.close(barrier=False)
