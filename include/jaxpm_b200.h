@@ -135,6 +135,12 @@ int32_t jpm_cic_readgrad_f32(void* stream, float* value, float* grad, const floa
 int32_t jpm_cic_paint_2d_f32(void* stream, float* mesh, const float* pos2, const float* weight, int64_t np,
                              int32_t nx, int32_t ny);
 
+/* Un-normalised density plane of a light cone in one pass over pos3[np][3] (cell units): particles with
+ * center - width/2 < z <= center + width/2 are painted (2-D CIC) at mod(xy, box_nx) / box_nx * plane_resolution onto
+ * plane[res][res] (accumulated into).  Replaces the particle part of jaxpm/lensing.py:11-44 (density_plane :20-35). */
+int32_t jpm_density_plane_f32(void* stream, float* plane, const float* pos3, int64_t np, float box_nx, double center,
+                              double width, int32_t plane_resolution);
+
 /* ------------------------------------------------------------------------
  * K2/K3/K4  FFT plan and the fused k-space pass
  * ---------------------------------------------------------------------- */

@@ -23,6 +23,7 @@ SIGNATURES = {
     "jpm_cic_paint_f32": ([vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint_dx_f32": ([vp, vp, vp, vp, f32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint_2d_f32": ([vp, vp, vp, vp, i64, i32, i32], i32),
+    "jpm_density_plane_f32": ([vp, vp, vp, i64, f32, C.c_double, C.c_double, i32], i32),
     "jpm_cic_cell_index_i32": ([vp, vp, vp, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_read_f32": ([vp, vp, vp, vp, i64, i32, i32, i32], i32),
     "jpm_cic_read_dx_f32": ([vp, vp, vp, vp, i32, i32, i32, i32, i32], i32),

@@ -69,6 +69,40 @@ paint2d_kernel(float* __restrict__ mesh, const float* __restrict__ pos, const fl
   }
 }
 
+// Density plane of a light cone in ONE pass over the particles (no xy / weight arrays are materialised):
+//   reference: jaxpm/lensing.py:11-44 (density_plane): xy = mod(pos[:2], nx); xy = xy / nx * res; weight = 1 where
+//   center - width/2 < pos[2] <= center + width/2; cic_paint_2d(zeros(res, res), xy, weight).  The normalisation
+//   (:37-38) and the optional smoothing are applied by the caller.
+__device__ __forceinline__ float pymod_f(float x, float n) {   // jnp.mod on floats: sign of the divisor
+  float r = fmodf(x, n);
+  if (r != 0.0f && r < 0.0f) r += n;
+  return r;
+}
+
+__global__ void __launch_bounds__(256)
+density_plane_kernel(float* __restrict__ plane, const float* __restrict__ pos, long long np, float nx, float lo,
+                     float hi, int res) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  const float fres = (float)res;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+    const float d = ld_stream(pos + 3 * p + 2);
+    if (!(d > lo && d <= hi)) continue;                        // weight 0: contributes exactly nothing
+    const float x = pymod_f(ld_stream(pos + 3 * p), nx) / nx * fres;
+    const float y = pymod_f(ld_stream(pos + 3 * p + 1), nx) / nx * fres;
+    const Cic1 cx = cic_abs<false>(x, res);
+    const Cic1 cy = cic_abs<false>(y, res);
+    const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1};
+    const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        const float k = wx[a] * wy[b];
+        if (k != 0.f) atomicAdd(plane + (long long)ix[a] * res + iy[b], k);
+      }
+  }
+}
+
 __global__ void __launch_bounds__(256)
 cell_index_kernel(int* __restrict__ out, const float* __restrict__ pos, long long np, int nx, int ny,
                   int nz, int hx, int hy, int rel) {
@@ -154,6 +188,21 @@ extern "C" int32_t jpm_cic_paint_2d_f32(void* stream, float* mesh, const float* 
   long long blocks = (np + 255) / 256;
   if (blocks > (long long)jpm::kNumSMs * 16) blocks = (long long)jpm::kNumSMs * 16;
   jpm::paint2d_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mesh, pos2, weight, np, nx, ny);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_density_plane_f32(void* stream, float* plane, const float* pos3, int64_t np, float box_nx,
+                                         double center, double width, int32_t plane_resolution) {
+  JPM_CHECK_ARG(plane && (pos3 || np == 0) && np >= 0 && box_nx > 0.f && plane_resolution > 0, "bad arguments");
+  if (np == 0) return JPM_OK;
+  long long blocks = (np + 255) / 256;
+  if (blocks > (long long)jpm::kNumSMs * 16) blocks = (long long)jpm::kNumSMs * 16;
+  // the comparison bounds as the reference forms them: Python floats (float64) center -+ width / 2, compared with
+  // the float32 coordinates as weak-typed scalars, i.e. rounded to float32
+  const float lo = (float)(center - width / 2), hi = (float)(center + width / 2);
+  jpm::density_plane_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(plane, pos3, np, box_nx, lo, hi,
+                                                                          plane_resolution);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }

@@ -228,7 +228,12 @@ def gen_widened():
     base = rng.standard_normal(pshape).astype(np.float32)
     m_w = painting.cic_paint_2d(jnp.asarray(base), jnp.asarray(pos), jnp.asarray(w))
     m_1 = painting.cic_paint_2d(jnp.zeros(pshape), jnp.asarray(pos), None)
-    save("widened", field=f, compensated=comp, pos2=pos, w2=w, base2=base, mesh2_weighted=m_w, mesh2_unit=m_1)
+    from jaxpm import lensing
+    pos3 = rng.uniform(-4, 20, (3000, 3)).astype(np.float32)
+    pos3[0] = (-1e-7, 16.0, 10.0)
+    dplane = lensing.density_plane(jnp.asarray(pos3), (16, 16, 16), 8.0, 4.0, 12)
+    save("widened", field=f, compensated=comp, pos2=pos, w2=w, base2=base, mesh2_weighted=m_w, mesh2_unit=m_1,
+         pos3=pos3, density_plane=dplane)
 
 
 if __name__ == "__main__":

@@ -211,3 +211,15 @@ def cic_paint_2d(mesh, positions, weight):
     flat = idx[..., 0].astype(np.int64) * mesh.shape[1] + idx[..., 1]
     acc = np.bincount(flat.ravel(), weights=k.ravel().astype(np.float64), minlength=mesh.size)
     return (mesh.astype(np.float64) + acc.reshape(mesh.shape)).astype(dt)
+
+
+def density_plane(positions, box_shape, center, width, plane_resolution):
+    """lensing.py:11-44 without the optional smoothing: mod, rescale, slab mask, cic_paint_2d, normalisation."""
+    nx, ny, nz = box_shape
+    pos = np.asarray(positions, dtype=np.float32)
+    xy = np.mod(pos[..., :2], np.float32(nx)).astype(np.float32)
+    xy = (xy / np.float32(nx) * np.float32(plane_resolution)).astype(np.float32)
+    d = pos[..., 2]
+    w = np.where((d > (center - width / 2)) & (d <= (center + width / 2)), 1., 0.).astype(np.float32)
+    plane = cic_paint_2d(np.zeros([plane_resolution, plane_resolution], np.float32), xy, w)
+    return (plane / np.float32((nx / plane_resolution) * (ny / plane_resolution) * width)).astype(np.float32)

@@ -162,3 +162,5 @@ def test_golden_power_spectrum_and_widened_rows(cuda):
     assert rel_err(N(cic_paint_2d(T(w["base2"], cuda), T(w["pos2"], cuda), T(w["w2"], cuda))), w["mesh2_weighted"]) < FIELD_TOL
     assert rel_err(N(cic_paint_2d(torch.zeros(tuple(w["base2"].shape), device=cuda), T(w["pos2"], cuda), None)),
                    w["mesh2_unit"]) < FIELD_TOL
+    from jaxpm_b200.lensing import density_plane
+    assert rel_err(N(density_plane(T(w["pos3"], cuda), (16, 16, 16), 8.0, 4.0, 12)), w["density_plane"]) < FIELD_TOL

@@ -177,3 +177,5 @@ def test_widened_rows():
     for base, w, key in ((g["base2"], g["w2"], "mesh2_weighted"), (np.zeros_like(g["base2"]), None, "mesh2_unit")):
         got = P2.cic_paint_2d(base, g["pos2"], w)
         assert np.abs(got - g[key]).max() / np.abs(g[key]).max() < 2e-6
+    dp = P2.density_plane(g["pos3"], (16, 16, 16), 8.0, 4.0, 12)      # lensing.py:11-44
+    assert np.abs(dp - g["density_plane"]).max() / np.abs(g["density_plane"]).max() < 2e-6
