@@ -490,6 +490,11 @@ yinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // grid: (ny / 16, lx).  Real arrays are [lx + 2 gx][nyp][nzp]: gx ghost planes per side in x (images of the
 // neighbour slabs; of this slab itself when P == 1), G ghost cells per side in y and z (periodic images).
 constexpr int kRows = 16;
+#ifndef JPM_ZPASS_CTAS
+#define JPM_ZPASS_CTAS 5
+#endif
+constexpr int kZPassCtas = JPM_ZPASS_CTAS;   // resident CTAs per SM the z-FORWARD pass is register-capped for (48 regs:
+                                             // 0.328 -> 0.316 ms; the same cap on the z-inverse pass loses 0.015 ms)
 #ifndef JPM_ZINV_BATCH
 #define JPM_ZINV_BATCH 16
 #endif
@@ -502,7 +507,7 @@ __device__ __forceinline__ int z_pass_plane(const Slab& sl, int by) {
   return (sl.P > 1 && sl.lx >= 16) ? ((by * 37) & (sl.lx - 1)) : by;
 }
 template <int NZ>
-__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
+__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>(), (threads_for<NZ / 2, kRows>() <= 256 ? kZPassCtas : 1))
 zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull, int x0) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
