@@ -78,24 +78,31 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------
 # CPU arm: the oracle (NumPy/SciPy restatement of the reference) on a bounded sample
 # ---------------------------------------------------------------------------------------
-def cpu_step_rate(n_sample, steps, warmup=0):
-    """Time `steps` drift-kick steps of an n_sample^3 sub-box with the oracle.  Returns
-    (particle-steps/s, seconds per step, threads)."""
+def cpu_step_rate(n_sample, steps, warmup=0, a_start=0.775):
+    """Time `steps` drift-kick steps of an n_sample^3 sub-box (same 1 Mpc/h cells, same Planck15 spectrum) with the
+    oracle, starting from a CLUSTERED state at the epoch the GPU arm times (the last steps of a 40-step run to a = 1):
+    seeded Gaussian ICs, 1LPT displacement / momentum extrapolated to a_start (shell-crossed pancakes and knots -
+    the workload family of the GPU arm; evolving the sample with 30 oracle steps would take ~10 minutes).
+    Returns (particle-steps/s, seconds per step, threads)."""
     import numpy as np
+    from jaxpm_b200.cosmology import Planck15 as P15, linear_matter_power
     from oracle import cosmology as OC
     from oracle import ode as OO
+    from oracle import pm as OPM
     shape = (n_sample,) * 3
     rng = np.random.default_rng(0)
-    grid = np.stack(np.meshgrid(*[np.arange(n_sample)] * 3, indexing="ij"), -1).astype(np.float32)
-    disp = (0.5 * rng.standard_normal(grid.shape)).astype(np.float32)
-    vel = (0.01 * rng.standard_normal(grid.shape)).astype(np.float32)
     cosmo = OC.Planck15()
     OC.growth_tables(cosmo)
+    c = P15()
+    wn = rng.standard_normal(shape).astype(np.float32)
+    ic = OPM.linear_field(wn, (float(n_sample),) * 3, lambda k: linear_matter_power(c, k))
+    disp, vel, _ = OPM.lpt(cosmo, ic, a=a_start, order=1)
     drift, kick = OO.symplectic_ode(shape, cosmo, paint_absolute_pos=False)
+    da = 0.9 / 40
     if warmup:
-        disp, vel = OO.semi_implicit_euler(drift, kick, disp, vel, 0.1, 0.1 + 0.01 * warmup, warmup)
+        disp, vel = OO.semi_implicit_euler(drift, kick, disp, vel, a_start - warmup * da, a_start, warmup)
     t0 = time.perf_counter()
-    OO.semi_implicit_euler(drift, kick, disp, vel, 0.2, 0.2 + 0.01 * steps, steps)
+    OO.semi_implicit_euler(drift, kick, disp, vel, a_start, a_start + steps * da, steps)
     dt = time.perf_counter() - t0
     return n_sample**3 * steps / dt, dt / steps, os.cpu_count()
 
@@ -106,8 +113,9 @@ def run_reference(args):
         return
     n_s = 128 if (args.steps + args.warmup) <= 12 else 64
     rate, sps, cores = cpu_step_rate(n_s, args.steps, args.warmup)
-    sample = (f"{args.steps} drift-kick steps of a {n_s}^3-particle / {n_s}^3-mesh sub-box of the "
-              f"{args.size}^3 workload (same cell size), oracle NumPy/SciPy port, scipy.fft workers=all")
+    sample = (f"{args.steps} drift-kick steps of a {n_s}^3-particle / {n_s}^3-mesh sub-box of the {args.size}^3 "
+              f"workload (same 1 Mpc/h cells, Planck15 ICs, clustered 1LPT state at a = 0.775), oracle NumPy/SciPy "
+              f"port, scipy.fft workers=all")
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": sps * 1e3,
@@ -179,9 +187,24 @@ def run_gpu(args):
 
     # ---- workload set-up (untimed): ICs -> 1LPT at a=0.1 -> displacement + momentum ------------
     ic = linear_field(shape, box, lambda k: linear_matter_power(cosmo, k), seed=0, device=dev)
-    dx, p, _ = lpt(cosmo, ic, a=0.1, order=1)
+    # LPT is set-up, reported separately: 1LPT = 1 fwd + 3 inv FFT + 3 reads, 2LPT = 2 fwd + 12 inv
+    lpt_ms = {}
+    for order in (2, 1):
+        lpt(cosmo, ic, a=0.1, order=order)   # warm (plans, tables)
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dx, p, _ = lpt(cosmo, ic, a=0.1, order=order)
+        ev1.record()
+        torch.cuda.synchronize()
+        lpt_ms[f"order{order}_ms"] = round(ev0.elapsed_time(ev1), 3)
+    lpt_order = args.lpt_order
+    if lpt_order == 2:
+        dx, p, _ = lpt(cosmo, ic, a=0.1, order=2)
+    ic_host = ic.cpu().pin_memory() if args.e2e_run else None
     del ic
     disp, vel = dx.contiguous(), p.contiguous()
+    del dx, p
     plan = ops.get_plan(shape, dev)
     # physical schedule: `--schedule-steps` (40, the step count of BASELINE.json's configs) equal steps in
     # a from 0.1 to 1; the timed region is the LAST K steps of that run (the most clustered state), the
@@ -191,6 +214,8 @@ def run_gpu(args):
     torch.cuda.empty_cache()
     # resident tile-sorted state (jaxpm_b200/csrc/sim.cu): loaded once, like the LPT set-up
     sim = ops.Sim(shape, shape, True, dev, tile=args.tile, margin=args.margin)
+    if args.force_mode != "spectral":
+        sim.set_force_mode(args.force_mode)
     sim.load(disp, vel)
 
     def step(n):
@@ -213,6 +238,7 @@ def run_gpu(args):
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     fallbacks = sim.fallback_counts()
+    finfo = sim.force_info()
     sim.store(disp, vel)
     t_dev = e0.elapsed_time(e1) * 1e-3
     value = npart * K / t_dev
@@ -227,6 +253,9 @@ def run_gpu(args):
         "fft_z_r2c+ghost_fold": 8 * nc, "fft_y_fwd+transpose": 8 * nc,
         "fft_x_fwd+greens_grad+ifft_x_x2+transpose": 12 * nc, "ifft_y_x3": 20 * nc,
         "ifft_z_c2r_x3+ghost_fill": 24 * nc,
+        # potential chain: one spectrum through the inverse half, one mesh box per tile in the read
+        "fft_x_fwd+greens+ifft_x+transpose": 8 * nc, "ifft_y": 8 * nc, "ifft_z_c2r+ghost_fill": 8 * nc,
+        "tile_scan+sim_readpot_kick_drift": 48 * npart + 4 * nc,
         "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)": 16 * nc, "ifft_y_x3|ifft_z_c2r_x3 (chunked pairs)": 44 * nc,
         "ghost_fold": 0, "ghost_fill": 0, "fft_r2c(cuFFT)": 8 * nc, "greens_grad": 16 * nc,
         "ifft_c2r_x3(cuFFT)": 24 * nc,
@@ -261,62 +290,140 @@ def run_gpu(args):
     try:
         with open(os.path.join(ROOT, "profiles", f"traffic_{N}.json")) as f:
             tj = json.load(f)["kernels"]
-        traffic = {"sim_paint": tj["sim_paint_kernel"]["traffic"], "tile_scan+sim_read3_kick_drift": tj["sim_read_kernel"]["traffic"],
-                   "fft_z_r2c+ghost_fold": tj["zfwd_kernel"]["traffic"], "fft_y_fwd+transpose": tj["yfwd_kernel"]["traffic"],
-                   "fft_x_fwd+greens_grad+ifft_x_x2+transpose": tj["xfused_kernel"]["traffic"],
-                   "ifft_y_x3": tj["yinv_kernel"]["traffic"], "ifft_z_c2r_x3+ghost_fill": tj["zinv_kernel"]["traffic"]}
+        names = {"sim_paint": "sim_paint_kernel", "tile_scan+sim_read3_kick_drift": "sim_read_kernel",
+                 "tile_scan+sim_readpot_kick_drift": "sim_readpot_kernel",
+                 "fft_z_r2c+ghost_fold": "zfwd_kernel", "fft_y_fwd+transpose": "yfwd_kernel",
+                 "fft_x_fwd+greens_grad+ifft_x_x2+transpose": "xfused_kernel", "ifft_y_x3": "yinv_kernel",
+                 "ifft_z_c2r_x3+ghost_fill": "zinv_kernel", "fft_x_fwd+greens+ifft_x+transpose": "xpot_kernel",
+                 "ifft_y": "ypot_kernel", "ifft_z_c2r+ghost_fill": "zinv_kernel(potential)"}
+        traffic = {stage: tj[kern]["traffic"] for stage, kern in names.items() if kern in tj}
     except Exception:
         pass
     own = {n: v for n, v in kernels.items() if "cuFFT" not in n and n != "mesh_memset" and "direct" not in n}
     dom_name = max(own, key=lambda n: own[n]["s"])
     dom = own[dom_name]
     step_alg_bytes = 60 * npart + 64 * nc
+    # the FFT chain as a whole against SURVEY.md's 48 B/cell (8 fwd + 16 k-space + 24 inv), next to the per-pass numbers
+    chain_s = sum(v["s"] for n, v in kernels.items() if n.startswith("fft_") or n.startswith("ifft_"))
+    chain = {"ms": round(chain_s * 1e3, 4), "alg_bytes_48_per_cell": 48 * nc,
+             "GBps_on_48B": round(48 * nc / chain_s / 1e9, 1) if chain_s > 0 else None,
+             "frac_on_48B": round(48 * nc / chain_s / 1e9 / peak, 4) if chain_s > 0 else None}
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": dom["GBps"], "peak": peak,
                 "peak_kind": peak_kind, "unit": "GB/s", "frac": dom["frac"], "traffic": traffic.get(dom_name),
                 "alg_bytes": dom["alg_bytes"],
                 "step_achieved": step_alg_bytes * K / t_dev / 1e9,
                 "step_frac": step_alg_bytes * K / t_dev / 1e9 / peak,
+                "fft_chain": chain,
                 "kernels": {n: {"ms": round(v["s"] * 1e3, 4), "GBps": round(v["GBps"], 1),
                                 "frac": round(v["frac"], 4)} for n, v in kernels.items()}}
     torch.cuda.empty_cache()
 
-    # ---- end to end through the host-buffer C-ABI entry (pinned host state, H2D + D2H per step) -
-    e2e_steps = max(1, min(K, args.e2e_steps))
+    # ---- the reference's functional API on the same (clustered) state: pm_forces(disp) -> forces, particle order
+    #      kept (jaxpm/pm.py:12-58): tile sort on entry, shared-memory paint, fused FFT chain, shared-memory gather
+    from jaxpm_b200 import pm as jpm_pm
+    api = {}
+    for label, fast in (("api_pm_forces_ms", True), ("api_pm_forces_slow_path_ms", False)):
+        if not fast and not args.direct:
+            continue
+        jpm_pm._FAST_API = fast
+        api[label] = round(time_kernel(lambda: jpm_pm.pm_forces(disp, mesh_shape=shape, paint_absolute_pos=False),
+                                       iters=3, warm=1) * 1e3, 3)
+    jpm_pm._FAST_API = True
+    ops._force_sims.clear()
+    torch.cuda.empty_cache()
+
+    # ---- parity carried by the bench line: the final matter power spectrum of the timed run (device estimator,
+    #      jaxpm/utils.py:76-128) against the SAME workload on the order-preserving kernels + cuFFT, three-transform
+    #      forces (the path the round-1 parity suite pins to the oracle); max relative difference over the k bins
+    from jaxpm_b200.painting import cic_paint_dx
+    from jaxpm_b200.utils import power_spectrum
+    parity = None
+    if not args.no_parity:
+        total = n_pre + K
+        _, pk_fast = power_spectrum(cic_paint_dx(disp), box_shape=box)
+        ic2 = linear_field(shape, box, lambda kk: linear_matter_power(cosmo, kk), seed=0, device=dev)
+        dx2, p2, _ = lpt(cosmo, ic2, a=0.1, order=lpt_order)
+        del ic2
+        d2, v2 = dx2.contiguous(), p2.contiguous()
+        del dx2, p2
+        ops.axpby(1.0, d2, d[0], v2, out=d2)
+        for n in range(total):
+            ops.pm_step_(plan, d2, v2, k[n], d[n + 1] if n + 1 < total else 0.0, True)
+        _, pk_ref = power_spectrum(cic_paint_dx(d2), box_shape=box)
+        rel = (pk_fast / pk_ref - 1).abs()
+        med = float((d2 - disp).abs().max(-1).values.median())
+        parity = {"final_pk_max_rel_diff": float(rel.max()), "bins": int(rel.numel()), "tolerance": 1e-4,
+                  "median_abs_dpos_cells": med,
+                  "against": "same ICs and schedule on the order-preserving kernels + cuFFT (functional-API slow path)"}
+        del d2, v2
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the host-buffer C-ABI entry on the SAME tile kernels (pinned host state, H2D + D2H of
+    #      the full particle state every step): PCIe-bound by construction (24 B in + 24 B out per particle-step)
+    e2e_steps = max(1, args.e2e_steps)
     ph = torch.empty(disp.shape, dtype=torch.float32).pin_memory()
     vh = torch.empty(vel.shape, dtype=torch.float32).pin_memory()
     ph.copy_(disp)
     vh.copy_(vel)
-    ops.pm_step_host_(plan, ph, vh, disp, vel, 0.0, 0.0, True)  # warm
+    sim.step_host(ph, vh, disp, vel, 0.0, 0.0)  # warm
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     for n in range(e2e_steps):
-        ops.pm_step_host_(plan, ph, vh, disp, vel, 1e-6, 1e-6, True)
+        sim.step_host(ph, vh, disp, vel, 1e-6, 1e-6)
     torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
     bytes_state = 2 * npart * 12
     e2e = {"value": npart * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
            "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
-           "entry": "jpm_pm_step_host_f32 (pinned host pos/vel in, pos/vel out)"}
+           "entry": "jpm_sim_step_host_f32 (pinned host pos/vel in -> tile sort, resident step, un-sort -> pos/vel out)",
+           "pcie_GBps_each_way": round(bytes_state * e2e_steps / t_e2e / 1e9, 1)}
+    del ph, vh
+    # run-level end to end, the call a user of the reference makes (notebooks/05-MultiHost_PM.py:85-135): host ICs in,
+    # LPT + the whole step schedule on the device, host particle state out
+    e2e_run = None
+    if args.e2e_run:
+        total = n_pre + K
+        out_p = torch.empty(disp.shape, dtype=torch.float32).pin_memory()
+        out_v = torch.empty(vel.shape, dtype=torch.float32).pin_memory()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        icd = ic_host.to(dev, non_blocking=True)
+        dxr, pr, _ = lpt(cosmo, icd, a=0.1, order=lpt_order)
+        dr, vr = dxr.contiguous(), pr.contiguous()
+        ops.axpby(1.0, dr, d[0], vr, out=dr)
+        sim.load(dr, vr)
+        for n in range(total):
+            sim.step(k[n], d[n + 1] if n + 1 < total else 0.0)
+        sim.store(dr, vr)
+        out_p.copy_(dr, non_blocking=True)
+        out_v.copy_(vr, non_blocking=True)
+        torch.cuda.synchronize()
+        t_run = time.perf_counter() - t0
+        e2e_run = {"value": npart * total / t_run, "unit": UNIT, "seconds": round(t_run, 4), "steps": total,
+                   "lpt_order": lpt_order, "h2d_bytes": int(ic_host.numel() * 4), "d2h_bytes": bytes_state,
+                   "entry": "host ICs -> lpt -> resident steps -> host (pos, vel)"}
+        del icd, dxr, pr, dr, vr, out_p, out_v
 
     # ---- CPU baseline (oracle port) on a bounded sample ----------------------------------------
     cpu = None
     if rank == 0 and not args.no_cpu:
         rate, sps, cores = cpu_step_rate(128, 1)
         cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": "1 drift-kick step of a 128^3 sub-box (same cell size), oracle NumPy/SciPy port "
-                         f"of the reference, {sps:.1f} s"}
+               "sample": "1 drift-kick step of a 128^3 sub-box (same 1 Mpc/h cells, Planck15 ICs, clustered 1LPT "
+                         f"state at a = 0.775), oracle NumPy/SciPy port of the reference, {sps:.1f} s"}
 
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then {args.schedule_steps} PM "
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, {lpt_order}LPT at a=0.1 then {args.schedule_steps} PM "
                                    f"drift-kick steps to a=1 (relative mode), Planck15, L={N} Mpc/h; timed = the "
                                    f"last {K} steps, {n_pre} untimed before",
                        "l2": "inputs larger than L2 (particle state 3.2 GB, mesh 0.5 GB at 512^3)",
-                       "parallelism": "single GPU"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches,
+                       "parallelism": "single GPU", "force_mode": args.force_mode},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_run": e2e_run, "gpu_launches": launches,
+            "api": api, "lpt": lpt_ms, "parity": parity, "force_path": finfo,
             "clocks": clocks, "sim": {"tile": sim.tile, "margin": sim.margin,
                                       "global_fallback_particles_paint_read": fallbacks[:2],
                                       "generic_stencil_particles_paint_read": fallbacks[2:]},
@@ -330,7 +437,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--force-mode", default="auto", choices=["spectral", "potential", "auto"],
+                    help="force path of the resident step (include/jaxpm_b200.h): three inverse transforms, one + "
+                         "difference stencil, or per step by the measured fp32 error bound")
+    ap.add_argument("--lpt-order", type=int, default=2, choices=[1, 2], help="LPT order of the initial state")
+    ap.add_argument("--no-parity", action="store_true", help="skip the P(k) parity leg")
+    ap.add_argument("--no-e2e-run", dest="e2e_run", action="store_false", help="skip the run-level end-to-end leg")
     ap.add_argument("--tile", type=int, default=16)
     ap.add_argument("--margin", type=int, default=1)
     ap.add_argument("--schedule-steps", type=int, default=40,

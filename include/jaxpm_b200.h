@@ -210,6 +210,15 @@ int32_t jpm_density_to_force_meshes_fused(jpm_plan* plan, void* stream, const fl
                                           float* force3, float r_split, const float* filter_tab,
                                           int32_t n_tab, float filter_kmax);
 
+/* The POTENTIAL chain (power-of-two meshes): real `density` -> psi = IFFT(G(k) delta_k / k^2) = -phi, ONE inverse
+ * transform.  The reference's force spectra -gradient_kernel(k, d) * pot_k (jaxpm/pm.py:51-56 with
+ * jaxpm/kernels.py:62-66) are EXACTLY the 4th-order central differences of this mesh,
+ *     F_d(c) = [8 (psi(c + e_d) - psi(c - e_d)) - (psi(c + 2 e_d) - psi(c - 2 e_d))] / 12,
+ * which the resident step forms in shared memory while it stages a tile (jpm_sim_set_force_mode). */
+int32_t jpm_density_to_potential_fused(jpm_plan* plan, void* stream, const float* density, float* psi,
+                                       float r_split, const float* filter_tab, int32_t n_tab,
+                                       float filter_kmax);
+
 /* One full PM step on resident particles (single GPU, absolute or relative positions):
  * memset mesh -> paint -> R2C -> greens-grad -> 3x C2R -> read3+kick+drift (kick-drift
  * form, in place on pos/vel).  jaxpm/ode.py:100-117 + :91-98 around jaxpm/pm.py:12-58. */
@@ -301,6 +310,12 @@ typedef struct jpm_sim jpm_sim; /* opaque; owns a tile-sorted copy of (pos, vel)
 int32_t jpm_sim_create(jpm_sim** sim, jpm_plan* plan, int32_t nx, int32_t ny, int32_t nz,
                        int32_t pnx, int32_t pny, int32_t pnz, int32_t hx, int32_t hy,
                        int32_t relative, int32_t tile, int32_t margin);
+/* Same, with flags: JPM_SIM_POSITIONS_ONLY keeps no velocities and no second ordering (16 instead of 56 bytes per
+ * particle): the state can be loaded (vel = NULL), painted and asked for forces, not stepped. */
+#define JPM_SIM_POSITIONS_ONLY 1
+int32_t jpm_sim_create_ex(jpm_sim** sim, jpm_plan* plan, int32_t nx, int32_t ny, int32_t nz,
+                          int32_t pnx, int32_t pny, int32_t pnz, int32_t hx, int32_t hy,
+                          int32_t relative, int32_t tile, int32_t margin, int32_t flags);
 int32_t jpm_sim_destroy(jpm_sim* sim);
 /* Build the sorted state from user-order arrays pos[np][3], vel[np][3] / write it back. */
 int32_t jpm_sim_load(jpm_sim* sim, void* stream, const float* pos, const float* vel);
@@ -312,13 +327,38 @@ int32_t jpm_sim_paint(jpm_sim* sim, void* stream, float* mesh);
  * the three force meshes through shared-memory boxes; writes the next tile ordering. */
 int32_t jpm_sim_read_kick_drift(jpm_sim* sim, void* stream, const float* fx, const float* fy,
                                 const float* fz, float kick_coef, float drift_coef);
+/* jaxpm/pm.py:12-58 `pm_forces` on the tile kernels: paint the loaded state (shared-memory boxes, TMA reduce-add),
+ * fused FFT chain with the k-space kernels of pm.py:49-56 (r_split, optional radial filter table as in
+ * jpm_greens_grad_c64), then the three reads + stack of pm.py:54-56: out[np][3] = scale * F, in the CALLER's
+ * particle order (the order of the arrays given to jpm_sim_load). */
+int32_t jpm_sim_forces(jpm_sim* sim, void* stream, float* out, float scale, float r_split,
+                       const float* filter_tab, int32_t n_tab, float filter_kmax);
 /* One PM step on the resident state: memset, paint, R2C, greens-grad, 3x C2R, read+kick+drift. */
 int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_coef);
+/* One step end to end through HOST buffers (pinned or pageable) on the tile kernels: H2D pos / vel [np][3], tile sort,
+ * jpm_sim_step, un-sort, D2H.  pos_dev / vel_dev: device staging [np][3].  Synchronises `stream`. */
+int32_t jpm_sim_step_host_f32(jpm_sim* sim, void* stream, float* pos_host, float* vel_host, float* pos_dev,
+                              float* vel_dev, float kick_coef, float drift_coef);
 /* One jpm_sim_step with a CUDA event recorded on `stream` at every stage boundary (memset, paint, each
  * FFT pass, read).  Synchronises the stream; fills names_out[i] (static strings) and ms_out[i] for the
  * *n_out <= cap stages.  This is how bench.py measures the per-kernel roofline live. */
 int32_t jpm_sim_step_profile(jpm_sim* sim, void* stream, float kick_coef, float drift_coef,
                              const char** names_out, float* ms_out, int32_t cap, int32_t* n_out);
+
+/* Force path of jpm_sim_step (resident state on a power-of-two mesh, margin 1):
+ *   JPM_FORCE_SPECTRAL  three inverse transforms of i a_d(k) delta_k / k^2 (jaxpm/pm.py:54-56 literally);
+ *   JPM_FORCE_POTENTIAL one inverse transform of delta_k / k^2, forces by the 4th-order difference stencil
+ *                       the reference's gradient kernel is the symbol of (same operator; fp32 differencing
+ *                       adds an absolute error ~ 5e-7 max|psi|, negligible once the field is clustered);
+ *   JPM_FORCE_AUTO      per step, from the device-measured bound 2.7e-6 rms(psi) / max|F|: potential when it is
+ *                       below 4e-6, spectral when above 6e-6 - every step stays within 1e-5 of the reference. */
+#define JPM_FORCE_SPECTRAL 0
+#define JPM_FORCE_POTENTIAL 1
+#define JPM_FORCE_AUTO 2
+int32_t jpm_sim_set_force_mode(jpm_sim* sim, int32_t mode);
+/* out6_host = {mode, mode of the next step, last evaluated error bound (< 0: none), steps run spectral, steps run
+ * potential, 1 if the potential path is available}.  Synchronises the stream. */
+int32_t jpm_sim_force_info(jpm_sim* sim, void* stream, double* out6_host);
 
 /* out4_host[0..1] = particles that took the global-memory fallback (drifted beyond the margin) in
  * paint / read so far; [2..3] = particles that took the generic (periodic-wrap) stencil inside the

@@ -42,6 +42,7 @@ SIGNATURES = {
     "jpm_kfilter_logtab_c64": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),
     "jpm_density_to_force_meshes": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_density_to_force_meshes_fused": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
+    "jpm_density_to_potential_fused": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_pm_step_f32": ([vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_pm_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32, i32], i32),
     "jpm_pk_bin_c64": ([vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, C.POINTER(i32), i32, C.POINTER(f32), f32, i32,
@@ -62,14 +63,19 @@ SIGNATURES = {
     "jpm_slab_ghost_width": ([vp, vp, C.POINTER(i32)], i32),
     "jpm_slab_halo_exceeded": ([vp, vp, C.POINTER(i32)], i32),
     "jpm_sim_create": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
+    "jpm_sim_create_ex": ([C.POINTER(vp), vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32, i32], i32),
     "jpm_sim_destroy": ([vp], i32),
     "jpm_sim_load": ([vp, vp, vp, vp], i32),
     "jpm_sim_store": ([vp, vp, vp, vp], i32),
     "jpm_sim_paint": ([vp, vp, vp], i32),
     "jpm_sim_read_kick_drift": ([vp, vp, vp, vp, vp, f32, f32], i32),
+    "jpm_sim_forces": ([vp, vp, vp, f32, f32, vp, i32, f32], i32),
     "jpm_sim_step": ([vp, vp, f32, f32], i32),
+    "jpm_sim_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32], i32),
     "jpm_sim_step_profile": ([vp, vp, f32, f32, C.POINTER(C.c_char_p), C.POINTER(f32), i32, C.POINTER(i32)], i32),
     "jpm_sim_stats_host": ([vp, vp, C.POINTER(i64)], i32),
+    "jpm_sim_set_force_mode": ([vp, i32], i32),
+    "jpm_sim_force_info": ([vp, vp, C.POINTER(C.c_double)], i32),
     "jpm_kernel_launch_count": ([], i64),
     "jpm_axpby_f32": ([vp, vp, f32, vp, f32, vp, i64], i32),
     "jpm_grid_plus_disp_f32": ([vp, vp, vp, i32, i32, i32, i32, i32], i32),

@@ -176,7 +176,8 @@ def linear_matter_power(cosmo, k, a=1.0):
     k = np.asarray(k, dtype=np.float64)
 
     def unnorm(kk):
-        return kk**cosmo.n_s * _eh_transfer(cosmo, kk)**2
+        with np.errstate(divide="ignore", invalid="ignore"):     # k = 0: the k^n_s factor makes P(0) = 0
+            return kk**cosmo.n_s * _eh_transfer(cosmo, kk)**2
 
     if "pknorm" not in cosmo._cache:
         lk = np.linspace(np.log(1e-5), np.log(1e3), 8192)

@@ -363,6 +363,29 @@ extern "C" int32_t jpm_density_to_force_meshes_fused(jpm_plan* p, void* stream, 
   return JPM_OK;
 }
 
+extern "C" int32_t jpm_density_to_potential_fused(jpm_plan* p, void* stream, const float* density, float* psi,
+                                                  float r_split, const float* filter_tab, int32_t n_tab,
+                                                  float filter_kmax) {
+  JPM_CHECK_ARG(!(p && p->is_slab), "not available on a multi-GPU slab plan");
+  JPM_CHECK_ARG(p && density && psi, "null pointer");
+  JPM_CHECK_ARG(!filter_tab || (n_tab >= 2 && filter_kmax > 0.f), "bad filter table");
+  int32_t rc = plan_enable_padded(p);
+  if (rc) return rc;
+  JPM_CHECK_ARG(p->G > 0 && p->fft_on, "potential chain needs a power-of-two mesh (fused FFT chain)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = p->ncell / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
+  JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+  pad_copy_kernel<true><<<dim3(blocks, 1), 256, 0, st>>>(p->density_p, const_cast<float*>(density), p->nx, p->ny,
+                                                        p->nz / 4, p->nyp, p->nzp, p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  if ((rc = pmfft_potential(p, st, r_split, filter_tab, n_tab, filter_kmax))) return rc;
+  pad_copy_kernel<false><<<dim3(blocks, 1), 256, 0, st>>>(p->force3_p, psi, p->nx, p->ny, p->nz / 4, p->nyp,
+                                                         p->nzp, p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
 extern "C" int32_t jpm_plan_create(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz) {
   JPM_CHECK_ARG(out, "null plan pointer");
   JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0, "bad mesh shape");

@@ -99,6 +99,11 @@ struct jpm_plan {
   int fft_zvariant = 1;            // experiments on the z-inverse pass (JPM_FFT_ZVAR bit 0: batched plain epilogue)
   TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
   TmapPack* tm_t01 = nullptr;   // [d]: T01 of rank d as {4 nzc, ny, lx} floats, box {32, 1, min(lx,256)}
+  TmapPack* tm_b3 = nullptr;    // [d]: planar B3 of rank d as {2 nzc, ny, lx, 3} floats, box {16, 1, min(lx,256), 1}
+  // potential chain (pmfft_potential): [0] sum_k |psi_k|^2 of the last evaluation (= mean_x psi^2), [1] bit pattern
+  // of max |F| seen by the last read (atomicMax on the float bits), [2..3] spare.  Device doubles.
+  double* pot_stats = nullptr;
+  bool want_sumsq = false;      // the next pmfft_forces also accumulates pot_stats[0] (auto force mode of csrc/sim.cu)
 };
 
 namespace jpm {
@@ -116,6 +121,8 @@ bool pmfft_shape_ok(int nx, int ny, int nz);
 int32_t slab_barrier(jpm_plan* p, cudaStream_t stream, bool exchange_ghost_width = false);
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
                      float filter_kmax);
+int32_t pmfft_potential(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
+                        float filter_kmax);
 void pmfft_destroy(jpm_plan* p);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
 // dims/strides innermost first, rank 3 or 4, fp32, no swizzle/interleave, OOB -> zero fill.

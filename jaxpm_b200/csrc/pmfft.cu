@@ -297,12 +297,12 @@ yfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 // (operation order of kspace_kernel<0>, plan.cu); then TWO inverse FFTs along x:
 //   T0 = IFFT_x(i a_x(kx) g delta)  -> B[0]   (x force; a_y, a_z do not depend on kx, so the y and z
 //   T1 = IFFT_x(g delta)            -> B[1]    forces share T1: their factors are applied in Y-inv / Z-inv)
-template <int N, int C, bool TMAST, bool PAIR>
+template <int N, int C, bool TMAST, bool PAIR, bool SUMSQ = false>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
 xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
               const float* __restrict__ wy, const float* __restrict__ wz, const float* __restrict__ ax,
               float norm, float r_split2, const float* __restrict__ ftab, int ntab, float fscale,
-              const __grid_constant__ TmapPack tp) {
+              const __grid_constant__ TmapPack tp, double* __restrict__ sumsq) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int L = radix_count(N);
   constexpr int RL = radix_at(N, L - 1, false);        // radix of the last forward == first inverse stage
@@ -347,6 +347,24 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
         keep[i][r].y *= g;
       }
     }
+  }
+  if (SUMSQ && sumsq) {
+    // sum_k |g delta_k|^2 over the full spectrum = mean_x psi^2 (error bound of the potential chain, csrc/sim.cu)
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < TPT; ++i) {
+      const int task = threadIdx.x + i * NT;
+      const int c = task % C;
+      if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+        const int kzi = kz0 + c;
+        const float herm = (kzi == 0 || 2 * kzi == sl.nz) ? 1.f : 2.f;
+#pragma unroll
+        for (int r = 0; r < RL; ++r) part = fmaf(herm, keep[i][r].x * keep[i][r].x + keep[i][r].y * keep[i][r].y, part);
+      }
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) atomicAdd(sumsq, (double)part);
   }
 #pragma unroll 1
   for (int d = 0; d < 2; ++d) {
@@ -406,6 +424,116 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
       tma_store_wait_read();
     }
   }
+}
+
+// ---- X-pot: the x pass of the POTENTIAL chain -----------------------------------------------------------
+// grid: (ntile, ly).  Forward FFT along x, delta_k (registers) times norm * G(k) / k^2, ONE inverse FFT along x:
+//   psi = IFFT(g delta) = -phi  (pm.py:51-52 with the sign folded)  ->  B[0][x][yg][kz] of the rank that owns x.
+// The reference's gradient kernel i (8 sin w - sin 2w) / 6 (kernels.py:62-66) is EXACTLY the symbol of the
+// 4th-order central difference D f = [8 (f(x+1) - f(x-1)) - (f(x+2) - f(x-2))] / 12, so the three force meshes
+// F_d = IFFT(i a_d g delta) = D_d psi are formed in real space by the read kernel (csrc/sim.cu) while it stages
+// the tile box: one inverse transform instead of three, 40 instead of 72 B/cell through the five passes.
+// `sumsq` (nullable) accumulates sum_k |psi_k|^2 over the full spectrum = mean_x psi^2 (Parseval), the
+// numerator of the fp32 cancellation bound that decides between this chain and the three-transform one.
+template <int N, int C, bool TMAST>
+__global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
+xpot_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
+            const float* __restrict__ wy, const float* __restrict__ wz, float norm, float r_split2,
+            const float* __restrict__ ftab, int ntab, float fscale, const __grid_constant__ TmapPack tp,
+            double* __restrict__ sumsq) {
+  constexpr int NT = threads_for<N, C, 8>();
+  constexpr int L = radix_count(N);
+  constexpr int RL = radix_at(N, L - 1, false);
+  constexpr int TASKS = (N / RL) * C;
+  constexpr int TPT = (TASKS + NT - 1) / NT;
+  extern __shared__ __align__(128) float2 sm[];
+  float2* tw = sm;            // [N]
+  float2* s = sm + N;         // [N][C]
+  float* swx = reinterpret_cast<float*>(s + N * C);   // [N] k_x table
+  __shared__ float s_part[32];
+  for (int i = threadIdx.x; i < N; i += NT) { tw[i] = twg[i]; swx[i] = wx[i]; }
+  const int kz0 = blockIdx.x * C;
+  const int ncol = min(C, sl.nzh - kz0);
+  const int yl = blockIdx.y, yg = sl.rank * sl.ly + yl;
+  GlobalIO gin{sl.at[sl.rank] + (long long)yl * sl.nzc + kz0, (long long)sl.ly * sl.nzc};
+  float2 keep[TPT][8];
+  run_stages<N, C, NT, false, false, false, true, LayCols<C>, 0>(s, tw, ncol, gin, NullIO{}, keep);
+  const float ky = wy[yg];
+  float part = 0.f;
+#pragma unroll
+  for (int i = 0; i < TPT; ++i) {
+    const int task = threadIdx.x + i * NT;
+    const int c = task % C, j = task / C;
+    if ((TASKS % NT == 0 || task < TASKS) && c < ncol) {
+      const int kzi = kz0 + c;
+      const float kz = wz[kzi];
+      const float herm = (kzi == 0 || 2 * kzi == sl.nz) ? 1.f : 2.f;   // modes the half-spectrum stands for
+#pragma unroll
+      for (int r = 0; r < RL; ++r) {
+        const float kx = swx[j + r * (N / RL)];
+        const float kxy2 = kx * kx + ky * ky;
+        const float kk = kxy2 + kz * kz;
+        float g = (kk == 0.f) ? 0.f : __frcp_rn(kk);
+        g *= norm;
+        if (r_split2 != 0.f) g *= expf(-kk * r_split2);
+        if (ftab) {
+          const float t = sqrtf(kk) * fscale;
+          const int ti = min((int)t, ntab - 2);
+          const float fr = fminf(t - (float)ti, 1.0f);
+          g *= ftab[ti] + fr * (ftab[ti + 1] - ftab[ti]);
+        }
+        keep[i][r].x *= g;
+        keep[i][r].y *= g;
+        part = fmaf(herm, keep[i][r].x * keep[i][r].x + keep[i][r].y * keep[i][r].y, part);
+      }
+    }
+  }
+  if (sumsq) {
+#pragma unroll
+    for (int off = 16; off; off >>= 1) part += __shfl_xor_sync(0xffffffffu, part, off);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  }
+  if constexpr (TMAST) {
+    SmemIO<LayCols<C>> stl{s};
+    run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, stl, keep);
+    fence_async_smem();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const int rows = min(sl.lx, 256);
+      for (int dst = 0; dst < sl.P; ++dst)
+        for (int r0 = 0; r0 < sl.lx; r0 += rows)
+          tma_store_4d(&tp.m[dst], 2 * kz0, yg, r0, 0, s + (size_t)(dst * sl.lx + r0) * C);
+      tma_store_commit();
+      tma_store_wait_read();
+    }
+  } else {
+    ScatterXPlanarIO gout{&sl, (long long)yg * sl.nzc + kz0};
+    run_stages<N, C, NT, true, true, true, false, LayCols<C>, 0>(s, tw, ncol, NullIO{}, gout, keep);
+    __syncthreads();
+  }
+  if (sumsq && threadIdx.x == 0) {
+    float tot = 0.f;
+    for (int w = 0; w < NT / 32; ++w) tot += s_part[w];
+    atomicAdd(sumsq, (double)tot);
+  }
+}
+
+// ---- Y-pot: inverse FFT along y of ONE spectrum (B[0]) in place, the y pass of the potential chain -----------
+// grid: (ntile, lx).  Same tiling as Y-fwd ([N][16] column tiles, 128-byte segments): the first stage loads from
+// global memory, the last one stores to it; every CTA owns its columns of the plane, so in place is race free.
+template <int N, int C>
+__global__ void __launch_bounds__(threads_for<N, C>())
+ypot_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, int x0) {
+  constexpr int NT = threads_for<N, C>();
+  static_assert(radix_count(N) >= 2, "in-place column pass needs the loads of a tile to precede its stores");
+  extern __shared__ __align__(128) float2 sm[];
+  float2* tw = sm;            // [N]
+  float2* s = sm + N;         // [N][C]
+  for (int i = threadIdx.x; i < N; i += NT) tw[i] = twg[i];
+  const int kz0 = blockIdx.x * C, xl = x0 + blockIdx.y;
+  const int ncol = min(C, sl.nzh - kz0);
+  GlobalIO gio{sl.b3[sl.rank] + (long long)xl * sl.ny * sl.nzc + kz0, sl.nzc};
+  run_stages<N, C, NT, true, false, false, false, LayCols<C>, 0>(s, tw, ncol, gio, gio, nullptr);
 }
 
 // ---- Y-inv: inverse FFT along y of the local x planes ---------------------------------------------------
@@ -622,7 +750,7 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull,
-            const float* __restrict__ az, int x0, int variant) {
+            const float* __restrict__ az, int x0, int variant, int ge_extra) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
@@ -686,7 +814,8 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   // destinations in x: own interior plane, left neighbour's high ghost, right neighbour's low ghost
   const long long cofs = (long long)comp * sl.npad;
   float* dstp[3] = {sl.force[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
-  const int ge = ghost_width(sl);
+  // ge_extra: the potential chain's mesh is differentiated by a +-2 stencil after the read box is staged
+  const int ge = min(gx, ghost_width(sl) + ge_extra);
   if (xl < ge) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
   if (xl >= lx - ge) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
   const int GH = G / 2;
@@ -810,6 +939,7 @@ static bool pow2_in_range(int n) { return n >= 16 && n <= 1024 && (n & (n - 1)) 
 
 template <int N, int C> constexpr size_t cols_smem() { return (size_t)(N + N * C) * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem() { return (size_t)(N + N * C) * sizeof(float2) + 2 * N * sizeof(float); }
+template <int N, int C> constexpr size_t xpot_smem() { return (size_t)(N + N * C) * sizeof(float2) + N * sizeof(float); }
 template <int N, int C> constexpr size_t xfused_smem_tma() { return xfused_smem<N, C>() + 2 * (size_t)N * C * sizeof(float2); }
 template <int N, int C> constexpr size_t xfused_smem_tma_planar() { return xfused_smem<N, C>() + (size_t)N * C * sizeof(float2); }
 template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (NZ / 2 + 1)) * sizeof(float2); }
@@ -841,6 +971,18 @@ static int32_t set_attrs(const Slab& sl) {
                                 (int)xfused_smem<N_, kXC>()));
   JPM_FFT_SWITCH(sl.ny, ATTR_Y)
 #undef ATTR_Y
+#define ATTR_YP(N_)                                                                                             \
+  JPM_CUDA(cudaFuncSetAttribute(ypot_kernel<N_, kColsC>, cudaFuncAttributeMaxDynamicSharedMemorySize,           \
+                                (int)cols_smem<N_, kColsC>()));
+  JPM_FFT_SWITCH(sl.ny, ATTR_YP)
+#undef ATTR_YP
+#define ATTR_XP(N_)                                                                                             \
+  JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
+                                (int)xpot_smem<N_, kXC>()));                                                    \
+  JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                (int)xpot_smem<N_, kXC>()));
+  JPM_FFT_SWITCH(sl.nx, ATTR_XP)
+#undef ATTR_XP
 #define ATTR_X(N_)                                                                                              \
   JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)xfused_smem<N_, kXC>()));                                                  \
@@ -849,6 +991,10 @@ static int32_t set_attrs(const Slab& sl) {
   JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)xfused_smem_tma_planar<N_, kXC>()));                                              \
   JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)xfused_smem_tma<N_, kXC>()));                                              \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                (int)xfused_smem_tma_planar<N_, kXC>()));                                       \
+  JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)xfused_smem_tma<N_, kXC>()));
   JPM_FFT_SWITCH(sl.nx, ATTR_X)
 #undef ATTR_X
@@ -900,14 +1046,22 @@ int32_t pmfft_setup(jpm_plan* p) {
     if (p->fft_tma_store) {
       if (!p->tm_at) p->tm_at = new TmapPack();
       if (!p->tm_t01) p->tm_t01 = new TmapPack();
+      if (!p->tm_b3) p->tm_b3 = new TmapPack();
       memset(p->tm_at, 0, sizeof(TmapPack));
       memset(p->tm_t01, 0, sizeof(TmapPack));
+      memset(p->tm_b3, 0, sizeof(TmapPack));
       const unsigned long long row = (unsigned long long)sl.nzc * sizeof(float2);
       for (int d = 0; d < sl.P; ++d) {
         const unsigned long long da[3] = {2ull * sl.nzc, (unsigned long long)sl.ly, (unsigned long long)sl.nx};
         const unsigned long long sa[2] = {row, row * sl.ly};
         const unsigned ba[3] = {2u * fft::kColsC, (unsigned)std::min(sl.ly, 256), 1u};
         if ((rc = encode_tensor_map(&p->tm_at->m[d], reinterpret_cast<float*>(sl.at[d]), 3, da, sa, ba))) return rc;
+        {   // planar B3 of rank d (the potential chain stores its single spectrum into component 0)
+          const unsigned long long db[4] = {2ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx, 3ull};
+          const unsigned long long sb[3] = {row, row * sl.ny, row * sl.ny * sl.lx};
+          const unsigned bb[4] = {2u * fft::kXC, 1u, (unsigned)std::min(sl.lx, 256), 1u};
+          if ((rc = encode_tensor_map(&p->tm_b3->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bb))) return rc;
+        }
         if (p->fft_pair) {
           const unsigned long long dt[3] = {4ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx};
           const unsigned long long st[2] = {2 * row, 2 * row * sl.ny};
@@ -961,6 +1115,9 @@ int32_t pmfft_enable(jpm_plan* p) {
 void pmfft_destroy(jpm_plan* p) {
   delete p->tm_at; p->tm_at = nullptr;
   delete p->tm_t01; p->tm_t01 = nullptr;
+  delete p->tm_b3; p->tm_b3 = nullptr;
+  if (p->pot_stats) cudaFree(p->pot_stats);
+  p->pot_stats = nullptr;
   void* bufs[] = {p->fft_at, p->fft_b3, p->fft_t01, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -995,6 +1152,7 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   // over chunks of planes, so that the consumer finds the producer's output in L2 (126 MB) instead of HBM
   const bool chunked = sl.P == 1 && p->fft_chunk > 0 && p->fft_chunk < sl.lx;
   const int cx = chunked ? p->fft_chunk : sl.lx;
+  double* sumsq_ptr = (p->want_sumsq && p->pot_stats) ? p->pot_stats : nullptr;
   int32_t rc;
   // every rank has painted: neighbours' ghost planes are final; agree on the ghost width of this step
   if ((rc = slab_barrier(p, st, true))) return rc;
@@ -1021,18 +1179,24 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   if ((rc = slab_barrier(p, st))) return rc;      // AT complete on every rank
   if (p->timer) p->timer->mark(st, chunked ? "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)" : "fft_y_fwd+transpose");
 #define RUN_X(N_)                                                                                              \
-  if (p->fft_tma_store && pair)                                                                                \
+  if (p->fft_tma_store && pair && sumsq_ptr)                                                                   \
+    xfused_kernel<N_, kXC, true, true, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);     \
+  else if (p->fft_tma_store && sumsq_ptr)                                                                      \
+    xfused_kernel<N_, kXC, true, false, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma_planar<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);     \
+  else if (p->fft_tma_store && pair)                                                                           \
     xfused_kernel<N_, kXC, true, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma<N_, kXC>(), st>>>( \
-        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);     \
   else if (p->fft_tma_store)                                                                                   \
     xfused_kernel<N_, kXC, true, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem_tma_planar<N_, kXC>(), st>>>( \
-        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);     \
   else if (pair)                                                                                               \
     xfused_kernel<N_, kXC, false, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
-        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);     \
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);     \
   else                                                                                                         \
     xfused_kernel<N_, kXC, false, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xfused_smem<N_, kXC>(), st>>>( \
-        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3);
+        sl, p->tw_x, p->wx, p->wy, p->wz, p->ax, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, sumsq_ptr);
   JPM_FFT_SWITCH(sl.nx, RUN_X)
 #undef RUN_X
   JPM_LAUNCH_CHECK();
@@ -1053,13 +1217,81 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
     if (p->timer && !chunked) p->timer->mark(st, "ifft_y_x3");
 #define RUN_ZI(N_)                                                                                             \
   zinv_kernel<N_><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
-      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant);
+      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0);
     JPM_FFT_SWITCH(sl.nz, RUN_ZI)
 #undef RUN_ZI
     JPM_LAUNCH_CHECK();
   }
   if ((rc = slab_barrier(p, st))) return rc;      // force ghost planes written by the neighbours are final
   if (p->timer) p->timer->mark(st, chunked ? "ifft_y_x3|ifft_z_c2r_x3 (chunked pairs)" : "ifft_z_c2r_x3+ghost_fill");
+  return JPM_OK;
+}
+
+// density_p (painted, ghosts NOT folded) -> psi = IFFT(G delta / k^2) in force3_p component 0, ghosts filled
+// (+2 planes for the read kernel's difference stencil).  Same passes / barriers as pmfft_forces with ONE
+// spectrum through the inverse half: 8 + 8 + 8 + 8 + 8 = 40 B/cell instead of 72.
+int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
+                        float filter_kmax) {
+  using namespace fft;
+  JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
+  const Slab& sl = p->slab;
+  const int nzh = sl.nzh;
+  const float norm = 1.0f / ((float)sl.nx * (float)sl.ny * (float)sl.nz);
+  const float fscale = filter_tab ? (float)(n_tab - 1) / filter_kmax : 0.f;
+  const int nty = (nzh + kColsC - 1) / kColsC, ntx = (nzh + kXC - 1) / kXC;
+  static const TmapPack kNoMaps{};
+  const TmapPack& tat = p->fft_tma_store ? *p->tm_at : kNoMaps;
+  const TmapPack& tb3 = p->fft_tma_store ? *p->tm_b3 : kNoMaps;
+  if (!p->pot_stats) JPM_CUDA(cudaMalloc(&p->pot_stats, 4 * sizeof(double)));
+  JPM_CUDA(cudaMemsetAsync(p->pot_stats, 0, 4 * sizeof(double), st));   // [0] sum |psi_k|^2, [1] max |F| bits of this step
+  int32_t rc;
+  if ((rc = slab_barrier(p, st, true))) return rc;
+#define RUN_ZF(N_)                                                                                             \
+  zfwd_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
+      sl, p->tw_zh, p->tw_zfull, 0);
+  JPM_FFT_SWITCH(sl.nz, RUN_ZF)
+#undef RUN_ZF
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "fft_z_r2c+ghost_fold");
+#define RUN_YF(N_)                                                                                             \
+  if (p->fft_tma_store)                                                                                        \
+    yfwd_kernel<N_, kColsC, true><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat, 0);                                                                                  \
+  else                                                                                                         \
+    yfwd_kernel<N_, kColsC, false><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>( \
+        sl, p->tw_y, tat, 0);
+  JPM_FFT_SWITCH(sl.ny, RUN_YF)
+#undef RUN_YF
+  JPM_LAUNCH_CHECK();
+  if ((rc = slab_barrier(p, st))) return rc;
+  if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
+#define RUN_XP(N_)                                                                                             \
+  if (p->fft_tma_store)                                                                                        \
+    xpot_kernel<N_, kXC, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>(  \
+        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats); \
+  else                                                                                                         \
+    xpot_kernel<N_, kXC, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats);
+  JPM_FFT_SWITCH(sl.nx, RUN_XP)
+#undef RUN_XP
+  JPM_LAUNCH_CHECK();
+  if ((rc = slab_barrier(p, st))) return rc;
+  if (p->timer) p->timer->mark(st, "fft_x_fwd+greens+ifft_x+transpose");
+#define RUN_YP(N_)                                                                                             \
+  ypot_kernel<N_, kColsC><<<dim3(nty, sl.lx, 1), threads_for<N_, kColsC>(), cols_smem<N_, kColsC>(), st>>>(    \
+      sl, p->tw_y, 0);
+  JPM_FFT_SWITCH(sl.ny, RUN_YP)
+#undef RUN_YP
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "ifft_y");
+#define RUN_ZP(N_)                                                                                             \
+  zinv_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
+      sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2);
+  JPM_FFT_SWITCH(sl.nz, RUN_ZP)
+#undef RUN_ZP
+  JPM_LAUNCH_CHECK();
+  if ((rc = slab_barrier(p, st))) return rc;
+  if (p->timer) p->timer->mark(st, "ifft_z_c2r+ghost_fill");
   return JPM_OK;
 }
 

@@ -28,6 +28,8 @@
 //   TMA = true : the mesh is the plan's ghost-zone array (plan_internal.cuh), where no box ever wraps:
 //                the read box (3 force meshes) arrives as ONE cp.async.bulk.tensor.4d signalled on an
 //                mbarrier, the paint box leaves as ONE cp.reduce.async.bulk.tensor.3d (.add.f32).
+#include <algorithm>
+#include <cmath>
 #include <cstdlib>
 
 #include "plan_internal.cuh"
@@ -60,6 +62,20 @@ struct jpm_sim {
   unsigned long long* stats = nullptr; // [0]/[1] paint/read global-memory fallbacks, [2]/[3] generic-stencil particles
   int cur = 0;
   bool painted = false, loaded = false;
+  bool pos_only = false;               // JPM_SIM_POSITIONS_ONLY: no velocities, no second ordering (paint / forces only)
+  // ---- potential ("FD") force path: psi mesh + real-space 4th-order differences (sim_readpot_kernel) ----
+  CUtensorMap tm_psi;                  // (PB, PB, BZ) boxes of force3_p component 0
+  bool pot_ok = false;                 // TMA path, margin 1, one GPU or slab plan with the fused chain
+  int force_mode = 0;                  // JPM_FORCE_SPECTRAL / JPM_FORCE_POTENTIAL / JPM_FORCE_AUTO
+  int cur_mode = 0;                    // what the next step runs (auto switches it from the measured error bound)
+  int pot_grid = 0;                    // persistent CTAs of sim_readpot_kernel
+  int pot_threads = 1024;              // threads per CTA of it (JPM_POT_THREADS=768: more registers per thread)
+  int* tile_counter = nullptr;
+  double* stats_host = nullptr;        // pinned copy of plan->pot_stats of the last finished step
+  cudaEvent_t stats_ev = nullptr;
+  bool stats_pending = false;
+  double last_bound = -1.0;            // last evaluated error bound (auto), < 0 = none yet
+  long long mode_steps[2] = {0, 0};    // steps run in spectral / potential mode
 };
 
 namespace jpm {
@@ -171,9 +187,11 @@ sim_fill_kernel(SimGeom g, const float* __restrict__ pos, const float* __restric
   const int slot = warp_claim<true>(cursor, tt, valid);
   if (valid) {
     spos[slot] = make_float4(x, y, z, __int_as_float(w));
-    svel[slot] = vel[3 * p];
-    svel[np + slot] = vel[3 * p + 1];
-    svel[2 * np + slot] = vel[3 * p + 2];
+    if (vel) {
+      svel[slot] = vel[3 * p];
+      svel[np + slot] = vel[3 * p + 1];
+      svel[2 * np + slot] = vel[3 * p + 2];
+    }
   }
 }
 
@@ -193,8 +211,10 @@ sim_store_kernel(SimGeom g, const float4* __restrict__ spos, const float* __rest
 // exclusive scan of count[nt] -> start[nt+1]; cursor = start; count = 0.  One CTA of 32 warps; warp w
 // owns the contiguous segment [w*seg, (w+1)*seg) and walks it 32 entries at a time (coalesced).
 __global__ void __launch_bounds__(1024)
-sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int nt) {
+sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int nt,
+                int* __restrict__ tile_counter = nullptr) {
   __shared__ int wsum[32];
+  if (threadIdx.x == 0 && tile_counter) *tile_counter = 0;   // work queue of the persistent read kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int seg = ((nt + 31) / 32 + 31) & ~31;
   const int b = warp * seg, e = min(b + seg, nt);
@@ -603,16 +623,18 @@ __device__ __forceinline__ void cp_async4(float* smem, const float* gmem) {
 }
 
 // ---- read3 + kick + drift + scatter into the next ordering --------------------------------------
-template <bool REL, int TS, int M, bool TMA>
+template <bool REL, int TS, int M, bool TMA, bool FMAX = false>
 __global__ void __launch_bounds__(512, 2)
 sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
                 const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ f0,
                 const float* __restrict__ f1, const float* __restrict__ f2, float kick, float drift,
                 long long np, int* __restrict__ cursor, float4* __restrict__ npos,
-                float* __restrict__ nvel, unsigned long long* __restrict__ stats, int l2ahead) {
+                float* __restrict__ nvel, unsigned long long* __restrict__ stats, int l2ahead,
+                unsigned* __restrict__ fmax_bits) {
   constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
   constexpr int BZ = TMA ? ((T + MZ + M + 1 + 3) & ~3) : B, NBOX = B * B * BZ;
   extern __shared__ __align__(128) float box[];        // [3][B][B][BZ]
+  float fmax = 0.f;
   __shared__ __align__(8) unsigned long long mbar;
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
@@ -742,6 +764,7 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
         }
         if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
       }
+      if (FMAX) fmax = fmaxf(fmax, fmaxf(fabsf(acc[0]), fmaxf(fabsf(acc[1]), fabsf(acc[2]))));
 #pragma unroll
       for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], vin[f]);
       p.x = fmaf(drift, v[0], p.x);
@@ -762,6 +785,314 @@ sim_read_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4*
   }
   nslow = __reduce_add_sync(0xffffffffu, nslow);
   if ((threadIdx.x & 31) == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
+  if (FMAX && fmax_bits) {   // largest force component seen (non-negative floats order like their bit patterns)
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmax));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(fmax_bits, m);
+  }
+}
+
+// ---- forces only: the three reads + stack of pm_forces (pm.py:54-56) from the tile-sorted state ------------
+// Same staging / gather as sim_read_kernel (TMA flavour), no kick / drift / re-sort: the interpolated force of
+// every particle goes to out[id][3] in the CALLER's particle order (id = Lagrangian site or list index).
+template <bool REL, int TS, int M>
+__global__ void __launch_bounds__(512, 2)
+sim_forces_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
+                  const int* __restrict__ start, const float* __restrict__ f0, const float* __restrict__ f1,
+                  const float* __restrict__ f2, float scale, float* __restrict__ out,
+                  unsigned long long* __restrict__ stats) {
+  constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = kTmaMz;
+  constexpr int BZ = (T + MZ + M + 1 + 3) & ~3, NBOX = B * B * BZ;
+  extern __shared__ __align__(128) float box[];        // [3][B][B][BZ]
+  __shared__ __align__(8) unsigned long long mbar;
+  const int t = blockIdx.x;
+  const int beg = start[t], end = start[t + 1];
+  if (beg == end) return;
+  const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
+  const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - MZ;
+  const float* fm[3] = {f0, f1, f2};
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar, 1);
+    fence_async_smem();
+    mbar_expect_tx(&mbar, 3u * NBOX * (unsigned)sizeof(float));
+    tma_load_4d(box, &tm, oz + g.mo, oy + g.mo, ox + g.mox, 0, &mbar);
+  }
+  int q = beg + threadIdx.x;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (q < end) p = __ldcs(spos + q);
+  __syncthreads();
+  mbar_wait(&mbar, 0);
+  int nslow = 0;
+  for (; q < end; q += blockDim.x) {
+    float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q + (int)blockDim.x < end) pn = __ldcs(spos + q + blockDim.x);
+    FastStencil s;
+    int lx, ly, lz;
+    float acc[3] = {0.f, 0.f, 0.f};
+    if (stencil_box<REL, B, B, BZ>(g, p, ox, oy, oz, s, lx, ly, lz)) {
+      const float* b0 = box + (lx * B + ly) * BZ + lz;
+      const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
+      const float kk[8] = {w00 * s.wz0, w00 * s.wz1, w01 * s.wz0, w01 * s.wz1,
+                           w10 * s.wz0, w10 * s.wz1, w11 * s.wz0, w11 * s.wz1};
+      constexpr int off[8] = {0, 1, BZ, BZ + 1, B * BZ, B * BZ + 1, B * BZ + BZ, B * BZ + BZ + 1};
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int f = 0; f < 3; ++f) acc[f] = fmaf(b0[f * NBOX + off[c]], kk[c], acc[f]);
+    } else {
+      Cic1 cx, cy, cz;
+      sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+      Corners c;
+      make_corners<B, BZ>(g, cx, cy, cz, ox, oy, oz, c);
+#pragma unroll
+      for (int cc = 0; cc < 8; ++cc) {
+        const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+        if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
+        const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
+        if (c.inside) {
+          const int o = (c.lx[a] * B + c.ly[b]) * BZ + c.lz[d];
+#pragma unroll
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
+        } else {
+          const long long o = mesh_index(g, c.ix[a], c.iy[b], c.iz[d]);
+#pragma unroll
+          for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(fm[f] + o), k, acc[f]);
+        }
+      }
+      if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
+    }
+    const int w = __float_as_int(p.w);
+    const long long id = REL ? ((long long)(w >> 20) * g.pny + ((w >> 10) & 1023)) * g.pnz + (w & 1023) : (long long)w;
+    out[3 * id] = acc[0] * scale;
+    out[3 * id + 1] = acc[1] * scale;
+    out[3 * id + 2] = acc[2] * scale;
+    p = pn;
+  }
+  nslow = __reduce_add_sync(0xffffffffu, nslow);
+  if ((threadIdx.x & 31) == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
+}
+
+// ---- potential flavour of read3 + kick + drift (the "FD" force path) --------------------------------------
+// The FFT chain delivers ONE mesh, psi = IFFT(G delta / k^2) (pmfft_potential, csrc/pmfft.cu).  The reference's
+// force spectra -gradient_kernel(k, d) * pot_k (pm.py:54-56, kernels.py:62-66) are the 4th-order central
+// differences of it,   F_d(c) = [8 (psi(c + e_d) - psi(c - e_d)) - (psi(c + 2 e_d) - psi(c - 2 e_d))] / 12,
+// so this kernel stages the psi box of a tile (2 more cells per side than the force box), differentiates it in
+// shared memory into the three force boxes and then runs the same gather + kick + drift + re-sort as
+// sim_read_kernel.  DRAM: one mesh box per tile instead of three.
+// PERSISTENT: one 1024-thread CTA per SM takes tiles from an atomic counter; the psi box of the NEXT tile lands
+// (TMA, mbarrier) in the second buffer while the particles of the current tile are processed.
+//   shared memory: psi[2][PB][PB][BZ] | F[3][B][B][BZ]       (tile 16, margin 1: 2 x 50.8 KB + 104 KB)
+// TMA flavour only (ghost-zone mesh, no box ever wraps), margin 1 (the ghost zone is 4 cells wide).
+template <int TS, int M> struct PotGeom {
+  static constexpr int T = 1 << TS, B = T + 2 * M + 1, PB = B + 4;
+  static constexpr int BZ = (T + kTmaMz + M + 3 + 3) & ~3;       // z cells: [oz, oz + BZ), oz = tile origin - 4
+  static constexpr int NBOX = B * B * BZ;                        // one force component
+  static constexpr int NPSI = PB * PB * BZ;
+  static constexpr int NPSI_PAD = (NPSI + 31) & ~31;             // keeps the second buffer 128-byte aligned
+  static constexpr int ZLO = kTmaMz - M, ZHI = kTmaMz + T + M;    // force cells [ZLO, ZHI] are gathered from
+  static_assert(ZLO - 2 >= 0 && ZHI + 2 < BZ, "the psi box must cover the +-2 stencil in z");
+  static constexpr int smem_bytes = (2 * NPSI_PAD + 3 * NBOX) * (int)sizeof(float);
+};
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
+                                            unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(dst)), "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// D psi along one axis at padded-mesh offset o with element stride sd (global-memory fallback)
+__device__ __forceinline__ float fd4_global(const float* __restrict__ psi, long long o, long long sd) {
+  const float d1 = __ldg(psi + o + sd) - __ldg(psi + o - sd);
+  const float d2 = __ldg(psi + o + 2 * sd) - __ldg(psi + o - 2 * sd);
+  return (2.0f / 3.0f) * d1 - (1.0f / 12.0f) * d2;
+}
+
+template <bool REL, int TS, int M, int NT>
+__global__ void __launch_bounds__(NT, 1)
+sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
+                   const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ psi,
+                   float kick, float drift, long long np, int* __restrict__ cursor, float4* __restrict__ npos,
+                   float* __restrict__ nvel, unsigned long long* __restrict__ stats, int* __restrict__ tile_counter,
+                   unsigned* __restrict__ fmax_bits, int l2ahead) {
+  using PG = PotGeom<TS, M>;
+  constexpr int B = PG::B, PB = PG::PB, BZ = PG::BZ, NBOX = PG::NBOX;
+  extern __shared__ __align__(128) float smem[];
+  float* const psib[2] = {smem, smem + PG::NPSI_PAD};
+  float* const box = smem + 2 * PG::NPSI_PAD;            // [3][B][B][BZ]
+  __shared__ __align__(8) unsigned long long mbar[2];
+  __shared__ int s_tile[2];
+  const int lane = threadIdx.x & 31;
+  int nslow = 0;
+  float fmax = 0.f;
+
+  // thread 0: next non-empty tile from the global counter; request its psi box
+  auto grab_and_load = [&](int buf) {
+    int t;
+    do {
+      t = atomicAdd(tile_counter, 1);
+    } while (t < g.nt && start[t] == start[t + 1]);
+    s_tile[buf] = t;
+    if (t < g.nt) {
+      const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
+      mbar_expect_tx(&mbar[buf], (unsigned)(PG::NPSI * sizeof(float)));
+      tma_load_3d(smem + buf * PG::NPSI_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M - 2 + g.mo, (tx << TS) - M - 2 + g.mox,
+                  &mbar[buf]);
+    }
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&mbar[0], 1);
+    mbar_init(&mbar[1], 1);
+    fence_async_smem();
+    grab_and_load(0);
+  }
+  __syncthreads();
+  unsigned phase0 = 0, phase1 = 0;
+  for (int buf = 0;; buf ^= 1) {
+    const int t = s_tile[buf];
+    if (t >= g.nt) break;
+    const int beg = start[t], end = start[t + 1];
+    const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
+    const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - kTmaMz;
+    // first particle of this thread streams in while the psi box lands and is differentiated
+    int q = beg + threadIdx.x;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float vin[3] = {0.f, 0.f, 0.f};
+    if (q < end) {
+      p = __ldcs(spos + q);
+#pragma unroll
+      for (int f = 0; f < 3; ++f) vin[f] = __ldcs(svel + f * np + q);
+    }
+    if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
+    else { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+    // F_d = D_d psi on the cells the gathers can touch: x, y in [0, B), z in [ZLO, ZHI]
+    {
+      const float* const ps = psib[buf];
+      constexpr int NZ = PG::ZHI - PG::ZLO + 1, NCELL = B * B * NZ;
+      constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
+      for (int i = threadIdx.x; i < NCELL; i += blockDim.x) {
+        const int r = i / NZ, lz = PG::ZLO + (i - r * NZ);
+        const int lx = r / B, ly = r - lx * B;
+        const float* c = ps + ((lx + 2) * PB + (ly + 2)) * BZ + lz;
+        const float fx = c8 * (c[PB * BZ] - c[-PB * BZ]) - c1 * (c[2 * PB * BZ] - c[-2 * PB * BZ]);
+        const float fy = c8 * (c[BZ] - c[-BZ]) - c1 * (c[2 * BZ] - c[-2 * BZ]);
+        const float fz = c8 * (c[1] - c[-1]) - c1 * (c[2] - c[-2]);
+        float* o = box + (lx * B + ly) * BZ + lz;
+        o[0] = fx; o[NBOX] = fy; o[2 * NBOX] = fz;
+      }
+    }
+    __syncthreads();      // force boxes complete; the other psi buffer was consumed one tile ago
+    if (threadIdx.x == 0) grab_and_load(buf ^ 1);
+    for (int qb = beg; qb < end; qb += blockDim.x) {
+      const bool valid = q < end;
+      const int qn = q + blockDim.x;
+      float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+      float vn[3] = {0.f, 0.f, 0.f};
+      if (qn < end) {
+        pn = __ldcs(spos + qn);
+#pragma unroll
+        for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
+      }
+      if (l2ahead > 0) {
+        const int qf = qn + l2ahead * (int)blockDim.x;
+        if (qf < end) {
+          prefetch_l2(spos + qf);
+          if ((threadIdx.x & 3) == 0) {
+#pragma unroll
+            for (int f = 0; f < 3; ++f) prefetch_l2(svel + f * np + qf);
+          }
+        }
+      }
+      int tt = 0, lx = 0, ly = 0, lz = 0;
+      bool fast = false;
+      FastStencil s;
+      if (valid) {
+        fast = stencil_box<REL, B, B, BZ>(g, p, ox, oy, oz, s, lx, ly, lz);
+        // the z extent of the force boxes that holds values is [ZLO, ZHI]
+        fast = fast && lz >= PG::ZLO && lz < PG::ZHI;
+        if (fast) {
+          tt = ((s.i0 >> TS) * g.nty + (s.j0 >> TS)) * g.ntz + (s.k0 >> TS);
+        } else {
+          Cic1 cx, cy, cz;
+          sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+          tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
+        }
+      }
+      const unsigned peers = __match_any_sync(0xffffffffu, valid ? tt : (0x40000000 | lane));
+      const int leader = __ffs(peers) - 1;
+      int slot = 0;
+      if (valid && lane == leader) slot = atomicAdd(cursor + tt, __popc(peers));
+      float v[3] = {0, 0, 0};
+      if (valid) {
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (fast) {
+          const float* b0 = box + (lx * B + ly) * BZ + lz;
+          const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
+          const float kk[8] = {w00 * s.wz0, w00 * s.wz1, w01 * s.wz0, w01 * s.wz1,
+                               w10 * s.wz0, w10 * s.wz1, w11 * s.wz0, w11 * s.wz1};
+          constexpr int off[8] = {0, 1, BZ, BZ + 1, B * BZ, B * BZ + 1, B * BZ + BZ, B * BZ + BZ + 1};
+          float mv[3][8];
+#pragma unroll
+          for (int f = 0; f < 3; ++f)
+#pragma unroll
+            for (int c = 0; c < 8; ++c) mv[f][c] = b0[f * NBOX + off[c]];
+#pragma unroll
+          for (int c = 0; c < 8; ++c)
+#pragma unroll
+            for (int f = 0; f < 3; ++f) acc[f] = fmaf(mv[f][c], kk[c], acc[f]);
+        } else {
+          // periodic-edge lanes and particles beyond the box: the generic corner rules; forces from the staged
+          // boxes when all 8 corners lie inside, else differentiated straight from the ghost-zone mesh
+          Cic1 cx, cy, cz;
+          sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
+          Corners c;
+          make_corners<B, BZ>(g, cx, cy, cz, ox, oy, oz, c);
+#pragma unroll
+          for (int a = 0; a < 2; ++a) c.inside = c.inside && c.lz[a] >= PG::ZLO && c.lz[a] <= PG::ZHI;
+#pragma unroll
+          for (int cc = 0; cc < 8; ++cc) {
+            const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
+            if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
+            const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
+            if (c.inside) {
+              const int o = (c.lx[a] * B + c.ly[b]) * BZ + c.lz[d];
+#pragma unroll
+              for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
+            } else {
+              const long long o = mesh_index(g, c.ix[a], c.iy[b], c.iz[d]);
+              acc[0] = fmaf(fd4_global(psi, o, g.msx), k, acc[0]);
+              acc[1] = fmaf(fd4_global(psi, o, g.msy), k, acc[1]);
+              acc[2] = fmaf(fd4_global(psi, o, 1), k, acc[2]);
+            }
+          }
+          if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
+        }
+        fmax = fmaxf(fmax, fmaxf(fabsf(acc[0]), fmaxf(fabsf(acc[1]), fabsf(acc[2]))));
+#pragma unroll
+        for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], vin[f]);
+        p.x = fmaf(drift, v[0], p.x);
+        p.y = fmaf(drift, v[1], p.y);
+        p.z = fmaf(drift, v[2], p.z);
+      }
+      slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
+      if (valid) {
+        npos[slot] = p;
+#pragma unroll
+        for (int f = 0; f < 3; ++f) nvel[f * np + slot] = v[f];
+      }
+      p = pn;
+      q = qn;
+#pragma unroll
+      for (int f = 0; f < 3; ++f) vin[f] = vn[f];
+    }
+    __syncthreads();      // every gather of this tile is done before the boxes are rebuilt; s_tile[buf ^ 1] visible
+  }
+  nslow = __reduce_add_sync(0xffffffffu, nslow);
+  if (lane == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
+  if (fmax_bits) {
+    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmax));   // non-negative floats order like their bits
+    if (lane == 0 && m) atomicMax(fmax_bits, m);
+  }
 }
 
 template <int TS, int M, bool TMA> constexpr int paint_smem() {
@@ -819,6 +1150,12 @@ using namespace jpm;
 extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int32_t ny, int32_t nz,
                                   int32_t pnx, int32_t pny, int32_t pnz, int32_t hx, int32_t hy,
                                   int32_t relative, int32_t tile, int32_t margin) {
+  return jpm_sim_create_ex(out, plan, nx, ny, nz, pnx, pny, pnz, hx, hy, relative, tile, margin, 0);
+}
+
+extern "C" int32_t jpm_sim_create_ex(jpm_sim** out, jpm_plan* plan, int32_t nx, int32_t ny, int32_t nz,
+                                     int32_t pnx, int32_t pny, int32_t pnz, int32_t hx, int32_t hy,
+                                     int32_t relative, int32_t tile, int32_t margin, int32_t flags) {
   JPM_CHECK_ARG(out, "null sim pointer");
   JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && pnx > 0 && pny > 0 && pnz > 0, "bad shape");
   JPM_CHECK_ARG((int64_t)nx * ny * nz < (1ll << 31), "mesh too large for int32 cell ids");
@@ -835,6 +1172,7 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   if (plan) JPM_CHECK_ARG(plan->nx == nx && plan->ny == ny && plan->nz == nz, "plan shape != sim mesh shape");
   jpm_sim* s = new jpm_sim();
   s->plan = plan;
+  s->pos_only = (flags & JPM_SIM_POSITIONS_ONLY) != 0;
   s->relative = relative;
   s->np = (long long)pnx * pny * pnz;
   s->g = make_geom(nx, ny, nz, pny, pnz, hx, hy, tile, margin);
@@ -855,6 +1193,7 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
   // TMA path: needs the plan's ghost-zone meshes (jpm_sim_step only) and a supported tile/margin pair
   memset(&s->tm_rho, 0, sizeof(CUtensorMap));
   memset(&s->tm_f3, 0, sizeof(CUtensorMap));
+  memset(&s->tm_psi, 0, sizeof(CUtensorMap));
   if (plan && tma_pair(ts, m) && nx >= s->g.T && ny >= s->g.T && nz >= s->g.T) {
     int32_t rc = plan_enable_padded(plan);
     if (rc) return rc;
@@ -883,14 +1222,59 @@ extern "C" int32_t jpm_sim_create(jpm_sim** out, jpm_plan* plan, int32_t nx, int
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
     JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_, true>,                                     \
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<false, TS_, M_, true, true>,                              \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_read_kernel<true, TS_, M_, true, true>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_forces_kernel<false, TS_, M_>,                                        \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
+    JPM_CUDA(cudaFuncSetAttribute(sim_forces_kernel<true, TS_, M_>,                                         \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, read_smem<TS_, M_, true>()));  \
   }
       JPM_SIM_DISPATCH_TMA(ts, m, SET_ATTR_TMA);
 #undef SET_ATTR_TMA
+      // potential path: margin 1 (the ghost zone is 4 = margin + 3 cells wide), fused FFT chain
+      if (m == 1 && plan->fft_on) {
+        const int PB = B + 4;
+        const unsigned bp[3] = {(unsigned)BZ, (unsigned)PB, (unsigned)PB};
+        if ((rc = encode_tensor_map(&s->tm_psi, plan->force3_p, 3, d3, st3, bp))) return rc;
+        int occ = 0;
+#define POT_ATTR(TS_, NT_)                                                                                 \
+  {                                                                                                         \
+    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<false, TS_, 1, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  PotGeom<TS_, 1>::smem_bytes));                                            \
+    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<true, TS_, 1, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                  PotGeom<TS_, 1>::smem_bytes));                                            \
+    JPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sim_readpot_kernel<true, TS_, 1, NT_>, NT_, \
+                                                           PotGeom<TS_, 1>::smem_bytes));                   \
+  }
+        s->pot_threads = 1024;
+        if (ts == 4) {
+          if (const char* e = getenv("JPM_POT_THREADS")) s->pot_threads = atoi(e) == 768 ? 768 : 1024;
+          if (s->pot_threads == 768) POT_ATTR(4, 768) else POT_ATTR(4, 1024)
+        } else {
+          POT_ATTR(3, 1024)
+        }
+#undef POT_ATTR
+        int dev = 0, sms = kNumSMs;
+        JPM_CUDA(cudaGetDevice(&dev));
+        JPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        s->pot_grid = std::max(1, occ) * sms;
+        s->pot_ok = occ > 0;
+      }
     }
   }
-  for (int i = 0; i < 2; ++i) {
+  JPM_CUDA(cudaMalloc(&s->tile_counter, sizeof(int)));
+  JPM_CUDA(cudaMemset(s->tile_counter, 0, sizeof(int)));
+  JPM_CUDA(cudaMallocHost(&s->stats_host, 4 * sizeof(double)));
+  JPM_CUDA(cudaEventCreateWithFlags(&s->stats_ev, cudaEventDisableTiming));
+  if (const char* e = getenv("JPM_FORCE_MODE")) {   // default force path of new sims (tests / A-B runs)
+    s->force_mode = atoi(e);
+    s->cur_mode = s->force_mode == 1 ? 1 : 0;
+  }
+  for (int i = 0; i < (s->pos_only ? 1 : 2); ++i) {
     JPM_CUDA(cudaMalloc(&s->pos[i], s->np * sizeof(float4)));
-    JPM_CUDA(cudaMalloc(&s->vel[i], 3 * s->np * sizeof(float)));
+    if (!s->pos_only) JPM_CUDA(cudaMalloc(&s->vel[i], 3 * s->np * sizeof(float)));
     JPM_CUDA(cudaMalloc(&s->start[i], (s->g.nt + 1) * sizeof(int)));
   }
   JPM_CUDA(cudaMalloc(&s->count, s->g.nt * sizeof(int)));
@@ -912,12 +1296,17 @@ extern "C" int32_t jpm_sim_destroy(jpm_sim* s) {
   if (s->count) cudaFree(s->count);
   if (s->cursor) cudaFree(s->cursor);
   if (s->stats) cudaFree(s->stats);
+  if (s->tile_counter) cudaFree(s->tile_counter);
+  if (s->stats_host) cudaFreeHost(s->stats_host);
+  if (s->stats_ev) cudaEventDestroy(s->stats_ev);
   delete s;
   return JPM_OK;
 }
 
 extern "C" int32_t jpm_sim_load(jpm_sim* s, void* stream, const float* pos, const float* vel) {
-  JPM_CHECK_ARG(s && pos && vel, "null pointer");
+  JPM_CHECK_ARG(s && pos, "null pointer");
+  JPM_CHECK_ARG(s->pos_only ? vel == nullptr : vel != nullptr,
+                "velocities are required, except for a JPM_SIM_POSITIONS_ONLY sim, which takes none");
   cudaStream_t st = (cudaStream_t)stream;
   const int blocks = div_up(s->np, 256);
   JPM_CUDA(cudaMemsetAsync(s->count, 0, s->g.nt * sizeof(int), st));
@@ -948,6 +1337,7 @@ extern "C" int32_t jpm_sim_load(jpm_sim* s, void* stream, const float* pos, cons
 
 extern "C" int32_t jpm_sim_store(jpm_sim* s, void* stream, float* pos, float* vel) {
   JPM_CHECK_ARG(s && (pos || vel), "null pointer");
+  JPM_CHECK_ARG(!(s->pos_only && vel), "a JPM_SIM_POSITIONS_ONLY sim holds no velocities");
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
   cudaStream_t st = (cudaStream_t)stream;
   if (s->relative)
@@ -990,21 +1380,32 @@ static int32_t sim_paint_impl(jpm_sim* s, cudaStream_t st, float* mesh, bool tma
 static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const float* fy, const float* fz,
                              float kick_coef, float drift_coef, bool tma) {
   const int nxt = s->cur ^ 1;
-  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt);
+  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt, s->tile_counter);
   JPM_LAUNCH_CHECK();
   const int ts = s->g.tshift, m = s->g.m;
   const SimGeom& g = tma ? s->gp : s->g;
+  const bool want_fmax = tma && s->force_mode == 2 && s->plan && s->plan->pot_stats;
+  unsigned* fmax_bits = want_fmax ? reinterpret_cast<unsigned*>(s->plan->pot_stats + 1) : nullptr;
   static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
 #define LAUNCH_READ_T(TS_, M_, TMA_)                                                                     \
-  {                                                                                                      \
+  if (TMA_ && want_fmax) {                                                                               \
+    if (s->relative)                                                                                     \
+      sim_read_kernel<true, TS_, M_, TMA_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(         \
+          s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead, fmax_bits);         \
+    else                                                                                                 \
+      sim_read_kernel<false, TS_, M_, TMA_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(        \
+          s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead, fmax_bits);         \
+  } else {                                                                                               \
     if (s->relative)                                                                                     \
       sim_read_kernel<true, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(               \
           s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
-          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead);                    \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead, fmax_bits);         \
     else                                                                                                 \
       sim_read_kernel<false, TS_, M_, TMA_><<<g.nt, 512, read_smem<TS_, M_, TMA_>(), st>>>(              \
           s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, fy, fz, kick_coef,          \
-          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead);                    \
+          drift_coef, s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, l2ahead, fmax_bits);         \
   }
 #define LAUNCH_READ(TS_, M_) LAUNCH_READ_T(TS_, M_, false)
 #define LAUNCH_READ_TMA(TS_, M_) LAUNCH_READ_T(TS_, M_, true)
@@ -1019,6 +1420,85 @@ static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const
   return JPM_OK;
 }
 
+// potential flavour: psi (force3_p component 0, ghosts filled) -> kick / drift / re-sort, persistent CTAs
+static int32_t sim_readpot_impl(jpm_sim* s, cudaStream_t st, float kick_coef, float drift_coef) {
+  const int nxt = s->cur ^ 1;
+  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt, s->tile_counter);
+  JPM_LAUNCH_CHECK();
+  const SimGeom& g = s->gp;
+  jpm_plan* p = s->plan;
+  unsigned* fmax_bits = p->pot_stats ? reinterpret_cast<unsigned*>(p->pot_stats + 1) : nullptr;
+  static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
+  const int grid = std::min(s->pot_grid, g.nt);
+#define LAUNCH_POT(REL_, TS_)                                                                              \
+  if (s->pot_threads == 768 && TS_ == 4)                                                                   \
+    sim_readpot_kernel<REL_, 4, 1, 768><<<grid, 768, PotGeom<4, 1>::smem_bytes, st>>>(                     \
+        s->tm_psi, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], p->force3_p, kick_coef, drift_coef, \
+        s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead);        \
+  else                                                                                                     \
+  sim_readpot_kernel<REL_, TS_, 1, 1024><<<grid, 1024, PotGeom<TS_, 1>::smem_bytes, st>>>(                 \
+      s->tm_psi, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], p->force3_p, kick_coef, drift_coef,  \
+      s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead)
+  if (s->g.tshift == 4) {
+    if (s->relative) LAUNCH_POT(true, 4); else LAUNCH_POT(false, 4);
+  } else {
+    if (s->relative) LAUNCH_POT(true, 3); else LAUNCH_POT(false, 3);
+  }
+#undef LAUNCH_POT
+  JPM_LAUNCH_CHECK();
+  s->cur = nxt;
+  s->painted = false;
+  return JPM_OK;
+}
+
+// fp32 cancellation bound of the potential path.  Differencing psi (rms psi_rms, FFT round-off ~ 5e-7 of its
+// maximum) leaves an absolute force error ~ 5.4e-7 * max|psi|; measured against the float64 oracle on 256^3 and
+// 512^3 LCDM fields (linear a = 0.1 and clustered a = 1, tools/phi_fd_precision.py): max|psi| <= 5.3 psi_rms, so
+//     max|dF| / max|F|  <~  2.7e-6 * psi_rms / max|F|.
+// AUTO runs the three-transform chain while that bound exceeds kPotSwitchUp and the potential chain below
+// kPotSwitchDown (hysteresis), so every step stays inside BASELINE.json's 1e-5 force tolerance.
+constexpr double kPotErrCoef = 2.7e-6, kPotSwitchDown = 4.0e-6, kPotSwitchUp = 6.0e-6;
+
+static void sim_poll_stats(jpm_sim* s) {
+  if (!s->stats_pending || cudaEventQuery(s->stats_ev) != cudaSuccess) return;
+  s->stats_pending = false;
+  const double sumsq = s->stats_host[0];
+  unsigned long long bits;
+  memcpy(&bits, &s->stats_host[1], sizeof(bits));
+  const unsigned fb = (unsigned)(bits & 0xffffffffull);
+  float fmax;
+  memcpy(&fmax, &fb, sizeof(fmax));
+  if (!(sumsq > 0.0) || !(fmax > 0.f)) return;
+  s->last_bound = kPotErrCoef * std::sqrt(sumsq) / (double)fmax;
+  if (s->force_mode == 2) {
+    if (s->last_bound < kPotSwitchDown) s->cur_mode = 1;
+    else if (s->last_bound > kPotSwitchUp) s->cur_mode = 0;
+  }
+}
+
+extern "C" int32_t jpm_sim_set_force_mode(jpm_sim* s, int32_t mode) {
+  JPM_CHECK_ARG(s, "null sim");
+  JPM_CHECK_ARG(mode >= 0 && mode <= 2, "force mode must be 0 (spectral), 1 (potential) or 2 (auto)");
+  JPM_CHECK_ARG(mode == 0 || s->pot_ok,
+                "potential force path needs the TMA tile path with margin 1 on a power-of-two mesh (fused FFT chain)");
+  s->force_mode = mode;
+  s->cur_mode = mode == 1 ? 1 : 0;
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_sim_force_info(jpm_sim* s, void* stream, double* out6_host) {
+  JPM_CHECK_ARG(s && out6_host, "null pointer");
+  JPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  sim_poll_stats(s);
+  out6_host[0] = (double)s->force_mode;
+  out6_host[1] = (double)s->cur_mode;
+  out6_host[2] = s->last_bound;
+  out6_host[3] = (double)s->mode_steps[0];
+  out6_host[4] = (double)s->mode_steps[1];
+  out6_host[5] = s->pot_ok ? 1.0 : 0.0;
+  return JPM_OK;
+}
+
 extern "C" int32_t jpm_sim_paint(jpm_sim* s, void* stream, float* mesh) {
   JPM_CHECK_ARG(s && mesh, "null pointer");
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
@@ -1029,11 +1509,45 @@ extern "C" int32_t jpm_sim_read_kick_drift(jpm_sim* s, void* stream, const float
                                            const float* fz, float kick_coef, float drift_coef) {
   JPM_CHECK_ARG(s && fx && fy && fz, "null pointer");
   JPM_CHECK_ARG(s->painted, "jpm_sim_read_kick_drift must follow jpm_sim_paint (tile occupancy)");
+  JPM_CHECK_ARG(!s->pos_only, "a JPM_SIM_POSITIONS_ONLY sim cannot step");
   return sim_read_impl(s, (cudaStream_t)stream, fx, fy, fz, kick_coef, drift_coef, false);
+}
+
+// pm_forces on the fast kernels: paint the loaded state (TMA reduce-add), fused FFT chain, gather the three
+// force components of every particle into out[np][3] in the caller's order.
+extern "C" int32_t jpm_sim_forces(jpm_sim* s, void* stream, float* out, float scale, float r_split,
+                                  const float* filter_tab, int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(s && s->plan && out, "null pointer / sim has no FFT plan attached");
+  JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
+  JPM_CHECK_ARG(s->tma, "jpm_sim_forces needs the TMA tile path (tile 8/16, margin 1/2, nz % 4 == 0)");
+  JPM_CHECK_ARG(!filter_tab || (n_tab >= 2 && filter_kmax > 0.f), "bad filter table");
+  cudaStream_t st = (cudaStream_t)stream;
+  jpm_plan* p = s->plan;
+  int32_t rc;
+  JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+  if ((rc = sim_paint_impl(s, st, p->density_p, true))) return rc;
+  if ((rc = plan_padded_forces(p, st, r_split, filter_tab, n_tab, filter_kmax))) return rc;
+  const SimGeom& g = s->gp;
+  const int ts = s->g.tshift, m = s->g.m;
+  const float *fx = p->force3_p, *fy = p->force3_p + p->npad, *fz = p->force3_p + 2 * p->npad;
+#define LAUNCH_FORCES(TS_, M_)                                                                           \
+  {                                                                                                      \
+    if (s->relative)                                                                                     \
+      sim_forces_kernel<true, TS_, M_><<<g.nt, 512, read_smem<TS_, M_, true>(), st>>>(                   \
+          s->tm_f3, g, s->pos[s->cur], s->start[s->cur], fx, fy, fz, scale, out, s->stats);              \
+    else                                                                                                 \
+      sim_forces_kernel<false, TS_, M_><<<g.nt, 512, read_smem<TS_, M_, true>(), st>>>(                  \
+          s->tm_f3, g, s->pos[s->cur], s->start[s->cur], fx, fy, fz, scale, out, s->stats);              \
+  }
+  JPM_SIM_DISPATCH_TMA(ts, m, LAUNCH_FORCES);
+#undef LAUNCH_FORCES
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
 }
 
 extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float drift_coef) {
   JPM_CHECK_ARG(s && s->plan, "sim has no FFT plan attached");
+  JPM_CHECK_ARG(!s->pos_only, "a JPM_SIM_POSITIONS_ONLY sim cannot step");
   JPM_CHECK_ARG(s->loaded, "sim has no particles loaded");
   cudaStream_t st = (cudaStream_t)stream;
   jpm_plan* p = s->plan;
@@ -1046,10 +1560,36 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
     if (tm) tm->mark(st, "mesh_memset");
     if ((rc = sim_paint_impl(s, st, p->density_p, true))) return rc;
     if (tm) tm->mark(st, "sim_paint");
-    if ((rc = plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f))) return rc;
-    rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
-                       drift_coef, true);
-    if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
+    if (s->force_mode != 0 && !s->pot_ok) {
+      set_error("potential force path not available for this sim (needs margin 1 and the fused FFT chain)");
+      return JPM_ERR_INVALID;
+    }
+    if (s->force_mode == 2) sim_poll_stats(s);
+    const bool want_stats = s->force_mode == 2;
+    if (want_stats && !p->pot_stats) {
+      JPM_CUDA(cudaMalloc(&p->pot_stats, 4 * sizeof(double)));
+    }
+    if (s->force_mode != 0 && s->cur_mode == 1) {
+      // potential chain: ONE inverse transform, forces differentiated in the read kernel
+      if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f))) return rc;
+      rc = sim_readpot_impl(s, st, kick_coef, drift_coef);
+      if (tm) tm->mark(st, "tile_scan+sim_readpot_kick_drift");
+      ++s->mode_steps[1];
+    } else {
+      if (want_stats) JPM_CUDA(cudaMemsetAsync(p->pot_stats, 0, 4 * sizeof(double), st));
+      p->want_sumsq = want_stats;
+      if ((rc = plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f))) return rc;
+      p->want_sumsq = false;
+      rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
+                         drift_coef, true);
+      if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
+      ++s->mode_steps[0];
+    }
+    if (rc == JPM_OK && want_stats && !s->stats_pending) {
+      JPM_CUDA(cudaMemcpyAsync(s->stats_host, p->pot_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      JPM_CUDA(cudaEventRecord(s->stats_ev, st));
+      s->stats_pending = true;
+    }
     return rc;
   }
   JPM_CHECK_ARG(!p->is_slab, "slab plan: the tile/margin pair must be one the TMA path supports");
@@ -1062,6 +1602,25 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
                      false);
   if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
   return rc;
+}
+
+// End to end through HOST buffers on the fast kernels: H2D pos / vel, tile sort (jpm_sim_load), one resident step,
+// un-sort (jpm_sim_store), D2H.  Synchronises `stream`.
+extern "C" int32_t jpm_sim_step_host_f32(jpm_sim* s, void* stream, float* pos_host, float* vel_host, float* pos_dev,
+                                         float* vel_dev, float kick_coef, float drift_coef) {
+  JPM_CHECK_ARG(s && pos_host && vel_host && pos_dev && vel_dev, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t bytes = (size_t)s->np * 3 * sizeof(float);
+  JPM_CUDA(cudaMemcpyAsync(pos_dev, pos_host, bytes, cudaMemcpyHostToDevice, st));
+  JPM_CUDA(cudaMemcpyAsync(vel_dev, vel_host, bytes, cudaMemcpyHostToDevice, st));
+  int32_t rc;
+  if ((rc = jpm_sim_load(s, stream, pos_dev, vel_dev))) return rc;
+  if ((rc = jpm_sim_step(s, stream, kick_coef, drift_coef))) return rc;
+  if ((rc = jpm_sim_store(s, stream, pos_dev, vel_dev))) return rc;
+  JPM_CUDA(cudaMemcpyAsync(pos_host, pos_dev, bytes, cudaMemcpyDeviceToHost, st));
+  JPM_CUDA(cudaMemcpyAsync(vel_host, vel_dev, bytes, cudaMemcpyDeviceToHost, st));
+  JPM_CUDA(cudaStreamSynchronize(st));
+  return JPM_OK;
 }
 
 // One jpm_sim_step with a CUDA event at every stage boundary.  Synchronises the stream.  names_out

@@ -138,17 +138,28 @@ def kick_drift_coefficients(cosmo, a0, a1, nsteps, scheme="symplectic"):
 
 def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_absolute_pos=True,
                      scheme="symplectic", halo_size=0, sharding=None, callback=None, resident=True,
-                     tile=None, margin=2):
+                     tile=None, margin=None, force_mode="spectral", info=None):
     """Run `nsteps` drift-kick steps in place on (pos, vel) and return them.
 
     The first drift is a plain axpy; every following force evaluation is one fused
     paint -> FFT -> k-space -> 3x iFFT -> read3+kick+drift chain, with the drift of the NEXT
     step folded into the same kernel that applies the kick.  `resident=True` keeps the particles
     in the tile-sorted device state of jaxpm_b200/csrc/sim.cu between steps (fast for scattered,
-    late-time distributions); `resident=False` runs the order-preserving kernels every step."""
+    late-time distributions); `resident=False` runs the order-preserving kernels every step.
+
+    `force_mode` (resident, power-of-two meshes): "spectral" = three inverse transforms of -gradient_kernel *
+    pot_k as pm.py:54-56 writes them; "potential" = one inverse transform of pot_k and the 4th-order difference
+    stencil that gradient_kernel (kernels.py:62-66) is the symbol of, applied in the read kernel; "auto" =
+    per step, whichever the device-measured fp32 error bound allows (see include/jaxpm_b200.h).
+    `info` (a dict) receives the force-path statistics of the run."""
     pos, vel = as_f32(pos), as_f32(vel)
     relative = not paint_absolute_pos
     mesh_shape = tuple(pos.shape[:3]) if (mesh_shape is None or relative) else tuple(mesh_shape)
+    if not _single(sharding) and not relative:
+        # the sharded steppers integrate displacements from Lagrangian sites (the only mode the reference supports
+        # multi-device, painting.py:51-55); absolute positions would be silently wrong
+        raise NotImplementedError("sharded nbody_kick_drift needs paint_absolute_pos=False (relative mode), "
+                                  "like the reference's multi-device path")
     d, k = kick_drift_coefficients(cosmo, a0, a1, nsteps, scheme)
     ops.axpby(1.0, pos, d[0], vel, out=pos)
     if not _single(sharding):
@@ -163,8 +174,12 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
                 callback(n, pos, vel)
         return pos, vel
     # resident tile-sorted state: load once, K fused steps, store back in the caller's order
+    if margin is None:
+        margin = 2 if force_mode == "spectral" else 1     # the potential path's psi box fills the 4-cell ghost zone
     sim = ops.Sim(mesh_shape, pos.shape[:3] if pos.dim() == 4 else (1, 1, pos.numel() // 3), relative,
                   pos.device, tile=tile, margin=margin)
+    if force_mode != "spectral":
+        sim.set_force_mode(force_mode)
     sim.load(pos, vel)
     for n in range(nsteps):
         sim.step(k[n], d[n + 1] if n + 1 < nsteps else 0.0)
@@ -172,6 +187,9 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
             sim.store(pos, vel)
             callback(n, pos, vel)
     sim.store(pos, vel)
+    if info is not None:
+        info.update(sim.force_info())
+        info["fallbacks"] = sim.fallback_counts()
     return pos, vel
 
 

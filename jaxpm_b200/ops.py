@@ -44,7 +44,36 @@ def get_plan(shape, device):
 
 
 def clear_plans():
+    _force_sims.clear()
     _plans.clear()
+
+
+_force_sims = {}
+
+
+def fast_path_shape(mesh_shape):
+    """True when the tile kernels + fused FFT chain serve this mesh (powers of two in [16, 1024])."""
+    return all(16 <= int(n) <= 1024 and (int(n) & (int(n) - 1)) == 0 for n in mesh_shape)
+
+
+def pm_forces_tiles(positions, mesh_shape, relative, r_split=0.0, filter_tab=None):
+    """jaxpm/pm.py:12-58 on the fast kernels: tile-sort the particles (positions only), shared-memory paint with
+    TMA reduce-add, fused FFT chain, shared-memory gather; forces come back in the caller's particle order.
+    The positions-only resident state (16 B per particle) is cached per (mesh, particle count, mode, device)."""
+    pos = as_f32(positions)
+    mesh_shape = tuple(int(n) for n in mesh_shape)
+    npart = pos.numel() // 3
+    pshape = tuple(pos.shape[:3]) if (relative or pos.dim() == 4) else (1, 1, npart)
+    key = (mesh_shape, pshape, bool(relative), pos.device.index or 0)
+    sim = _force_sims.get(key)
+    if sim is None:
+        _force_sims.clear()          # one cached state at a time: it is 16 B per particle
+        sim = _force_sims[key] = Sim(mesh_shape, pshape, relative, pos.device, tile=16 if min(mesh_shape) >= 64 else 8,
+                                     margin=1, positions_only=True)
+    sim.load(pos)
+    out = torch.empty(pos.shape, dtype=torch.float32, device=pos.device)
+    sim.forces(out, 1.0, r_split, filter_tab)
+    return out
 
 
 def _wargs(weight, n, device):
@@ -220,6 +249,15 @@ def force_meshes_from_density_fused(density, plan, r_split=0.0, filter_tab=None)
     return out
 
 
+def potential_from_density_fused(density, plan, r_split=0.0, filter_tab=None):
+    """psi = IFFT(G delta_k / k^2) = -phi through the one-inverse-transform chain (csrc/pmfft.cu)."""
+    d = as_f32(density)
+    out = torch.empty(plan.shape, dtype=torch.float32, device=d.device)
+    fp, nt, km, keep = _ftab(filter_tab, d.device)
+    call("jpm_density_to_potential_fused", plan.handle, stream(), ptr(d), ptr(out), float(r_split), fp, nt, km)
+    return out
+
+
 def lpt2_source(delta_k, plan):
     """delta2 of jaxpm/pm.py:88-109 from the first-order spectrum."""
     sh = torch.empty((6, *plan.spec_shape), dtype=torch.complex64, device=delta_k.device)
@@ -290,7 +328,7 @@ class Sim:
     """Tile-sorted resident particle state (jpm_sim): load once, step many times, store back."""
 
     def __init__(self, mesh_shape, particle_shape, relative, device, halo=(0, 0), tile=None, margin=2,
-                 with_plan=True, plan=None):
+                 with_plan=True, plan=None, positions_only=False):
         self.mesh_shape = tuple(int(s) for s in mesh_shape)
         self.pshape = tuple(int(s) for s in particle_shape)
         self.relative, self.device, self.halo = bool(relative), device, halo
@@ -301,9 +339,10 @@ class Sim:
         self.plan = plan if plan is not None else (get_plan(self.mesh_shape, device) if with_plan else None)
         h = C.c_void_p()
         with torch.cuda.device(device):
-            call("jpm_sim_create", C.byref(h), self.plan.handle if self.plan else None, *self.mesh_shape,
-                 *self.pshape, halo[0], halo[1], int(self.relative), tile, margin)
+            call("jpm_sim_create_ex", C.byref(h), self.plan.handle if self.plan else None, *self.mesh_shape,
+                 *self.pshape, halo[0], halo[1], int(self.relative), tile, margin, 1 if positions_only else 0)
         self.handle = h
+        self.positions_only = bool(positions_only)
 
     def __del__(self):
         try:
@@ -312,8 +351,17 @@ class Sim:
         except Exception:
             pass
 
-    def load(self, pos, vel):
+    def load(self, pos, vel=None):
         call("jpm_sim_load", self.handle, stream(), ptr(pos, torch.float32), ptr(vel, torch.float32))
+
+    def forces(self, out=None, scale=1.0, r_split=0.0, filter_tab=None):
+        """pm_forces of the loaded state on the tile kernels -> [np, 3] in the caller's particle order."""
+        npart = self.pshape[0] * self.pshape[1] * self.pshape[2]
+        if out is None:
+            out = torch.empty((npart, 3), dtype=torch.float32, device=self.device)
+        fp, nt, km, keep = _ftab(filter_tab, self.device)
+        call("jpm_sim_forces", self.handle, stream(), ptr(out, torch.float32), float(scale), float(r_split), fp, nt, km)
+        return out
 
     def store(self, pos, vel):
         call("jpm_sim_store", self.handle, stream(), ptr(pos, torch.float32), ptr(vel, torch.float32))
@@ -330,6 +378,12 @@ class Sim:
     def step(self, kick, drift):
         call("jpm_sim_step", self.handle, stream(), float(kick), float(drift))
 
+    def step_host(self, pos_host, vel_host, pos_dev, vel_dev, kick, drift):
+        """Host-buffer entry (pinned CPU tensors in / out) on the tile kernels; synchronises the stream."""
+        assert not pos_host.is_cuda and not vel_host.is_cuda
+        call("jpm_sim_step_host_f32", self.handle, stream(), pos_host.data_ptr(), vel_host.data_ptr(),
+             ptr(pos_dev, torch.float32), ptr(vel_dev, torch.float32), float(kick), float(drift))
+
     def step_profile(self, kick, drift):
         """One step with per-stage CUDA-event timing: [(stage name, milliseconds), ...]."""
         names = (C.c_char_p * 24)()
@@ -337,6 +391,19 @@ class Sim:
         n = C.c_int32(0)
         call("jpm_sim_step_profile", self.handle, stream(), float(kick), float(drift), names, ms, 24, C.byref(n))
         return [(names[i].decode(), float(ms[i])) for i in range(n.value)]
+
+    FORCE_MODES = {"spectral": 0, "potential": 1, "auto": 2}
+
+    def set_force_mode(self, mode):
+        """'spectral' (three inverse transforms), 'potential' (one + difference stencil) or 'auto'."""
+        call("jpm_sim_set_force_mode", self.handle, int(self.FORCE_MODES.get(mode, mode)))
+
+    def force_info(self):
+        out = (C.c_double * 6)()
+        call("jpm_sim_force_info", self.handle, stream(), out)
+        names = {v: k for k, v in self.FORCE_MODES.items()}
+        return {"mode": names[int(out[0])], "next": names[int(out[1])], "error_bound": float(out[2]),
+                "steps_spectral": int(out[3]), "steps_potential": int(out[4]), "potential_available": bool(out[5])}
 
     def fallback_counts(self):
         out = (C.c_int64 * 4)()

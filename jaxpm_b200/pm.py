@@ -18,6 +18,11 @@ from .distributed import HalfSpectrum, _single, fft3d, ifft3d, normal_field
 from .growth import dGf2a, dGfa, growth_factor, growth_factor_second, growth_rate, growth_rate_second
 
 
+import os as _os
+
+_FAST_API = _os.environ.get("JPM_FAST_API", "1") != "0"   # JPM_FAST_API=0: order-preserving kernels + cuFFT everywhere
+
+
 def _filter_key(ft):
     return None if ft is None else (ft[0], float(ft[1]))
 
@@ -75,7 +80,10 @@ class _ForcesFromSpectrum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, field, positions, relative, r_split, filter_tab):
         plan = ops.get_plan(field.shape, field.device)
-        f3 = ops.force_meshes_from_density(field, plan, r_split, filter_tab)
+        if ops.fast_path_shape(plan.shape) and _FAST_API:
+            f3 = ops.force_meshes_from_density_fused(field, plan, r_split, filter_tab)
+        else:
+            f3 = ops.force_meshes_from_density(field, plan, r_split, filter_tab)
         out = ops.cic_read3(f3, positions, 1.0, relative)
         ctx.save_for_backward(positions, f3)
         ctx.cfg = (plan, relative, r_split, filter_tab)
@@ -126,6 +134,10 @@ def pm_forces(positions, mesh_shape=None, delta=None, r_split=0, paint_absolute_
     if delta is None:
         if relative:
             mesh_shape = tuple(positions.shape[:3])  # pm.py:36-39: mesh comes from the displacement shape
+        if (ops.fast_path_shape(mesh_shape) and not (positions.requires_grad and torch.is_grad_enabled())
+                and positions.numel() > 0 and _FAST_API):
+            # no gradient requested: tile-binned paint, fused FFT chain, shared-memory gather
+            return ops.pm_forces_tiles(positions, mesh_shape, relative, float(r_split), filter_tab)
         return _PMForces.apply(positions, tuple(mesh_shape), relative, float(r_split), filter_tab)
     if isinstance(delta, torch.Tensor) and delta.is_complex():
         # a spectrum from fft3d: go back to the real field once (cheap, keeps one code path)

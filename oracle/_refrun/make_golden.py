@@ -202,6 +202,30 @@ def gen_distributed():
     save("distributed", **out)
 
 
+def gen_distributed_slab():
+    """x-slab decompositions (pdims (P, 1)) of a power-of-two mesh, the shapes the fused peer-memory slab path
+    (jaxpm_b200/slab.py) serves: the reference's own paint / read / pm_forces / uniform_particles, sharded."""
+    shape, halo = (32, 16, 16), 8
+    rng = np.random.default_rng(23)
+    disp = np.clip(1.4 * rng.standard_normal((*shape, 3)), -3.9, 3.9).astype(np.float32)
+    field = rng.standard_normal(shape).astype(np.float32)
+    out = dict(disp=disp, field=field, halo=np.int32(halo))
+    clear_mesh()
+    out["single_paint"] = painting.cic_paint_dx(jnp.asarray(disp))
+    out["single_forces"] = pm.pm_forces(jnp.asarray(disp), mesh_shape=shape, paint_absolute_pos=False)
+    for pd in ((2, 1), (4, 1)):
+        tag = f"p{pd[0]}{pd[1]}"
+        sh = NamedSharding(make_mesh(pd), P('x', 'y'))
+        out[f"{tag}_paint"] = painting.cic_paint_dx(jnp.asarray(disp), halo_size=(halo, halo), sharding=sh)
+        out[f"{tag}_read"] = painting.cic_read_dx(jnp.asarray(field), jnp.asarray(disp), halo_size=(halo, halo),
+                                                  sharding=sh)
+        out[f"{tag}_forces"] = pm.pm_forces(jnp.asarray(disp), mesh_shape=shape, paint_absolute_pos=False,
+                                            halo_size=(halo, halo), sharding=sh)
+        out[f"{tag}_particles"] = distributed.uniform_particles(shape, sharding=sh)
+        clear_mesh()
+    save("distributed_slab", **out)
+
+
 def gen_power_spectrum():
     rng = np.random.default_rng(17)
     shape, box = (16, 16, 24), (100.0, 100.0, 150.0)
@@ -239,7 +263,7 @@ def gen_widened():
 if __name__ == "__main__":
     only = sys.argv[1:]
     for fn in (gen_paint_read_abs, gen_paint_read_rel, gen_kernels, gen_pm_forces, gen_lpt, gen_growth_ode,
-               gen_distributed, gen_power_spectrum, gen_widened):
+               gen_distributed, gen_distributed_slab, gen_power_spectrum, gen_widened):
         if only and fn.__name__ not in only:
             continue
         fn()

@@ -164,3 +164,86 @@ def test_golden_power_spectrum_and_widened_rows(cuda):
                    w["mesh2_unit"]) < FIELD_TOL
     from jaxpm_b200.lensing import density_plane
     assert rel_err(N(density_plane(T(w["pos3"], cuda), (16, 16, 16), 8.0, 4.0, 12)), w["density_plane"]) < FIELD_TOL
+
+
+# ---- multi-GPU decompositions against the reference-source fixtures ------------------------
+def _padded_density(plan, cuda):
+    """The rank's ghost-zone density array [nxp][nyp][nzp] (painted, ghosts not folded)."""
+    import ctypes as C
+    from jaxpm_b200._lib import call, ptr, stream
+    dims = (C.c_int32 * 3)()
+    call("jpm_plan_padded_get_f32", plan.handle, stream(), 0, None, dims)
+    out = torch.empty(tuple(int(d) for d in dims), dtype=torch.float32, device=cuda)
+    call("jpm_plan_padded_get_f32", plan.handle, stream(), 0, ptr(out), dims)
+    return out
+
+
+@pytest.mark.parametrize("P", [2, 4])
+def test_golden_slab_path(cuda, P):
+    """The fused peer-memory slab path (jaxpm_b200/slab.py, csrc/pmfft.cu, csrc/sim.cu) with P ranks in this process,
+    fed the inputs of tests/golden/distributed_slab.npz and compared DIRECTLY with what the reference's own sharded
+    cic_paint_dx / pm_forces computed for pdims (P, 1), halo 8 (jaxpm/painting.py:192-215, pm.py:12-58,
+    distributed.py:45-113): the painted density (per-rank ghost-zone arrays folded on the host) and the force on
+    every particle (one kick of unit coefficient from zero velocity)."""
+    from jaxpm_b200.slab import SlabPlan, SlabStepper
+    g = gold("distributed_slab")
+    disp, gx = g["disp"], int(g["halo"])
+    shape = disp.shape[:3]
+    nx, ny, nz = shape
+    lx = nx // P
+    plans = [SlabPlan(shape, P, r, gx, cuda) for r in range(P)]
+    for p in plans:
+        p.attach_local(plans)
+    streams = [torch.cuda.Stream(cuda) for _ in range(P)]
+    dl = [T(disp[r * lx:(r + 1) * lx], cuda) for r in range(P)]
+    vl = [torch.zeros_like(d) for d in dl]
+    torch.cuda.synchronize()
+    st = []
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            st.append(SlabStepper(dl[r], vl[r], gx, P, r, tile=8, margin=1, plan=plans[r]))
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            st[r].step(1.0, 0.0)                     # vel = 0 + 1 * F(disp); no drift
+    G = 4
+    rho = np.zeros(shape, np.float64)
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            st[r].store(dl[r], vl[r])
+            a = N(_padded_density(plans[r], cuda)).astype(np.float64)
+        # local plane xl of the rank's mesh (its slab + gx ghost planes per side) is global plane r lx - gx + xl;
+        # y / z carry G periodic ghost cells per side; the kGhost spare planes around the x range stay empty
+        xs = (r * lx - gx + np.arange(lx + 2 * gx)) % nx
+        ys = (np.arange(ny + 2 * G) - G) % ny
+        zs = (np.arange(nz + 2 * G) - G) % nz
+        assert a[:G].sum() == 0 and a[G + lx + 2 * gx:].sum() == 0
+        np.add.at(rho, (xs[:, None, None], ys[None, :, None], zs[None, None, :]), a[G:G + lx + 2 * gx])
+    torch.cuda.synchronize()
+    assert rel_err(rho, g[f"p{P}1_paint"]) < FIELD_TOL
+    forces = np.concatenate([N(v) for v in vl])
+    assert rel_err(forces, g[f"p{P}1_forces"]) < FIELD_TOL
+    np.testing.assert_array_equal(np.concatenate([N(d) for d in dl]), disp)       # zero drift: positions untouched
+    for s_ in st:
+        s_.close(barrier=False)
+
+
+@pytest.mark.parametrize("fixture,pdims", [("distributed", (2, 2)), ("distributed", (1, 4)), ("distributed", (4, 1)),
+                                           ("distributed", (2, 4)), ("distributed_slab", (2, 1)),
+                                           ("distributed_slab", (4, 1))])
+def test_golden_particle_to_rank_assignment(cuda, fixture, pdims):
+    """uniform_particles(sharding=Sharding(pdims, rank=r)) of the PRODUCT == the block of the reference's sharded
+    uniform_particles (jaxpm/distributed.py:168-190) that rank r owns: bit-exact (integers), every rank."""
+    from jaxpm_b200.distributed import Sharding, get_local_shape, uniform_particles
+    g = gold(fixture)
+    ref = g[f"p{pdims[0]}{pdims[1]}_particles"]
+    shape = ref.shape[:3]
+    for r in range(pdims[0] * pdims[1]):
+        sh = Sharding(pdims, rank=r)
+        loc = get_local_shape(shape, sh)
+        if fixture == "distributed":
+            np.testing.assert_array_equal(loc, g[f"p{pdims[0]}{pdims[1]}_local_shape"])
+        got = N(uniform_particles(shape, sharding=sh, device=cuda))
+        assert got.shape == (*loc, 3)
+        blk = ref[sh.rx * loc[0]:(sh.rx + 1) * loc[0], sh.ry * loc[1]:(sh.ry + 1) * loc[1]]
+        np.testing.assert_array_equal(got.astype(np.int32), blk)
+        np.testing.assert_array_equal(got, blk.astype(np.float32))

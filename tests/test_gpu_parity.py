@@ -218,7 +218,17 @@ def test_lpt(cuda, cfg, absolute, order):
 
 @pytest.mark.parametrize("absolute", [True, False])
 def test_nbody_config1(cuda, absolute):
-    """configs[0]: 64^3 / 64^3, 256 Mpc/h, Planck15, 1LPT at a=0.1 then 10 PM steps to a=1."""
+    """configs[0]: 64^3 / 64^3, 256 Mpc/h, Planck15, 1LPT at a=0.1 then 10 PM steps to a=1.
+
+    Pinned two ways (no outlier allowance):
+    (i) EVERY step on its own: the CUDA path advances the oracle's state n by one drift-kick step and must land on
+        the oracle's state n+1 - positions to fp32 rounding, velocities to the field tolerance, every particle.
+        Both sides then see bit-identical positions at the paint, so the reference's discontinuity at the periodic
+        edge (a coordinate in (-4e-6, 0) loses its corner-0 mass: index N is dropped, painting_utils.py:53-65 +
+        mode='drop') is decided identically and cannot produce outliers.
+    (ii) the free-running 10-step CUDA trajectory against the oracle's: the matter power spectrum within 1e-4
+        (north star); particle positions only statistically - two fp32-equivalent runs legitimately differ by
+        O(1) in one cell whenever a particle crosses 0 within rounding noise, see (i)."""
     from jaxpm_b200.cosmology import Planck15
     from jaxpm_b200.ode import nbody_kick_drift
     from jaxpm_b200.painting import cic_paint, cic_paint_dx
@@ -229,27 +239,39 @@ def test_nbody_config1(cuda, absolute):
     cosmo, ocos = Planck15(), OC.Planck15()
     dx, p, _ = OPM.lpt(ocos, ic, particles=grid if absolute else None, a=0.1, order=1)
     drift, kick = OO.symplectic_ode(shape, ocos, paint_absolute_pos=absolute)
-    rpos, rvel = OO.semi_implicit_euler(drift, kick, grid + dx if absolute else dx, p, 0.1, 1.0, 10)
+    ts = np.linspace(0.1, 1.0, 11)
+    states = [((grid + dx).astype(np.float32) if absolute else dx, p)]
+    for n in range(10):
+        states.append(OO.semi_implicit_euler(drift, kick, *states[-1], ts[n], ts[n + 1], 1))
+    pos_tol = 2e-5 if absolute else 5e-6          # fp32 spacing at |x| ~ 64 is 7.6e-6, at |disp| ~ 8 it is 1e-6
+    for n in range(10):
+        for mode in ("spectral", "potential"):
+            gp_, gv_ = nbody_kick_drift(cosmo, T(states[n][0], cuda), T(states[n][1], cuda), ts[n], ts[n + 1], 1,
+                                        mesh_shape=shape, paint_absolute_pos=absolute, margin=1, force_mode=mode)
+            assert np.abs(gp_.cpu().numpy() - states[n + 1][0]).max() < pos_tol, (n, mode)
+            # the potential path's extra fp32 differencing error is bounded by the AUTO criterion, not by 1e-5, on
+            # the smooth early field of this 4 Mpc/h-cell box (psi / F is large): 5e-5 there, 1e-5 for spectral
+            vtol = FIELD_TOL if mode == "spectral" else 5e-5
+            dv_ref = states[n + 1][1] - states[n][1]
+            dv = gv_.cpu().numpy() - states[n][1]
+            assert np.abs(dv - dv_ref).max() / np.abs(dv_ref).max() < vtol, (n, mode)
+    rpos, rvel = states[-1]
     gdx, gp, _ = lpt(cosmo, T(ic, cuda), particles=T(grid, cuda) if absolute else None, a=0.1, order=1)
     start = (T(grid, cuda) + gdx) if absolute else gdx
-    pos, vel = nbody_kick_drift(cosmo, start.clone(), gp.clone(), 0.1, 1.0, 10, mesh_shape=shape,
-                                paint_absolute_pos=absolute)
-    if absolute:
-        field = cic_paint(torch.zeros(shape, device=cuda), pos).cpu().numpy()
-        rfield = OP.cic_paint(np.zeros(shape, np.float32), rpos)
-    else:
-        field = cic_paint_dx(pos).cpu().numpy()
-        rfield = OP.cic_paint_dx(rpos)
-    # fp32 rounding over 10 steps: positions agree to ~1e-5 cells.  The reference's relative rule is
-    # DISCONTINUOUS at the periodic edge (a particle at -1e-7 loses its corner-0 mass: index n is dropped,
-    # painting_utils.py:53-65 + mode='drop'), so a particle that crosses y = 0 within rounding noise changes the
-    # density by O(1) and shifts its ~100 neighbours by ~1e-2 cells: allow a 1e-3 fraction of such outliers.
-    err = np.abs(pos.cpu().numpy() - rpos).max(-1)
-    assert np.median(err) < 2e-5
-    assert (err > 1e-3).mean() < 1e-3 and err.max() < 0.2
-    _, ps = OU.power_spectrum(field, box_shape=box)
-    _, rps = OU.power_spectrum(rfield, box_shape=box)
-    assert np.abs(ps / rps - 1).max() < 1e-4
+    for mode in ("spectral", "auto"):
+        pos, vel = nbody_kick_drift(cosmo, start.clone(), gp.clone(), 0.1, 1.0, 10, mesh_shape=shape,
+                                    paint_absolute_pos=absolute, margin=1, force_mode=mode)
+        if absolute:
+            field = cic_paint(torch.zeros(shape, device=cuda), pos).cpu().numpy()
+            rfield = OP.cic_paint(np.zeros(shape, np.float32), rpos)
+        else:
+            field = cic_paint_dx(pos).cpu().numpy()
+            rfield = OP.cic_paint_dx(rpos)
+        err = np.abs(pos.cpu().numpy() - rpos).max(-1)
+        assert np.median(err) < 2e-5, mode
+        _, ps = OU.power_spectrum(field, box_shape=box)
+        _, rps = OU.power_spectrum(rfield, box_shape=box)
+        assert np.abs(ps / rps - 1).max() < 1e-4, mode
 
 
 def test_leapfrog_midpoint_and_rhs(cuda):

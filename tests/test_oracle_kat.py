@@ -164,3 +164,25 @@ def test_kdk_integrators_run_and_agree_at_small_dt():
     y = ode.leapfrog_midpoint(ode.make_diffrax_ode((N, N, N)), np.stack([grid + disp, vel]), 0.1, 0.12, 4,
                               cosmo)
     assert np.abs(p1 - y[0]).max() < 5e-3
+
+
+def _fd4(psi, axis):
+    """4th-order central difference of a periodic array."""
+    r = lambda s: np.roll(psi, -s, axis=axis)
+    return (2.0 / 3.0) * (r(1) - r(-1)) - (1.0 / 12.0) * (r(2) - r(-2))
+
+
+def test_gradient_kernel_is_the_fd4_symbol():
+    """The identity the potential force path of csrc/sim.cu rests on: the reference's gradient kernel
+    i (8 sin w - sin 2w) / 6 (kernels.py:62-66) is the Fourier symbol of the 4th-order central difference, so
+    IFFT(-gradient_kernel(d) * pot_k) (pm.py:54-56) == D_d psi with psi = -IFFT(pot_k).  Float64, oracle kernels."""
+    from oracle import kernels as OK
+    shape = (16, 12, 20)
+    x = np.random.default_rng(0).standard_normal(shape)
+    dk = OK.fft3d(x)
+    kvec = OK.fftk(dk)
+    pot = dk * OK.invlaplace_kernel(kvec)
+    psi = -OK.ifft3d(pot)
+    for d in range(3):
+        ref = OK.ifft3d(-OK.gradient_kernel(kvec, d) * pot)
+        assert np.abs(_fd4(psi, d) - ref).max() < 1e-12 * np.abs(ref).max()
