@@ -183,6 +183,12 @@ int32_t jpm_lpt2_shear_c64(jpm_plan* plan, void* stream, const void* delta_k, vo
                            float norm);
 /* delta2 = s00*s11 + s22*(s00+s11) - s01^2 - s02^2 - s12^2 (pm.py:92-109 accumulated form). */
 int32_t jpm_lpt2_source_f32(void* stream, float* delta2, const float* shear6, int64_t ncell);
+/* Reverse mode of the 2LPT source (what jax.grad of jaxpm/pm.py:88-111 transposes to):
+ * t6[q] = cot * d delta2 / d s_q for the 6 shear meshes (00,11,22,01,02,12) ... */
+int32_t jpm_lpt2_source_adj_f32(void* stream, float* t6, const float* shear6, const float* cot, int64_t ncell);
+/* ... and the transpose of jpm_lpt2_shear_c64 (its multipliers a_i a_j / k^2 are real and even, so the operator is
+ * self-adjoint): out = sum_q (a_i a_j)(1/k^2) in6[q] * norm, in6 = the R2C spectra of t6. */
+int32_t jpm_lpt2_shear_adj_c64(jpm_plan* plan, void* stream, const void* in6, void* out, float norm);
 
 /* Generic k-space multiply used by linear_field (pm.py:134-143): out = in * tab(|k| scaled)
  * where kphys^2 = sum_d (w_d * kscale_d)^2 and the table is linear in log10(kphys) on

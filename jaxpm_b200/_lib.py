@@ -39,6 +39,8 @@ SIGNATURES = {
     "jpm_greens_div_c64": ([vp, vp, vp, vp, f32, f32, vp, i32, f32], i32),
     "jpm_lpt2_shear_c64": ([vp, vp, vp, vp, f32], i32),
     "jpm_lpt2_source_f32": ([vp, vp, vp, i64], i32),
+    "jpm_lpt2_source_adj_f32": ([vp, vp, vp, vp, i64], i32),
+    "jpm_lpt2_shear_adj_c64": ([vp, vp, vp, vp, f32], i32),
     "jpm_kfilter_logtab_c64": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),
     "jpm_density_to_force_meshes": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),
     "jpm_density_to_force_meshes_fused": ([vp, vp, vp, vp, f32, vp, i32, f32], i32),

@@ -28,6 +28,8 @@ namespace jpm {
 // KIND 0: force spectra  out_d = i a_d delta / k^2 * G * norm       (3 outputs)
 // KIND 1: shear spectra  out_ij = a_i a_j delta / k^2 * norm        (6 outputs: 00 11 22 01 02 12)
 // KIND 2: transpose of KIND 0 (its VJP): out = sum_d (-i a_d) in_d / k^2 * G * norm   (3 inputs, 1 output)
+// KIND 3: transpose of KIND 1 (the multipliers a_i a_j / k^2 are real and even: self-adjoint):
+//         out = sum_q a_i a_j in_q / k^2 * norm                                      (6 inputs, 1 output)
 // Threads run along z (fastest axis) so loads/stores of the interleaved complex rows coalesce.
 // ---------------------------------------------------------------------------------
 template <int KIND>
@@ -48,7 +50,7 @@ kspace_kernel(const float2* __restrict__ dk, float2* __restrict__ out, const flo
       const float kk = kxy2 + kz * kz;
       float g = (kk == 0.f) ? 0.f : (1.0f / kk);  // -invlaplace = 1/k^2, 0 at k=0
       g *= norm;
-      if (KIND != 1) {
+      if (KIND != 1 && KIND != 3) {
         if (r_split2 != 0.f) g *= expf(-kk * r_split2);
         if (ftab) {
           const float t = sqrtf(kk) * fscale;
@@ -65,6 +67,18 @@ kspace_kernel(const float2* __restrict__ dk, float2* __restrict__ out, const flo
         // (-i a g)(re + i im) = (a g im, -a g re)
         __stcs(out + o, make_float2(g0 * d0.y + g1 * d1.y + g2 * d2.y,
                                     -(g0 * d0.x + g1 * d1.x + g2 * d2.x)));
+        continue;
+      }
+      if (KIND == 3) {
+        const float m[6] = {a0 * a0 * g, a1 * a1 * g, a2 * a2 * g, a0 * a1 * g, a0 * a2 * g, a1 * a2 * g};
+        float2 acc = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) {
+          const float2 v = __ldcs(dk + q * nspec + o);
+          acc.x = fmaf(m[q], v.x, acc.x);
+          acc.y = fmaf(m[q], v.y, acc.y);
+        }
+        __stcs(out + o, acc);
         continue;
       }
       const float2 d = __ldcs(dk + o);
@@ -126,6 +140,23 @@ lpt2_source_kernel(float* __restrict__ d2, const float* __restrict__ s, long lon
   }
 }
 
+
+// VJP of lpt2_source_kernel: t_q = g * d delta2 / d s_q  (6 meshes), pm.py:92-109 differentiated
+__global__ void __launch_bounds__(256)
+lpt2_source_adj_kernel(float* __restrict__ t, const float* __restrict__ s, const float* __restrict__ g, long long n) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float s00 = s[i], s11 = s[n + i], s22 = s[2 * n + i];
+    const float s01 = s[3 * n + i], s02 = s[4 * n + i], s12 = s[5 * n + i];
+    const float gi = g[i];
+    t[i] = gi * (s11 + s22);
+    t[n + i] = gi * (s00 + s22);
+    t[2 * n + i] = gi * (s00 + s11);
+    t[3 * n + i] = -2.0f * gi * s01;
+    t[4 * n + i] = -2.0f * gi * s02;
+    t[5 * n + i] = -2.0f * gi * s12;
+  }
+}
 
 static void build_tables(int n, int nh, std::vector<float>& w, std::vector<float>& a) {
   // fftk: w = 2*pi*fftfreq(n) (kernels.py:10-23, [ext] jaxdecomp.fftfreq3d), stored fp32;
@@ -446,6 +477,7 @@ extern "C" int32_t jpm_plan_destroy(jpm_plan* p) {
   pmfft_destroy(p);
   if (p->density_p) cudaFree(p->density_p);
   if (p->force3_p) cudaFree(p->force3_p);
+  if (p->psi_p) cudaFree(p->psi_p);
   void* bufs[] = {p->work, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->density, p->spec, p->spec3, p->force3};
   for (void* b : bufs)
     if (b) cudaFree(b);
@@ -506,6 +538,27 @@ extern "C" int32_t jpm_lpt2_shear_c64(jpm_plan* p, void* stream, const void* del
   kspace_kernel<1><<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
       (const float2*)delta_k, (float2*)out6, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->nx, p->ny,
       p->nzh, p->nspec, norm, 0.f, nullptr, 0, 0.f);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_lpt2_shear_adj_c64(jpm_plan* p, void* stream, const void* in6, void* out, float norm) {
+  JPM_CHECK_ARG(!(p && p->is_slab), "not available on a multi-GPU slab plan");
+  JPM_CHECK_ARG(p && in6 && out, "null pointer");
+  kspace_kernel<3><<<kspace_grid(p), 256, 0, (cudaStream_t)stream>>>(
+      (const float2*)in6, (float2*)out, p->wx, p->wy, p->wz, p->ax, p->ay, p->az, p->nx, p->ny,
+      p->nzh, p->nspec, norm, 0.f, nullptr, 0, 0.f);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_lpt2_source_adj_f32(void* stream, float* t6, const float* shear6, const float* cot,
+                                           int64_t ncell) {
+  JPM_CHECK_ARG(t6 && shear6 && cot && ncell >= 0, "null pointer");
+  if (ncell == 0) return JPM_OK;
+  long long blocks = (ncell + 255) / 256;
+  if (blocks > kNumSMs * 16) blocks = kNumSMs * 16;
+  lpt2_source_adj_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(t6, shear6, cot, ncell);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }

@@ -33,6 +33,7 @@ struct Slab {
   int nzh, nzc;          // nz / 2 + 1 and its pitch (multiple of 8)
   float* dens[8];        // [nxp][nyp][nzp]       density (painted into, ghosts not folded)
   float* force[8];       // [3][nxp][nyp][nzp]    force meshes, ghosts filled
+  float* psi[8];         // [nxp][nyp][nzp]       potential chain: psi = IFFT(G delta / k^2), ghosts filled
   float2* at[8];         // [nx][ly][nzc]         z,y-transformed density, transposed: all x of the rank's y rows
   float2* b3[8];         // [3][lx][ny][nzc]      y-inverse-transformed spectra of the rank's x planes ([2] doubles as
                          //                       the z-transformed density the forward y pass reads)
@@ -84,6 +85,7 @@ struct jpm_plan {
   long long npad = 0;
   float* density_p = nullptr; // [nxp][nyp][nzp]
   float* force3_p = nullptr;  // [3][nxp][nyp][nzp]
+  float* psi_p = nullptr;     // [nxp][nyp][nzp]  potential chain + gradient pass (allocated on first use; P == 1)
   cufftHandle r2c_p = 0, c2r3_p = 0;
   // ---- pmfft (csrc/pmfft.cu): hand-written fused FFT chain on the padded meshes, power-of-two shapes --
   float2* fft_at = nullptr;   // P == 1: the AT buffer   [nx][ny][nzc]
@@ -121,8 +123,11 @@ bool pmfft_shape_ok(int nx, int ny, int nz);
 int32_t slab_barrier(jpm_plan* p, cudaStream_t stream, bool exchange_ghost_width = false);
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
                      float filter_kmax);
+// to_psi = false: psi lands in force3_p component 0 (read by sim_readpot_kernel); true: in the separate psi mesh,
+// from which pmfft_gradient forms the three force meshes (4th-order differences) in force3_p.
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax);
+                        float filter_kmax, bool to_psi = false);
+int32_t pmfft_gradient(jpm_plan* p, cudaStream_t stream);
 void pmfft_destroy(jpm_plan* p);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).
 // dims/strides innermost first, rank 3 or 4, fp32, no swizzle/interleave, OOB -> zero fill.

@@ -750,7 +750,7 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 template <int NZ>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull,
-            const float* __restrict__ az, int x0, int variant, int ge_extra) {
+            const float* __restrict__ az, int x0, int variant, int ge_extra, int to_psi) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
   float2* tw = sm;            // [NH]
@@ -813,11 +813,12 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   run_stages<NH, kRows, NT, true, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
   // destinations in x: own interior plane, left neighbour's high ghost, right neighbour's low ghost
   const long long cofs = (long long)comp * sl.npad;
-  float* dstp[3] = {sl.force[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
+  float* const* const dmesh = to_psi ? sl.psi : sl.force;      // potential chain: the psi mesh (one component)
+  float* dstp[3] = {dmesh[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
   // ge_extra: the potential chain's mesh is differentiated by a +-2 stencil after the read box is staged
   const int ge = min(gx, ghost_width(sl) + ge_extra);
-  if (xl < ge) dstp[1] = sl.force[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
-  if (xl >= lx - ge) dstp[2] = sl.force[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
+  if (xl < ge) dstp[1] = dmesh[(sl.rank + sl.P - 1) % sl.P] + cofs + (long long)(gx + lx + xl) * nyp * nzp;
+  if (xl >= lx - ge) dstp[2] = dmesh[(sl.rank + 1) % sl.P] + cofs + (long long)(xl - (lx - gx)) * nyp * nzp;
   const int GH = G / 2;
   if ((variant & 1) && !dstp[1] && !dstp[2] && y0 >= G && y0 + kRows <= ny - G) {
     // block without x / y images to write: straight-line, 8 shared-memory loads in flight, then 8 row stores
@@ -860,6 +861,57 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
       }
     }
   }
+}
+
+
+// ---- gradient pass of the potential chain -----------------------------------------------------------------
+// F_d = D_d psi with the 4th-order central difference the reference's gradient kernel is the symbol of
+// (kernels.py:62-66; see X-pot above): psi mesh (ghosts filled) -> the three force meshes INCLUDING their ghost
+// cells, so that the tile boxes of the read kernel never wrap.  One thread per 4 consecutive z cells; neighbours
+// in y and z are periodic images inside the padded array (index -/+ n), in x too when P == 1; the x planes of a
+// slab beyond what the neighbours filled hold nothing a particle within the halo reach reads.
+// HBM: 4 B/cell read + 12 B/cell written; the +-2 planes / rows are L2 / L1 hits.
+__global__ void __launch_bounds__(256)
+fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi) {
+  const int nzp = sl.nzp, nyp = sl.nyp, nz4 = nzp / 4;
+  const int z4 = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int yp = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const int xp = x_lo + blockIdx.z;
+  if (z4 >= nz4 || yp >= nyp) return;
+  const float* __restrict__ ps = sl.psi[sl.rank];
+  const long long sx = (long long)nyp * nzp;
+  const int nxl = sl.lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
+  auto wrapy = [&](int j) { return j < 0 ? j + sl.ny : (j >= nyp ? j - sl.ny : j); };
+  auto wrapx = [&](int i) {
+    if (sl.P == 1) return i < 0 ? i + sl.nx : (i >= nxl ? i - sl.nx : i);
+    return min(max(i, 0), nxl - 1);
+  };
+  const float* row = ps + (long long)xp * sx + (long long)yp * nzp;
+  const float4 c = *reinterpret_cast<const float4*>(row + 4 * z4);
+  // z neighbours: the float4 below / above (periodic images inside the padded row)
+  const int zl = z4 > 0 ? z4 - 1 : z4 - 1 + sl.nz / 4, zh = z4 + 1 < nz4 ? z4 + 1 : z4 + 1 - sl.nz / 4;
+  const float4 a = *reinterpret_cast<const float4*>(row + 4 * zl);
+  const float4 b = *reinterpret_cast<const float4*>(row + 4 * zh);
+  constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
+  float4 fz;
+  fz.x = c8 * (c.y - a.w) - c1 * (c.z - a.z);
+  fz.y = c8 * (c.z - c.x) - c1 * (c.w - a.w);
+  fz.z = c8 * (c.w - c.y) - c1 * (b.x - c.x);
+  fz.w = c8 * (b.x - c.z) - c1 * (b.y - c.y);
+  auto ld = [&](int i, int j) {
+    return *reinterpret_cast<const float4*>(ps + (long long)i * sx + (long long)j * nzp + 4 * z4);
+  };
+  const float4 y1 = ld(xp, wrapy(yp + 1)), y_1 = ld(xp, wrapy(yp - 1)), y2 = ld(xp, wrapy(yp + 2)), y_2 = ld(xp, wrapy(yp - 2));
+  const float4 x1 = ld(wrapx(xp + 1), yp), x_1 = ld(wrapx(xp - 1), yp), x2 = ld(wrapx(xp + 2), yp), x_2 = ld(wrapx(xp - 2), yp);
+  float4 fx, fy;
+  fx.x = c8 * (x1.x - x_1.x) - c1 * (x2.x - x_2.x); fx.y = c8 * (x1.y - x_1.y) - c1 * (x2.y - x_2.y);
+  fx.z = c8 * (x1.z - x_1.z) - c1 * (x2.z - x_2.z); fx.w = c8 * (x1.w - x_1.w) - c1 * (x2.w - x_2.w);
+  fy.x = c8 * (y1.x - y_1.x) - c1 * (y2.x - y_2.x); fy.y = c8 * (y1.y - y_1.y) - c1 * (y2.y - y_2.y);
+  fy.z = c8 * (y1.z - y_1.z) - c1 * (y2.z - y_2.z); fy.w = c8 * (y1.w - y_1.w) - c1 * (y2.w - y_2.w);
+  float* out = sl.force[sl.rank] + (long long)xp * sx + (long long)yp * nzp + 4 * z4;
+  __stcs(reinterpret_cast<float4*>(out), fx);
+  __stcs(reinterpret_cast<float4*>(out + sl.npad), fy);
+  __stcs(reinterpret_cast<float4*>(out + 2 * sl.npad), fz);
 }
 
 // ---- inter-GPU barrier over peer-mapped flags ------------------------------------------------------------
@@ -1217,7 +1269,7 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
     if (p->timer && !chunked) p->timer->mark(st, "ifft_y_x3");
 #define RUN_ZI(N_)                                                                                             \
   zinv_kernel<N_><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
-      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0);
+      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0, 0);
     JPM_FFT_SWITCH(sl.nz, RUN_ZI)
 #undef RUN_ZI
     JPM_LAUNCH_CHECK();
@@ -1231,9 +1283,15 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
 // (+2 planes for the read kernel's difference stencil).  Same passes / barriers as pmfft_forces with ONE
 // spectrum through the inverse half: 8 + 8 + 8 + 8 + 8 = 40 B/cell instead of 72.
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax) {
+                        float filter_kmax, bool to_psi) {
   using namespace fft;
   JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
+  if (to_psi && !p->slab.psi[p->slab.rank]) {
+    JPM_CHECK_ARG(p->slab.P == 1, "slab plan without a psi mesh");
+    JPM_CUDA(cudaMalloc(&p->psi_p, p->npad * sizeof(float)));
+    JPM_CUDA(cudaMemsetAsync(p->psi_p, 0, p->npad * sizeof(float), st));
+    p->slab.psi[0] = p->psi_p;
+  }
   const Slab& sl = p->slab;
   const int nzh = sl.nzh;
   const float norm = 1.0f / ((float)sl.nx * (float)sl.ny * (float)sl.nz);
@@ -1286,12 +1344,23 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   if (p->timer) p->timer->mark(st, "ifft_y");
 #define RUN_ZP(N_)                                                                                             \
   zinv_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
-      sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2);
+      sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2, to_psi ? 1 : 0);
   JPM_FFT_SWITCH(sl.nz, RUN_ZP)
 #undef RUN_ZP
   JPM_LAUNCH_CHECK();
   if ((rc = slab_barrier(p, st))) return rc;
   if (p->timer) p->timer->mark(st, "ifft_z_c2r+ghost_fill");
+  return JPM_OK;
+}
+
+// psi mesh (ghosts filled by pmfft_potential(to_psi)) -> force3_p, ghost cells included.
+int32_t pmfft_gradient(jpm_plan* p, cudaStream_t st) {
+  const Slab& sl = p->slab;
+  JPM_CHECK_ARG(sl.psi[sl.rank], "no psi mesh (run pmfft_potential(to_psi) first)");
+  const int nxl = sl.lx + 2 * sl.gx;
+  fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, nxl), 256, 0, st>>>(sl, 0, nxl);
+  JPM_LAUNCH_CHECK();
+  if (p->timer) p->timer->mark(st, "fd_gradient");
   return JPM_OK;
 }
 

@@ -65,15 +65,24 @@ struct jpm_sim {
   bool pos_only = false;               // JPM_SIM_POSITIONS_ONLY: no velocities, no second ordering (paint / forces only)
   // ---- potential ("FD") force path: psi mesh + real-space 4th-order differences (sim_readpot_kernel) ----
   CUtensorMap tm_psi;                  // (PB, PB, BZ) boxes of force3_p component 0
-  bool pot_ok = false;                 // TMA path, margin 1, one GPU or slab plan with the fused chain
+  bool pot_ok = false;                 // potential chain available: TMA tile path + fused FFT chain (power-of-two mesh)
+  bool potfused_ok = false;            // ... and its fused read kernel (margin 1: psi box = force box + 2 cells)
+  int pot_variant = 0;                 // 0: gradient pass (pmfft_gradient) + sim_read_kernel; 1: sim_readpot_kernel
   int force_mode = 0;                  // JPM_FORCE_SPECTRAL / JPM_FORCE_POTENTIAL / JPM_FORCE_AUTO
   int cur_mode = 0;                    // what the next step runs (auto switches it from the measured error bound)
   int pot_grid = 0;                    // persistent CTAs of sim_readpot_kernel
   int pot_threads = 1024;              // threads per CTA of it (JPM_POT_THREADS=768: more registers per thread)
+  int read_persist = 0;                // JPM_READ_PERSIST=768|1024: three-mesh read as the persistent double-buffered kernel
+  int persist_grid = 0;
   int* tile_counter = nullptr;
-  double* stats_host = nullptr;        // pinned copy of plan->pot_stats of the last finished step
-  cudaEvent_t stats_ev = nullptr;
-  bool stats_pending = false;
+  // AUTO: the statistics of step n (device doubles, plan->pot_stats) are copied to pinned slot n % 3 behind the step;
+  // the mode of step n is decided from the slot of step n - 2 after waiting for ITS event - a fixed lag, so the
+  // sequence of modes does not depend on how far the host runs ahead of the device (reproducible runs, and the
+  // same decision on every rank of a multi-GPU run)
+  double* stats_host = nullptr;        // pinned [3][4]
+  cudaEvent_t stats_ev[3] = {nullptr, nullptr, nullptr};
+  bool stats_pending[3] = {false, false, false};
+  long long nstep = 0;
   double last_bound = -1.0;            // last evaluated error bound (auto), < 0 = none yet
   long long mode_steps[2] = {0, 0};    // steps run in spectral / potential mode
 };
@@ -891,6 +900,9 @@ template <int TS, int M> struct PotGeom {
   static constexpr int ZLO = kTmaMz - M, ZHI = kTmaMz + T + M;    // force cells [ZLO, ZHI] are gathered from
   static_assert(ZLO - 2 >= 0 && ZHI + 2 < BZ, "the psi box must cover the +-2 stencil in z");
   static constexpr int smem_bytes = (2 * NPSI_PAD + 3 * NBOX) * (int)sizeof(float);
+  // persistent flavour of the three-mesh read: two (3, B, B, BZ) force boxes, no psi
+  static constexpr int NF3_PAD = (3 * NBOX + 31) & ~31;
+  static constexpr int smem_bytes_f3 = 2 * NF3_PAD * (int)sizeof(float);
 };
 
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
@@ -908,7 +920,7 @@ __device__ __forceinline__ float fd4_global(const float* __restrict__ psi, long 
   return (2.0f / 3.0f) * d1 - (1.0f / 12.0f) * d2;
 }
 
-template <bool REL, int TS, int M, int NT>
+template <bool REL, int TS, int M, int NT, bool POT = true>
 __global__ void __launch_bounds__(NT, 1)
 sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
                    const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ psi,
@@ -918,8 +930,8 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
   using PG = PotGeom<TS, M>;
   constexpr int B = PG::B, PB = PG::PB, BZ = PG::BZ, NBOX = PG::NBOX;
   extern __shared__ __align__(128) float smem[];
-  float* const psib[2] = {smem, smem + PG::NPSI_PAD};
-  float* const box = smem + 2 * PG::NPSI_PAD;            // [3][B][B][BZ]
+  // POT: psi[2] | F[3][B][B][BZ] (built from psi);  !POT: F[2][3][B][B][BZ] loaded by TMA (psi = the three force meshes)
+  const float* box = smem + 2 * PG::NPSI_PAD;
   __shared__ __align__(8) unsigned long long mbar[2];
   __shared__ int s_tile[2];
   const int lane = threadIdx.x & 31;
@@ -935,9 +947,15 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
     s_tile[buf] = t;
     if (t < g.nt) {
       const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-      mbar_expect_tx(&mbar[buf], (unsigned)(PG::NPSI * sizeof(float)));
-      tma_load_3d(smem + buf * PG::NPSI_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M - 2 + g.mo, (tx << TS) - M - 2 + g.mox,
-                  &mbar[buf]);
+      if (POT) {
+        mbar_expect_tx(&mbar[buf], (unsigned)(PG::NPSI * sizeof(float)));
+        tma_load_3d(smem + buf * PG::NPSI_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M - 2 + g.mo,
+                    (tx << TS) - M - 2 + g.mox, &mbar[buf]);
+      } else {
+        mbar_expect_tx(&mbar[buf], 3u * NBOX * (unsigned)sizeof(float));
+        tma_load_4d(smem + buf * PG::NF3_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M + g.mo,
+                    (tx << TS) - M + g.mox, 0, &mbar[buf]);
+      }
     }
   };
   if (threadIdx.x == 0) {
@@ -965,9 +983,16 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
     }
     if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
     else { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
+    if (!POT) {
+      // the boxes of this tile have landed; the other buffer was last read before the barrier that ended the
+      // previous tile, so the next tile's boxes can be requested right away
+      box = smem + buf * PG::NF3_PAD;
+      if (threadIdx.x == 0) grab_and_load(buf ^ 1);
+    }
     // F_d = D_d psi on the cells the gathers can touch: x, y in [0, B), z in [ZLO, ZHI]
-    {
-      const float* const ps = psib[buf];
+    if (POT) {
+      float* const fbox = smem + 2 * PG::NPSI_PAD;
+      const float* const ps = smem + buf * PG::NPSI_PAD;
       constexpr int NZ = PG::ZHI - PG::ZLO + 1, NCELL = B * B * NZ;
       constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
       for (int i = threadIdx.x; i < NCELL; i += blockDim.x) {
@@ -977,12 +1002,12 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
         const float fx = c8 * (c[PB * BZ] - c[-PB * BZ]) - c1 * (c[2 * PB * BZ] - c[-2 * PB * BZ]);
         const float fy = c8 * (c[BZ] - c[-BZ]) - c1 * (c[2 * BZ] - c[-2 * BZ]);
         const float fz = c8 * (c[1] - c[-1]) - c1 * (c[2] - c[-2]);
-        float* o = box + (lx * B + ly) * BZ + lz;
+        float* o = fbox + (lx * B + ly) * BZ + lz;
         o[0] = fx; o[NBOX] = fy; o[2 * NBOX] = fz;
       }
+      __syncthreads();      // force boxes complete; the other psi buffer was consumed one tile ago
+      if (threadIdx.x == 0) grab_and_load(buf ^ 1);
     }
-    __syncthreads();      // force boxes complete; the other psi buffer was consumed one tile ago
-    if (threadIdx.x == 0) grab_and_load(buf ^ 1);
     for (int qb = beg; qb < end; qb += blockDim.x) {
       const bool valid = q < end;
       const int qn = q + blockDim.x;
@@ -1008,8 +1033,8 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
       FastStencil s;
       if (valid) {
         fast = stencil_box<REL, B, B, BZ>(g, p, ox, oy, oz, s, lx, ly, lz);
-        // the z extent of the force boxes that holds values is [ZLO, ZHI]
-        fast = fast && lz >= PG::ZLO && lz < PG::ZHI;
+        // POT: the z extent of the force boxes that holds values is [ZLO, ZHI]
+        if (POT) fast = fast && lz >= PG::ZLO && lz < PG::ZHI;
         if (fast) {
           tt = ((s.i0 >> TS) * g.nty + (s.j0 >> TS)) * g.ntz + (s.k0 >> TS);
         } else {
@@ -1047,8 +1072,10 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
           sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
           Corners c;
           make_corners<B, BZ>(g, cx, cy, cz, ox, oy, oz, c);
+          if (POT) {
 #pragma unroll
-          for (int a = 0; a < 2; ++a) c.inside = c.inside && c.lz[a] >= PG::ZLO && c.lz[a] <= PG::ZHI;
+            for (int a = 0; a < 2; ++a) c.inside = c.inside && c.lz[a] >= PG::ZLO && c.lz[a] <= PG::ZHI;
+          }
 #pragma unroll
           for (int cc = 0; cc < 8; ++cc) {
             const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
@@ -1060,9 +1087,14 @@ sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const floa
               for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
             } else {
               const long long o = mesh_index(g, c.ix[a], c.iy[b], c.iz[d]);
-              acc[0] = fmaf(fd4_global(psi, o, g.msx), k, acc[0]);
-              acc[1] = fmaf(fd4_global(psi, o, g.msy), k, acc[1]);
-              acc[2] = fmaf(fd4_global(psi, o, 1), k, acc[2]);
+              if (POT) {
+                acc[0] = fmaf(fd4_global(psi, o, g.msx), k, acc[0]);
+                acc[1] = fmaf(fd4_global(psi, o, g.msy), k, acc[1]);
+                acc[2] = fmaf(fd4_global(psi, o, 1), k, acc[2]);
+              } else {
+#pragma unroll
+                for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(psi + f * g.mb + o), k, acc[f]);
+              }
             }
           }
           if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
@@ -1260,14 +1292,38 @@ extern "C" int32_t jpm_sim_create_ex(jpm_sim** out, jpm_plan* plan, int32_t nx, 
         JPM_CUDA(cudaGetDevice(&dev));
         JPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
         s->pot_grid = std::max(1, occ) * sms;
-        s->pot_ok = occ > 0;
+        s->potfused_ok = occ > 0;
       }
+      if (m == 1 && ts == 4) {
+        if (const char* e = getenv("JPM_READ_PERSIST")) s->read_persist = atoi(e) == 768 ? 768 : (atoi(e) == 1024 ? 1024 : 0);
+        if (s->read_persist) {
+          int occ = 0, dev = 0, sms = kNumSMs;
+#define PERSIST_ATTR(NT_)                                                                                   \
+  {                                                                                                         \
+    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<false, 4, 1, NT_, false>,                              \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PotGeom<4, 1>::smem_bytes_f3)); \
+    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<true, 4, 1, NT_, false>,                               \
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PotGeom<4, 1>::smem_bytes_f3)); \
+    JPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sim_readpot_kernel<true, 4, 1, NT_, false>, NT_, \
+                                                           PotGeom<4, 1>::smem_bytes_f3));                  \
+  }
+          if (s->read_persist == 768) PERSIST_ATTR(768) else PERSIST_ATTR(1024)
+#undef PERSIST_ATTR
+          JPM_CUDA(cudaGetDevice(&dev));
+          JPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+          s->persist_grid = std::max(1, occ) * sms;
+          if (occ < 1) s->read_persist = 0;
+        }
+      }
+      s->pot_ok = plan->fft_on && !plan->is_slab;
+      if (const char* e = getenv("JPM_POT_VARIANT")) s->pot_variant = atoi(e);
+      if (s->pot_variant == 1 && !s->potfused_ok) s->pot_variant = 0;
     }
   }
   JPM_CUDA(cudaMalloc(&s->tile_counter, sizeof(int)));
   JPM_CUDA(cudaMemset(s->tile_counter, 0, sizeof(int)));
-  JPM_CUDA(cudaMallocHost(&s->stats_host, 4 * sizeof(double)));
-  JPM_CUDA(cudaEventCreateWithFlags(&s->stats_ev, cudaEventDisableTiming));
+  JPM_CUDA(cudaMallocHost(&s->stats_host, 3 * 4 * sizeof(double)));
+  for (int i = 0; i < 3; ++i) JPM_CUDA(cudaEventCreateWithFlags(&s->stats_ev[i], cudaEventDisableTiming));
   if (const char* e = getenv("JPM_FORCE_MODE")) {   // default force path of new sims (tests / A-B runs)
     s->force_mode = atoi(e);
     s->cur_mode = s->force_mode == 1 ? 1 : 0;
@@ -1298,7 +1354,8 @@ extern "C" int32_t jpm_sim_destroy(jpm_sim* s) {
   if (s->stats) cudaFree(s->stats);
   if (s->tile_counter) cudaFree(s->tile_counter);
   if (s->stats_host) cudaFreeHost(s->stats_host);
-  if (s->stats_ev) cudaEventDestroy(s->stats_ev);
+  for (int i = 0; i < 3; ++i)
+    if (s->stats_ev[i]) cudaEventDestroy(s->stats_ev[i]);
   delete s;
   return JPM_OK;
 }
@@ -1387,6 +1444,24 @@ static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const
   const bool want_fmax = tma && s->force_mode == 2 && s->plan && s->plan->pot_stats;
   unsigned* fmax_bits = want_fmax ? reinterpret_cast<unsigned*>(s->plan->pot_stats + 1) : nullptr;
   static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
+  if (tma && s->read_persist) {
+    // persistent flavour: one CTA per SM, tiles from an atomic counter, the next tile's boxes in flight
+    const int grid = std::min(s->persist_grid, g.nt);
+#define LAUNCH_PERSIST(REL_, NT_)                                                                          \
+  sim_readpot_kernel<REL_, 4, 1, NT_, false><<<grid, NT_, PotGeom<4, 1>::smem_bytes_f3, st>>>(             \
+      s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, kick_coef, drift_coef, s->np,     \
+      s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead)
+    if (s->read_persist == 768) {
+      if (s->relative) LAUNCH_PERSIST(true, 768); else LAUNCH_PERSIST(false, 768);
+    } else {
+      if (s->relative) LAUNCH_PERSIST(true, 1024); else LAUNCH_PERSIST(false, 1024);
+    }
+#undef LAUNCH_PERSIST
+    JPM_LAUNCH_CHECK();
+    s->cur = nxt;
+    s->painted = false;
+    return JPM_OK;
+  }
 #define LAUNCH_READ_T(TS_, M_, TMA_)                                                                     \
   if (TMA_ && want_fmax) {                                                                               \
     if (s->relative)                                                                                     \
@@ -1459,12 +1534,19 @@ static int32_t sim_readpot_impl(jpm_sim* s, cudaStream_t st, float kick_coef, fl
 // kPotSwitchDown (hysteresis), so every step stays inside BASELINE.json's 1e-5 force tolerance.
 constexpr double kPotErrCoef = 2.7e-6, kPotSwitchDown = 4.0e-6, kPotSwitchUp = 6.0e-6;
 
-static void sim_poll_stats(jpm_sim* s) {
-  if (!s->stats_pending || cudaEventQuery(s->stats_ev) != cudaSuccess) return;
-  s->stats_pending = false;
-  const double sumsq = s->stats_host[0];
+constexpr int kStatsLag = 2;
+
+// evaluate the statistics of step `step` (waits for that step to finish on the device)
+static void sim_eval_stats(jpm_sim* s, long long step) {
+  if (step < 0) return;
+  const int i = (int)(step % 3);
+  if (!s->stats_pending[i]) return;
+  if (cudaEventSynchronize(s->stats_ev[i]) != cudaSuccess) return;
+  s->stats_pending[i] = false;
+  const double* h = s->stats_host + 4 * i;
+  const double sumsq = h[0];
   unsigned long long bits;
-  memcpy(&bits, &s->stats_host[1], sizeof(bits));
+  memcpy(&bits, &h[1], sizeof(bits));
   const unsigned fb = (unsigned)(bits & 0xffffffffull);
   float fmax;
   memcpy(&fmax, &fb, sizeof(fmax));
@@ -1480,7 +1562,7 @@ extern "C" int32_t jpm_sim_set_force_mode(jpm_sim* s, int32_t mode) {
   JPM_CHECK_ARG(s, "null sim");
   JPM_CHECK_ARG(mode >= 0 && mode <= 2, "force mode must be 0 (spectral), 1 (potential) or 2 (auto)");
   JPM_CHECK_ARG(mode == 0 || s->pot_ok,
-                "potential force path needs the TMA tile path with margin 1 on a power-of-two mesh (fused FFT chain)");
+                "potential force path needs the TMA tile path on a power-of-two mesh (fused FFT chain), one GPU");
   s->force_mode = mode;
   s->cur_mode = mode == 1 ? 1 : 0;
   return JPM_OK;
@@ -1489,7 +1571,7 @@ extern "C" int32_t jpm_sim_set_force_mode(jpm_sim* s, int32_t mode) {
 extern "C" int32_t jpm_sim_force_info(jpm_sim* s, void* stream, double* out6_host) {
   JPM_CHECK_ARG(s && out6_host, "null pointer");
   JPM_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-  sim_poll_stats(s);
+  for (long long n = s->nstep - 3; n < s->nstep; ++n) sim_eval_stats(s, n);     // in step order
   out6_host[0] = (double)s->force_mode;
   out6_host[1] = (double)s->cur_mode;
   out6_host[2] = s->last_bound;
@@ -1561,19 +1643,27 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
     if ((rc = sim_paint_impl(s, st, p->density_p, true))) return rc;
     if (tm) tm->mark(st, "sim_paint");
     if (s->force_mode != 0 && !s->pot_ok) {
-      set_error("potential force path not available for this sim (needs margin 1 and the fused FFT chain)");
+      set_error("potential force path not available for this sim (needs the TMA tile path and the fused FFT chain)");
       return JPM_ERR_INVALID;
     }
-    if (s->force_mode == 2) sim_poll_stats(s);
+    if (s->force_mode == 2) sim_eval_stats(s, s->nstep - kStatsLag);
     const bool want_stats = s->force_mode == 2;
     if (want_stats && !p->pot_stats) {
       JPM_CUDA(cudaMalloc(&p->pot_stats, 4 * sizeof(double)));
     }
-    if (s->force_mode != 0 && s->cur_mode == 1) {
+    if (s->force_mode != 0 && s->cur_mode == 1 && s->pot_variant == 1) {
       // potential chain: ONE inverse transform, forces differentiated in the read kernel
       if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f))) return rc;
       rc = sim_readpot_impl(s, st, kick_coef, drift_coef);
       if (tm) tm->mark(st, "tile_scan+sim_readpot_kick_drift");
+      ++s->mode_steps[1];
+    } else if (s->force_mode != 0 && s->cur_mode == 1) {
+      // potential chain: ONE inverse transform, then one real-space pass psi -> three force meshes
+      if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f, true))) return rc;
+      if ((rc = pmfft_gradient(p, st))) return rc;
+      rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
+                         drift_coef, true);
+      if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
       ++s->mode_steps[1];
     } else {
       if (want_stats) JPM_CUDA(cudaMemsetAsync(p->pot_stats, 0, 4 * sizeof(double), st));
@@ -1585,11 +1675,13 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
       if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
       ++s->mode_steps[0];
     }
-    if (rc == JPM_OK && want_stats && !s->stats_pending) {
-      JPM_CUDA(cudaMemcpyAsync(s->stats_host, p->pot_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      JPM_CUDA(cudaEventRecord(s->stats_ev, st));
-      s->stats_pending = true;
+    if (rc == JPM_OK && want_stats) {
+      const int i = (int)(s->nstep % 3);
+      JPM_CUDA(cudaMemcpyAsync(s->stats_host + 4 * i, p->pot_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      JPM_CUDA(cudaEventRecord(s->stats_ev[i], st));
+      s->stats_pending[i] = true;
     }
+    ++s->nstep;
     return rc;
   }
   JPM_CHECK_ARG(!p->is_slab, "slab plan: the tile/margin pair must be one the TMA path supports");

@@ -258,8 +258,8 @@ def potential_from_density_fused(density, plan, r_split=0.0, filter_tab=None):
     return out
 
 
-def lpt2_source(delta_k, plan):
-    """delta2 of jaxpm/pm.py:88-109 from the first-order spectrum."""
+def lpt2_source(delta_k, plan, return_shear=False):
+    """delta2 of jaxpm/pm.py:88-109 from the first-order spectrum (optionally also the 6 shear meshes)."""
     sh = torch.empty((6, *plan.spec_shape), dtype=torch.complex64, device=delta_k.device)
     call("jpm_lpt2_shear_c64", plan.handle, stream(), ptr(delta_k, torch.complex64), ptr(sh),
          1.0 / plan.ncell)
@@ -268,7 +268,21 @@ def lpt2_source(delta_k, plan):
         call("jpm_ifft3d_c2r", plan.handle, stream(), ptr(sh[3 * b:3 * b + 3]), ptr(s6[3 * b:3 * b + 3]), 3)
     out = torch.empty(plan.shape, dtype=torch.float32, device=delta_k.device)
     call("jpm_lpt2_source_f32", stream(), ptr(out), ptr(s6), plan.ncell)
-    return out
+    return (out, s6) if return_shear else out
+
+
+def lpt2_source_vjp(s6, cot, plan):
+    """Reverse mode of lpt2_source with respect to the linear field: sum_q L_q(cot * d delta2 / d s_q) with the
+    self-adjoint shear operators L_q = C2R diag(a_i a_j / k^2 / Nc) R2C."""
+    cot = as_f32(cot)
+    t6 = torch.empty_like(s6)
+    call("jpm_lpt2_source_adj_f32", stream(), ptr(t6), ptr(s6), ptr(cot), plan.ncell)
+    tk = torch.empty((6, *plan.spec_shape), dtype=torch.complex64, device=cot.device)
+    for q in range(6):
+        call("jpm_fft3d_r2c", plan.handle, stream(), ptr(t6[q]), ptr(tk[q]))
+    acc = torch.empty(plan.spec_shape, dtype=torch.complex64, device=cot.device)
+    call("jpm_lpt2_shear_adj_c64", plan.handle, stream(), ptr(tk), ptr(acc), 1.0 / plan.ncell)
+    return irfft3_(acc, plan, 1)
 
 
 def kfilter_logtab(spec, plan, tab, log10_kmin, log10_kmax, kscale, norm=1.0):

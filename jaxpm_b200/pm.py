@@ -198,12 +198,18 @@ class _Lpt2Source(torch.autograd.Function):
     @staticmethod
     def forward(ctx, ic, plan):
         dk = ops.rfft3(ic, plan)
-        return ops.lpt2_source(dk, plan)
+        if not ctx.needs_input_grad[0]:
+            return ops.lpt2_source(dk, plan)
+        delta2, s6 = ops.lpt2_source(dk, plan, return_shear=True)
+        ctx.save_for_backward(s6)
+        ctx.plan = plan
+        return delta2
 
     @staticmethod
     def backward(ctx, g):
-        raise NotImplementedError("reverse mode through the 2LPT source is not implemented yet "
-                                  "(use order=1 for gradient runs)")
+        # delta2 = s00 s11 + s22 (s00 + s11) - s01^2 - s02^2 - s12^2 with s_q = L_q(ic), L_q self-adjoint
+        (s6,) = ctx.saved_tensors
+        return ops.lpt2_source_vjp(s6, g.contiguous(), ctx.plan), None
 
 
 def linear_field(mesh_shape, box_size, pk, seed, sharding=None, white_noise=None, device="cuda"):

@@ -54,13 +54,17 @@ def test_potential_chain(cuda, shape):
             assert rel_err(fd4(psi.astype(np.float64), d), fref) < 10 * tol, (d, r_split)
 
 
+@pytest.mark.parametrize("variant", ["pass", "fused"])
 @pytest.mark.parametrize("relative", [False, True])
 @pytest.mark.parametrize("shape,tile", [((32, 32, 32), 8), ((32, 64, 32), 16), ((64, 64, 64), 16)])
-def test_sim_step_potential(cuda, relative, shape, tile):
+def test_sim_step_potential(cuda, monkeypatch, relative, shape, tile, variant):
     """K resident steps with the potential force path == spectral path == oracle, including particles at the
-    periodic edges (generic stencil inside the box) and beyond the margin (forces differentiated from global memory)."""
+    periodic edges (generic stencil inside the box) and beyond the margin (global-memory fallback).
+    variant "pass": one real-space pass psi -> three force meshes, then the ordinary read kernel;
+    variant "fused": the persistent read kernel differentiates the psi box of each tile in shared memory."""
     from jaxpm_b200.cosmology import Planck15
     from jaxpm_b200.ode import nbody_kick_drift
+    monkeypatch.setenv("JPM_POT_VARIANT", "1" if variant == "fused" else "0")
     grid, disp = displaced(shape, 1.0)
     x = disp if relative else grid + disp
     vel = (0.3 * np.random.default_rng(9).standard_normal(x.shape)).astype(np.float32)
@@ -105,12 +109,24 @@ def test_force_mode_auto_follows_the_error_bound(cuda):
     assert out["rough"]["steps_potential"] >= 2 and 0 < out["rough"]["error_bound"] < 4e-6, out["rough"]
 
 
-def test_potential_mode_needs_margin_one(cuda):
+def test_potential_mode_availability(cuda):
+    """Margin 2 runs the potential chain through the gradient pass; a mesh the fused FFT chain does not serve
+    (not a power of two) refuses the mode loudly instead of silently falling back."""
     from jaxpm_b200 import ops
     from jaxpm_b200._lib import JpmError
-    sim = ops.Sim((32, 32, 32), (32, 32, 32), True, cuda, tile=8, margin=2)
-    with pytest.raises(JpmError):
-        sim.set_force_mode("potential")
+    shape = (32, 32, 32)
+    _, disp = displaced(shape, 1.0)
+    vel = np.zeros_like(disp)
+    out = {}
+    for mode in ("spectral", "potential"):
+        sim = ops.Sim(shape, shape, True, cuda, tile=8, margin=2)
+        sim.set_force_mode(mode)
+        sim.load(T(disp, cuda), T(vel, cuda))
+        sim.step(1.0, 0.0)
+        p, v = torch.empty(disp.shape, device=cuda), torch.empty(disp.shape, device=cuda)
+        sim.store(p, v)
+        out[mode] = v.cpu().numpy()
+    assert rel_err(out["potential"], out["spectral"]) < FIELD_TOL
     sim24 = ops.Sim((24, 40, 20), (24, 40, 20), True, cuda, tile=8, margin=1)     # not a power-of-two mesh
     with pytest.raises(JpmError):
         sim24.set_force_mode("auto")
