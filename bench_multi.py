@@ -21,6 +21,11 @@ def run_multi(args, world, rank, dev):
 
     N = args.size
     pdims = (world, 1)
+    if getattr(args, "pdims", None):
+        pdims = tuple(int(v) for v in args.pdims.lower().split("x"))
+        assert pdims[0] * pdims[1] == world, f"--pdims {args.pdims} needs {pdims[0] * pdims[1]} ranks"
+        if pdims[1] > 1:
+            args.nccl = True            # pencils: NCCL halo exchange + all-to-all transposes (halo.py, pfft.py)
     sh = Sharding(pdims)
     h = args.halo
     shape = (N, N, N)
@@ -30,7 +35,7 @@ def run_multi(args, world, rank, dev):
 
     # identical ICs on every rank (generated redundantly, untimed), then keep the local block
     ic = linear_field(shape, (float(N),) * 3, lambda k: linear_matter_power(cosmo, k), seed=0, device=dev)
-    dx, p, _ = lpt(cosmo, ic, a=0.1, order=1)
+    dx, p, _ = lpt(cosmo, ic, a=0.1, order=args.lpt_order)
     blk = lambda a: a[sh.rx * lx:(sh.rx + 1) * lx, sh.ry * ly:(sh.ry + 1) * ly].contiguous()
     disp, vel = blk(dx), blk(p)
     del ic, dx, p
@@ -38,8 +43,9 @@ def run_multi(args, world, rank, dev):
     torch.cuda.empty_cache()
     n_pre, d, k = schedule(cosmo, args, kick_drift_coefficients)
     ops.axpby(1.0, disp, d[0], vel, out=disp)
+    force_mode = args.force_mode if not (args.nccl or args.no_resident) else "spectral"
     stepper = halo.make_stepper(disp, vel, h, sh, resident=not args.no_resident, tile=args.tile,
-                                margin=args.margin, fused=not args.nccl)
+                                margin=args.margin, fused=not args.nccl, force_mode=force_mode)
     fused = type(stepper).__name__ == "SlabStepper"
 
     def step(n):
@@ -67,9 +73,45 @@ def run_multi(args, world, rank, dev):
     npart = N**3
     value = npart * K / t_dev
 
+    finfo = stepper.force_info() if hasattr(stepper, "force_info") else None
+    stepper.store(disp, vel)
+    # ---- parity carried by the bench line: the final matter power spectrum of this N-GPU run against the SAME
+    #      workload run on ONE GPU (rank 0, resident tile kernels, three-transform forces); device estimator of
+    #      jaxpm/utils.py:76-128 on the gathered particle set; max relative difference over the k bins
+    parity = None
+    if not args.no_parity:
+        from jaxpm_b200.painting import cic_paint_dx
+        from jaxpm_b200.utils import power_spectrum
+        parts = [torch.empty_like(disp) for _ in range(world)] if rank == 0 else None
+        dist.gather(disp, parts, dst=0)
+        if rank == 0:
+            full = torch.cat([torch.cat(parts[rx * pdims[1]:(rx + 1) * pdims[1]], dim=1) for rx in range(pdims[0])], dim=0)
+            del parts
+            box = (float(N),) * 3
+            _, pk_multi = power_spectrum(cic_paint_dx(full), box_shape=box)
+            ic = linear_field(shape, box, lambda kk: linear_matter_power(cosmo, kk), seed=0, device=dev)
+            dx1, p1, _ = lpt(cosmo, ic, a=0.1, order=args.lpt_order)
+            del ic
+            d1, v1 = dx1.contiguous(), p1.contiguous()
+            del dx1, p1
+            ops.axpby(1.0, d1, d[0], v1, out=d1)
+            sim1 = ops.Sim(shape, shape, True, dev, tile=args.tile, margin=args.margin)
+            sim1.load(d1, v1)
+            total = n_pre + K
+            for n in range(total):
+                sim1.step(k[n], d[n + 1] if n + 1 < total else 0.0)
+            sim1.store(d1, v1)
+            _, pk_one = power_spectrum(cic_paint_dx(d1), box_shape=box)
+            rel = (pk_multi / pk_one - 1).abs()
+            parity = {"final_pk_max_rel_diff_vs_1gpu": float(rel.max()), "bins": int(rel.numel()), "tolerance": 1e-4,
+                      "median_abs_dpos_cells": float((full - d1).abs().max(-1).values.median()),
+                      "against": "same ICs and schedule on one GPU (rank 0), resident tile kernels, spectral forces"}
+            del full, d1, v1, sim1
+            ops.clear_plans()
+            torch.cuda.empty_cache()
+        dist.barrier()
     # end to end: host-resident local state in, one step, host-resident state out (every rank)
     e2e_steps = max(1, min(K, args.e2e_steps))
-    stepper.store(disp, vel)
     ph, vh = disp.cpu().pin_memory(), vel.cpu().pin_memory()
     dist.barrier()
     torch.cuda.synchronize()
@@ -111,10 +153,14 @@ def run_multi(args, world, rank, dev):
         nzc = (N // 2 + 1 + 7) // 8 * 8
         lxl = N // world
         remote = (world - 1) / world
-        transposes = (lxl * N * nzc * 8) * remote * 3          # AT (1 spectrum) + T01 (2 spectra) leaving the rank
+        pot_steps = finfo["steps_potential"] if finfo else 0
+        pot = pot_steps > 0 and finfo["next"] == "potential"     # the timed steps ran the potential chain
+        nspec = 2 if pot else 3                                  # AT (1 spectrum) + psi (1) | + T01 (2 spectra)
+        transposes = (lxl * N * nzc * 8) * remote * nspec
         ge = timing["ghost_planes_used"]
         plane = (N + 8) * (N + 8) * 4
-        ghosts_out = 3 * 2 * ge * plane                          # force ghost planes written to the two neighbours
+        # ghost planes written to the two neighbours: three force meshes, or psi with 2 more planes for the stencil
+        ghosts_out = (2 * min(ge + 2, h) * plane) if pot else (3 * 2 * ge * plane)
         ghosts_in = 2 * ge * plane                               # density ghost planes read from them
         sent = transposes + ghosts_out
         nvlink = {"sent_bytes_per_rank_per_step": int(sent), "read_bytes_per_rank_per_step": int(ghosts_in),
@@ -127,10 +173,12 @@ def run_multi(args, world, rank, dev):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": t_dev / K * 1e3, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, 1LPT at a=0.1 then {args.schedule_steps} PM "
+            "config": {"workload": f"{N}^3 particles on {N}^3 mesh, {args.lpt_order}LPT at a=0.1 then {args.schedule_steps} PM "
                                    f"drift-kick steps to a=1 (relative mode), Planck15, L={N} Mpc/h; timed = the "
                                    f"last {K} steps, {n_pre} untimed before",
-                       "l2": "inputs larger than L2", "parallelism": f"slab pdims={pdims}, halo={h}",
+                       "l2": "inputs larger than L2",
+                       "parallelism": f"{'slab' if pdims[1] == 1 else 'pencil'} pdims={pdims}, halo={h}",
+                       "force_mode": force_mode,
                        "resident": not args.no_resident,
                        "exchange": ("halo reduce / FFT transposes / halo fill inside the FFT kernels over NVLink peer "
                                     "memory (slab.py), 4 flag barriers per step, no NCCL on the data path") if fused
@@ -139,7 +187,7 @@ def run_multi(args, world, rank, dev):
                          "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,
                          "unit": "GB/s", "frac": step_alg_bytes * K / t_dev / 1e9 / world / peak, "traffic": None},
             "cpu_baseline": None, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
-            "timing": timing, "nvlink": nvlink,
+            "timing": timing, "nvlink": nvlink, "parity": parity, "force_path": finfo,
         }))
     stepper.close()
     dist.destroy_process_group()

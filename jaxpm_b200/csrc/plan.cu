@@ -653,7 +653,7 @@ extern "C" int32_t jpm_pm_step_host_f32(jpm_plan* p, void* stream, float* pos_ho
 // ---------------------------------------------------------------------------------
 namespace jpm {
 
-struct SlabLayout { size_t dens, force, at, b3, t01, flags, total; };
+struct SlabLayout { size_t dens, force, psi, at, b3, t01, flags, total; };
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -662,6 +662,7 @@ static SlabLayout slab_layout(const Slab& sl) {
   size_t o = 0;
   L.dens = o;  o = align_up(o + (size_t)sl.npad * sizeof(float), 1024);
   L.force = o; o = align_up(o + 3 * (size_t)sl.npad * sizeof(float), 1024);
+  L.psi = o;   o = align_up(o + (size_t)sl.npad * sizeof(float), 1024);
   L.at = o;    o = align_up(o + (size_t)sl.nx * sl.ly * sl.nzc * sizeof(float2), 1024);
   L.b3 = o;    o = align_up(o + 3 * (size_t)sl.lx * sl.ny * sl.nzc * sizeof(float2), 1024);
   L.t01 = o;   o = align_up(o + (size_t)sl.lx * sl.ny * sl.nzc * sizeof(float4), 1024);
@@ -679,6 +680,7 @@ static void slab_point(Slab& sl, int r, void* base_v) {
   const size_t skip = (size_t)sl.G * sl.nyp * sl.nzp;
   sl.dens[r] = (float*)(base + L.dens) + skip;
   sl.force[r] = (float*)(base + L.force) + skip;
+  sl.psi[r] = (float*)(base + L.psi) + skip;
   sl.at[r] = (float2*)(base + L.at);
   sl.b3[r] = (float2*)(base + L.b3);
   sl.t01[r] = (float4*)(base + L.t01);

@@ -49,6 +49,11 @@ constexpr int kFlagXmin = 96;      // int: lowest / highest local x plane touche
 constexpr int kFlagXmax = 97;      //      sim_paint_kernel; INT_MAX / INT_MIN = unknown)
 constexpr int kFlagGe = 98;        // int: ghost planes per side in use this step = max over ranks of what each needs
 constexpr int kFlagGeSlots = 128;  // [P] the ranks' needs, written by the peers in the first barrier of a step
+// global force statistics of a step (AUTO force mode, csrc/sim.cu): two slots (step parity) of 4 words each, every
+// rank adds its share into EVERY rank's block (system-scope atomics over NVLink), so that all ranks read the same
+// numbers and take the same decision: [0..1] u64 fixed point (2^-24) of sum_k |psi_k|^2, [2] bits of max |F|
+constexpr int kFlagStats = 160;
+constexpr double kStatsFix = 16777216.0;
 
 // one tensor map per destination rank (TMA stores of the transposing FFT passes)
 struct alignas(64) TmapPack { CUtensorMap m[8]; };
@@ -120,13 +125,17 @@ int32_t plan_padded_forces(jpm_plan* p, cudaStream_t stream, float r_split, cons
 int32_t pmfft_enable(jpm_plan* p);
 int32_t pmfft_setup(jpm_plan* p);
 bool pmfft_shape_ok(int nx, int ny, int nz);
-int32_t slab_barrier(jpm_plan* p, cudaStream_t stream, bool exchange_ghost_width = false);
+// reach_extra: planes beyond the particles' reach the step still needs (2 for the potential chain's stencil)
+int32_t slab_barrier(jpm_plan* p, cudaStream_t stream, bool exchange_ghost_width = false, int reach_extra = 0);
+// skip_first_barrier: the caller has already run slab_barrier(p, stream, true, ...) for this evaluation
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
-                     float filter_kmax);
+                     float filter_kmax, bool skip_first_barrier = false);
+// P > 1: add this rank's pot_stats of the finished step into slot `slot` of every rank's flag block
+int32_t slab_stats_share(jpm_plan* p, cudaStream_t stream, int slot);
 // to_psi = false: psi lands in force3_p component 0 (read by sim_readpot_kernel); true: in the separate psi mesh,
 // from which pmfft_gradient forms the three force meshes (4th-order differences) in force3_p.
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax, bool to_psi = false);
+                        float filter_kmax, bool to_psi = false, bool skip_first_barrier = false);
 int32_t pmfft_gradient(jpm_plan* p, cudaStream_t stream);
 void pmfft_destroy(jpm_plan* p);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).

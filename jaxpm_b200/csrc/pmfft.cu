@@ -872,12 +872,17 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 // slab beyond what the neighbours filled hold nothing a particle within the halo reach reads.
 // HBM: 4 B/cell read + 12 B/cell written; the +-2 planes / rows are L2 / L1 hits.
 __global__ void __launch_bounds__(256)
-fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi) {
+fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi, unsigned* __restrict__ fmax_bits) {
   const int nzp = sl.nzp, nyp = sl.nyp, nz4 = nzp / 4;
   const int z4 = blockIdx.x * 32 + (threadIdx.x & 31);
   const int yp = blockIdx.y * 8 + (threadIdx.x >> 5);
   const int xp = x_lo + blockIdx.z;
-  if (z4 >= nz4 || yp >= nyp) return;
+  if (sl.P > 1) {
+    // planes the particles of this step reach: the slab + ghost_width planes per side (+-2 more hold psi)
+    const int ge = ghost_width(sl);
+    if (xp < sl.gx - ge || xp >= sl.gx + sl.lx + ge) return;
+  }
+  if (z4 >= nz4 || yp >= nyp) return;       // whole warps: z4 is the lane index, nz4 - 32 * blockIdx.x is checked per lane
   const float* __restrict__ ps = sl.psi[sl.rank];
   const long long sx = (long long)nyp * nzp;
   const int nxl = sl.lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
@@ -912,6 +917,15 @@ fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi) {
   __stcs(reinterpret_cast<float4*>(out), fx);
   __stcs(reinterpret_cast<float4*>(out + sl.npad), fy);
   __stcs(reinterpret_cast<float4*>(out + 2 * sl.npad), fz);
+  if (fmax_bits) {
+    // largest force component on the mesh: denominator of the fp32 cancellation bound (csrc/sim.cu, AUTO mode)
+    float m = fmaxf(fmaxf(fmaxf(fabsf(fx.x), fabsf(fx.y)), fmaxf(fabsf(fx.z), fabsf(fx.w))),
+                    fmaxf(fmaxf(fabsf(fy.x), fabsf(fy.y)), fmaxf(fabsf(fy.z), fabsf(fy.w))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(fz.x), fabsf(fz.y)), fmaxf(fabsf(fz.z), fabsf(fz.w))));
+    const unsigned act = __activemask();
+    const unsigned mb = __reduce_max_sync(act, __float_as_uint(m));
+    if ((threadIdx.x & 31) == (__ffs(act) - 1) && mb > *fmax_bits) atomicMax(fmax_bits, mb);
+  }
 }
 
 // ---- inter-GPU barrier over peer-mapped flags ------------------------------------------------------------
@@ -919,7 +933,7 @@ fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi) {
 // waits until its own slots all reach `epoch`.  One CTA, one thread per peer.  A lost peer trips the
 // timeout (~4 s) and raises the error word instead of hanging the GPU.
 template <bool GHOSTW>
-__global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch) {
+__global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch, int reach_extra) {
   const int t = threadIdx.x;
   __threadfence_system();
   if (t < sl.P) {
@@ -933,7 +947,7 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
         const int raw = max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.lx - 1)));
         need = min(sl.gx, raw);
         // the outermost ghost plane was touched: some particle is at (or wrapped past) the reach of the halo
-        if (raw >= sl.gx && t == 0) sl.flags[sl.rank][kFlagReach] = 1u;
+        if (raw + reach_extra >= sl.gx && t == 0) sl.flags[sl.rank][kFlagReach] = 1u;
       }
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sl.flags[t] + kFlagGeSlots + sl.rank), "r"(need) : "memory");
     }
@@ -965,6 +979,17 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
     mine[kFlagXmax] = (int)0x80000000;
   }
   __threadfence_system();
+}
+
+// this rank's force statistics -> slot `slot` of every rank's flag block (exact: fixed-point u64 add, u32 max)
+__global__ void slab_stats_kernel(const __grid_constant__ Slab sl, const double* __restrict__ stats, int slot) {
+  const int r = threadIdx.x;
+  if (r >= sl.P) return;
+  const double q = fmin(fmax(stats[0] * kStatsFix, 0.0), 9.0e18);
+  const unsigned fb = reinterpret_cast<const unsigned*>(stats + 1)[0];
+  unsigned* dst = sl.flags[r] + kFlagStats + 4 * slot;
+  atomicAdd_system(reinterpret_cast<unsigned long long*>(dst), (unsigned long long)q);
+  atomicMax_system(dst + 2, fb);
 }
 
 // ghost planes per side in use this step (see slab_barrier_kernel); P == 1: the periodic images, always gx
@@ -1131,6 +1156,8 @@ int32_t pmfft_setup(jpm_plan* p) {
   cudaFuncAttributes fa;
   JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<true>));
   JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_barrier_kernel<false>));
+  JPM_CUDA(cudaFuncGetAttributes(&fa, fft::slab_stats_kernel));
+  JPM_CUDA(cudaFuncGetAttributes(&fa, fft::fdgrad_kernel));
   return fft::set_attrs(sl);
 }
 
@@ -1177,10 +1204,10 @@ void pmfft_destroy(jpm_plan* p) {
   p->fft_on = false;
 }
 
-int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width) {
+int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width, int reach_extra) {
   if (p->slab.P == 1) return JPM_OK;
-  if (exchange_ghost_width) fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch);
-  else fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch);
+  if (exchange_ghost_width) fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, reach_extra);
+  else fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch, 0);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }
@@ -1188,7 +1215,7 @@ int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width) {
 // density_p (painted, ghosts NOT folded) -> force3_p (ghosts filled).  P == 1: five kernels on `st`;
 // P > 1: the same five kernels, each rank on its own stream, with four flag barriers between them.
 int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
-                     float filter_kmax) {
+                     float filter_kmax, bool skip_first_barrier) {
   using namespace fft;
   JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
   const Slab& sl = p->slab;
@@ -1207,7 +1234,7 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   double* sumsq_ptr = (p->want_sumsq && p->pot_stats) ? p->pot_stats : nullptr;
   int32_t rc;
   // every rank has painted: neighbours' ghost planes are final; agree on the ghost width of this step
-  if ((rc = slab_barrier(p, st, true))) return rc;
+  if (!skip_first_barrier && (rc = slab_barrier(p, st, true))) return rc;
   for (int x0 = 0; x0 < sl.lx; x0 += cx) {
     const int nxl = std::min(cx, sl.lx - x0);
 #define RUN_ZF(N_)                                                                                             \
@@ -1279,11 +1306,18 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   return JPM_OK;
 }
 
+int32_t slab_stats_share(jpm_plan* p, cudaStream_t st, int slot) {
+  if (p->slab.P == 1 || !p->pot_stats) return JPM_OK;
+  fft::slab_stats_kernel<<<1, 32, 0, st>>>(p->slab, p->pot_stats, slot);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
 // density_p (painted, ghosts NOT folded) -> psi = IFFT(G delta / k^2) in force3_p component 0, ghosts filled
 // (+2 planes for the read kernel's difference stencil).  Same passes / barriers as pmfft_forces with ONE
 // spectrum through the inverse half: 8 + 8 + 8 + 8 + 8 = 40 B/cell instead of 72.
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax, bool to_psi) {
+                        float filter_kmax, bool to_psi, bool skip_first_barrier) {
   using namespace fft;
   JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
   if (to_psi && !p->slab.psi[p->slab.rank]) {
@@ -1303,7 +1337,7 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   if (!p->pot_stats) JPM_CUDA(cudaMalloc(&p->pot_stats, 4 * sizeof(double)));
   JPM_CUDA(cudaMemsetAsync(p->pot_stats, 0, 4 * sizeof(double), st));   // [0] sum |psi_k|^2, [1] max |F| bits of this step
   int32_t rc;
-  if ((rc = slab_barrier(p, st, true))) return rc;
+  if (!skip_first_barrier && (rc = slab_barrier(p, st, true, 2))) return rc;
 #define RUN_ZF(N_)                                                                                             \
   zfwd_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
       sl, p->tw_zh, p->tw_zfull, 0);
@@ -1358,7 +1392,8 @@ int32_t pmfft_gradient(jpm_plan* p, cudaStream_t st) {
   const Slab& sl = p->slab;
   JPM_CHECK_ARG(sl.psi[sl.rank], "no psi mesh (run pmfft_potential(to_psi) first)");
   const int nxl = sl.lx + 2 * sl.gx;
-  fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, nxl), 256, 0, st>>>(sl, 0, nxl);
+  unsigned* fmax_bits = p->pot_stats ? reinterpret_cast<unsigned*>(p->pot_stats + 1) : nullptr;
+  fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, nxl), 256, 0, st>>>(sl, 0, nxl, fmax_bits);
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "fd_gradient");
   return JPM_OK;

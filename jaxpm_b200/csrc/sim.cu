@@ -63,18 +63,10 @@ struct jpm_sim {
   int cur = 0;
   bool painted = false, loaded = false;
   bool pos_only = false;               // JPM_SIM_POSITIONS_ONLY: no velocities, no second ordering (paint / forces only)
-  // ---- potential ("FD") force path: psi mesh + real-space 4th-order differences (sim_readpot_kernel) ----
-  CUtensorMap tm_psi;                  // (PB, PB, BZ) boxes of force3_p component 0
+  // ---- potential force path: ONE inverse transform (psi mesh) + the gradient pass of csrc/pmfft.cu ----
   bool pot_ok = false;                 // potential chain available: TMA tile path + fused FFT chain (power-of-two mesh)
-  bool potfused_ok = false;            // ... and its fused read kernel (margin 1: psi box = force box + 2 cells)
-  int pot_variant = 0;                 // 0: gradient pass (pmfft_gradient) + sim_read_kernel; 1: sim_readpot_kernel
   int force_mode = 0;                  // JPM_FORCE_SPECTRAL / JPM_FORCE_POTENTIAL / JPM_FORCE_AUTO
   int cur_mode = 0;                    // what the next step runs (auto switches it from the measured error bound)
-  int pot_grid = 0;                    // persistent CTAs of sim_readpot_kernel
-  int pot_threads = 1024;              // threads per CTA of it (JPM_POT_THREADS=768: more registers per thread)
-  int read_persist = 0;                // JPM_READ_PERSIST=768|1024: three-mesh read as the persistent double-buffered kernel
-  int persist_grid = 0;
-  int* tile_counter = nullptr;
   // AUTO: the statistics of step n (device doubles, plan->pot_stats) are copied to pinned slot n % 3 behind the step;
   // the mode of step n is decided from the slot of step n - 2 after waiting for ITS event - a fixed lag, so the
   // sequence of modes does not depend on how far the host runs ahead of the device (reproducible runs, and the
@@ -82,6 +74,7 @@ struct jpm_sim {
   double* stats_host = nullptr;        // pinned [3][4]
   cudaEvent_t stats_ev[3] = {nullptr, nullptr, nullptr};
   bool stats_pending[3] = {false, false, false};
+  bool stats_fixed[3] = {false, false, false};   // slot holds the slab ranks' global statistics (u64 fixed point)
   long long nstep = 0;
   double last_bound = -1.0;            // last evaluated error bound (auto), < 0 = none yet
   long long mode_steps[2] = {0, 0};    // steps run in spectral / potential mode
@@ -220,10 +213,8 @@ sim_store_kernel(SimGeom g, const float4* __restrict__ spos, const float* __rest
 // exclusive scan of count[nt] -> start[nt+1]; cursor = start; count = 0.  One CTA of 32 warps; warp w
 // owns the contiguous segment [w*seg, (w+1)*seg) and walks it 32 entries at a time (coalesced).
 __global__ void __launch_bounds__(1024)
-sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int nt,
-                int* __restrict__ tile_counter = nullptr) {
+sim_scan_kernel(int* __restrict__ count, int* __restrict__ start, int* __restrict__ cursor, int nt) {
   __shared__ int wsum[32];
-  if (threadIdx.x == 0 && tile_counter) *tile_counter = 0;   // work queue of the persistent read kernel
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int seg = ((nt + 31) / 32 + 31) & ~31;
   const int b = warp * seg, e = min(b + seg, nt);
@@ -880,253 +871,6 @@ sim_forces_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float
   if ((threadIdx.x & 31) == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
 }
 
-// ---- potential flavour of read3 + kick + drift (the "FD" force path) --------------------------------------
-// The FFT chain delivers ONE mesh, psi = IFFT(G delta / k^2) (pmfft_potential, csrc/pmfft.cu).  The reference's
-// force spectra -gradient_kernel(k, d) * pot_k (pm.py:54-56, kernels.py:62-66) are the 4th-order central
-// differences of it,   F_d(c) = [8 (psi(c + e_d) - psi(c - e_d)) - (psi(c + 2 e_d) - psi(c - 2 e_d))] / 12,
-// so this kernel stages the psi box of a tile (2 more cells per side than the force box), differentiates it in
-// shared memory into the three force boxes and then runs the same gather + kick + drift + re-sort as
-// sim_read_kernel.  DRAM: one mesh box per tile instead of three.
-// PERSISTENT: one 1024-thread CTA per SM takes tiles from an atomic counter; the psi box of the NEXT tile lands
-// (TMA, mbarrier) in the second buffer while the particles of the current tile are processed.
-//   shared memory: psi[2][PB][PB][BZ] | F[3][B][B][BZ]       (tile 16, margin 1: 2 x 50.8 KB + 104 KB)
-// TMA flavour only (ghost-zone mesh, no box ever wraps), margin 1 (the ghost zone is 4 cells wide).
-template <int TS, int M> struct PotGeom {
-  static constexpr int T = 1 << TS, B = T + 2 * M + 1, PB = B + 4;
-  static constexpr int BZ = (T + kTmaMz + M + 3 + 3) & ~3;       // z cells: [oz, oz + BZ), oz = tile origin - 4
-  static constexpr int NBOX = B * B * BZ;                        // one force component
-  static constexpr int NPSI = PB * PB * BZ;
-  static constexpr int NPSI_PAD = (NPSI + 31) & ~31;             // keeps the second buffer 128-byte aligned
-  static constexpr int ZLO = kTmaMz - M, ZHI = kTmaMz + T + M;    // force cells [ZLO, ZHI] are gathered from
-  static_assert(ZLO - 2 >= 0 && ZHI + 2 < BZ, "the psi box must cover the +-2 stencil in z");
-  static constexpr int smem_bytes = (2 * NPSI_PAD + 3 * NBOX) * (int)sizeof(float);
-  // persistent flavour of the three-mesh read: two (3, B, B, BZ) force boxes, no psi
-  static constexpr int NF3_PAD = (3 * NBOX + 31) & ~31;
-  static constexpr int smem_bytes_f3 = 2 * NF3_PAD * (int)sizeof(float);
-};
-
-__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* tm, int c0, int c1, int c2,
-                                            unsigned long long* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-      ::"r"(smem_u32(dst)), "l"((unsigned long long)tm), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
-      : "memory");
-}
-
-// D psi along one axis at padded-mesh offset o with element stride sd (global-memory fallback)
-__device__ __forceinline__ float fd4_global(const float* __restrict__ psi, long long o, long long sd) {
-  const float d1 = __ldg(psi + o + sd) - __ldg(psi + o - sd);
-  const float d2 = __ldg(psi + o + 2 * sd) - __ldg(psi + o - 2 * sd);
-  return (2.0f / 3.0f) * d1 - (1.0f / 12.0f) * d2;
-}
-
-template <bool REL, int TS, int M, int NT, bool POT = true>
-__global__ void __launch_bounds__(NT, 1)
-sim_readpot_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
-                   const float* __restrict__ svel, const int* __restrict__ start, const float* __restrict__ psi,
-                   float kick, float drift, long long np, int* __restrict__ cursor, float4* __restrict__ npos,
-                   float* __restrict__ nvel, unsigned long long* __restrict__ stats, int* __restrict__ tile_counter,
-                   unsigned* __restrict__ fmax_bits, int l2ahead) {
-  using PG = PotGeom<TS, M>;
-  constexpr int B = PG::B, PB = PG::PB, BZ = PG::BZ, NBOX = PG::NBOX;
-  extern __shared__ __align__(128) float smem[];
-  // POT: psi[2] | F[3][B][B][BZ] (built from psi);  !POT: F[2][3][B][B][BZ] loaded by TMA (psi = the three force meshes)
-  const float* box = smem + 2 * PG::NPSI_PAD;
-  __shared__ __align__(8) unsigned long long mbar[2];
-  __shared__ int s_tile[2];
-  const int lane = threadIdx.x & 31;
-  int nslow = 0;
-  float fmax = 0.f;
-
-  // thread 0: next non-empty tile from the global counter; request its psi box
-  auto grab_and_load = [&](int buf) {
-    int t;
-    do {
-      t = atomicAdd(tile_counter, 1);
-    } while (t < g.nt && start[t] == start[t + 1]);
-    s_tile[buf] = t;
-    if (t < g.nt) {
-      const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-      if (POT) {
-        mbar_expect_tx(&mbar[buf], (unsigned)(PG::NPSI * sizeof(float)));
-        tma_load_3d(smem + buf * PG::NPSI_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M - 2 + g.mo,
-                    (tx << TS) - M - 2 + g.mox, &mbar[buf]);
-      } else {
-        mbar_expect_tx(&mbar[buf], 3u * NBOX * (unsigned)sizeof(float));
-        tma_load_4d(smem + buf * PG::NF3_PAD, &tm, (tz << TS) - kTmaMz + g.mo, (ty << TS) - M + g.mo,
-                    (tx << TS) - M + g.mox, 0, &mbar[buf]);
-      }
-    }
-  };
-  if (threadIdx.x == 0) {
-    mbar_init(&mbar[0], 1);
-    mbar_init(&mbar[1], 1);
-    fence_async_smem();
-    grab_and_load(0);
-  }
-  __syncthreads();
-  unsigned phase0 = 0, phase1 = 0;
-  for (int buf = 0;; buf ^= 1) {
-    const int t = s_tile[buf];
-    if (t >= g.nt) break;
-    const int beg = start[t], end = start[t + 1];
-    const int tz = t % g.ntz, ty = (t / g.ntz) % g.nty, tx = t / (g.ntz * g.nty);
-    const int ox = (tx << TS) - M, oy = (ty << TS) - M, oz = (tz << TS) - kTmaMz;
-    // first particle of this thread streams in while the psi box lands and is differentiated
-    int q = beg + threadIdx.x;
-    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-    float vin[3] = {0.f, 0.f, 0.f};
-    if (q < end) {
-      p = __ldcs(spos + q);
-#pragma unroll
-      for (int f = 0; f < 3; ++f) vin[f] = __ldcs(svel + f * np + q);
-    }
-    if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1; }
-    else { mbar_wait(&mbar[1], phase1); phase1 ^= 1; }
-    if (!POT) {
-      // the boxes of this tile have landed; the other buffer was last read before the barrier that ended the
-      // previous tile, so the next tile's boxes can be requested right away
-      box = smem + buf * PG::NF3_PAD;
-      if (threadIdx.x == 0) grab_and_load(buf ^ 1);
-    }
-    // F_d = D_d psi on the cells the gathers can touch: x, y in [0, B), z in [ZLO, ZHI]
-    if (POT) {
-      float* const fbox = smem + 2 * PG::NPSI_PAD;
-      const float* const ps = smem + buf * PG::NPSI_PAD;
-      constexpr int NZ = PG::ZHI - PG::ZLO + 1, NCELL = B * B * NZ;
-      constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
-      for (int i = threadIdx.x; i < NCELL; i += blockDim.x) {
-        const int r = i / NZ, lz = PG::ZLO + (i - r * NZ);
-        const int lx = r / B, ly = r - lx * B;
-        const float* c = ps + ((lx + 2) * PB + (ly + 2)) * BZ + lz;
-        const float fx = c8 * (c[PB * BZ] - c[-PB * BZ]) - c1 * (c[2 * PB * BZ] - c[-2 * PB * BZ]);
-        const float fy = c8 * (c[BZ] - c[-BZ]) - c1 * (c[2 * BZ] - c[-2 * BZ]);
-        const float fz = c8 * (c[1] - c[-1]) - c1 * (c[2] - c[-2]);
-        float* o = fbox + (lx * B + ly) * BZ + lz;
-        o[0] = fx; o[NBOX] = fy; o[2 * NBOX] = fz;
-      }
-      __syncthreads();      // force boxes complete; the other psi buffer was consumed one tile ago
-      if (threadIdx.x == 0) grab_and_load(buf ^ 1);
-    }
-    for (int qb = beg; qb < end; qb += blockDim.x) {
-      const bool valid = q < end;
-      const int qn = q + blockDim.x;
-      float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
-      float vn[3] = {0.f, 0.f, 0.f};
-      if (qn < end) {
-        pn = __ldcs(spos + qn);
-#pragma unroll
-        for (int f = 0; f < 3; ++f) vn[f] = __ldcs(svel + f * np + qn);
-      }
-      if (l2ahead > 0) {
-        const int qf = qn + l2ahead * (int)blockDim.x;
-        if (qf < end) {
-          prefetch_l2(spos + qf);
-          if ((threadIdx.x & 3) == 0) {
-#pragma unroll
-            for (int f = 0; f < 3; ++f) prefetch_l2(svel + f * np + qf);
-          }
-        }
-      }
-      int tt = 0, lx = 0, ly = 0, lz = 0;
-      bool fast = false;
-      FastStencil s;
-      if (valid) {
-        fast = stencil_box<REL, B, B, BZ>(g, p, ox, oy, oz, s, lx, ly, lz);
-        // POT: the z extent of the force boxes that holds values is [ZLO, ZHI]
-        if (POT) fast = fast && lz >= PG::ZLO && lz < PG::ZHI;
-        if (fast) {
-          tt = ((s.i0 >> TS) * g.nty + (s.j0 >> TS)) * g.ntz + (s.k0 >> TS);
-        } else {
-          Cic1 cx, cy, cz;
-          sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-          tt = tile_of<TS>(g, cx.i0, cy.i0, cz.i0);
-        }
-      }
-      const unsigned peers = __match_any_sync(0xffffffffu, valid ? tt : (0x40000000 | lane));
-      const int leader = __ffs(peers) - 1;
-      int slot = 0;
-      if (valid && lane == leader) slot = atomicAdd(cursor + tt, __popc(peers));
-      float v[3] = {0, 0, 0};
-      if (valid) {
-        float acc[3] = {0.f, 0.f, 0.f};
-        if (fast) {
-          const float* b0 = box + (lx * B + ly) * BZ + lz;
-          const float w00 = s.wx0 * s.wy0, w10 = s.wx1 * s.wy0, w01 = s.wx0 * s.wy1, w11 = s.wx1 * s.wy1;
-          const float kk[8] = {w00 * s.wz0, w00 * s.wz1, w01 * s.wz0, w01 * s.wz1,
-                               w10 * s.wz0, w10 * s.wz1, w11 * s.wz0, w11 * s.wz1};
-          constexpr int off[8] = {0, 1, BZ, BZ + 1, B * BZ, B * BZ + 1, B * BZ + BZ, B * BZ + BZ + 1};
-          float mv[3][8];
-#pragma unroll
-          for (int f = 0; f < 3; ++f)
-#pragma unroll
-            for (int c = 0; c < 8; ++c) mv[f][c] = b0[f * NBOX + off[c]];
-#pragma unroll
-          for (int c = 0; c < 8; ++c)
-#pragma unroll
-            for (int f = 0; f < 3; ++f) acc[f] = fmaf(mv[f][c], kk[c], acc[f]);
-        } else {
-          // periodic-edge lanes and particles beyond the box: the generic corner rules; forces from the staged
-          // boxes when all 8 corners lie inside, else differentiated straight from the ghost-zone mesh
-          Cic1 cx, cy, cz;
-          sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
-          Corners c;
-          make_corners<B, BZ>(g, cx, cy, cz, ox, oy, oz, c);
-          if (POT) {
-#pragma unroll
-            for (int a = 0; a < 2; ++a) c.inside = c.inside && c.lz[a] >= PG::ZLO && c.lz[a] <= PG::ZHI;
-          }
-#pragma unroll
-          for (int cc = 0; cc < 8; ++cc) {
-            const int a = cc & 1, b = (cc >> 1) & 1, d = cc >> 2;
-            if (REL && (c.ix[a] < 0 || c.iy[b] < 0 || c.iz[d] < 0)) continue;
-            const float k = (c.wx[a] * c.wy[b]) * c.wz[d];
-            if (c.inside) {
-              const int o = (c.lx[a] * B + c.ly[b]) * BZ + c.lz[d];
-#pragma unroll
-              for (int f = 0; f < 3; ++f) acc[f] = fmaf(box[f * NBOX + o], k, acc[f]);
-            } else {
-              const long long o = mesh_index(g, c.ix[a], c.iy[b], c.iz[d]);
-              if (POT) {
-                acc[0] = fmaf(fd4_global(psi, o, g.msx), k, acc[0]);
-                acc[1] = fmaf(fd4_global(psi, o, g.msy), k, acc[1]);
-                acc[2] = fmaf(fd4_global(psi, o, 1), k, acc[2]);
-              } else {
-#pragma unroll
-                for (int f = 0; f < 3; ++f) acc[f] = fmaf(__ldg(psi + f * g.mb + o), k, acc[f]);
-              }
-            }
-          }
-          if (c.inside) ++nslow; else atomicAdd(stats + 1, 1ull);
-        }
-        fmax = fmaxf(fmax, fmaxf(fabsf(acc[0]), fmaxf(fabsf(acc[1]), fabsf(acc[2]))));
-#pragma unroll
-        for (int f = 0; f < 3; ++f) v[f] = fmaf(kick, acc[f], vin[f]);
-        p.x = fmaf(drift, v[0], p.x);
-        p.y = fmaf(drift, v[1], p.y);
-        p.z = fmaf(drift, v[2], p.z);
-      }
-      slot = __shfl_sync(0xffffffffu, slot, leader) + __popc(peers & ((1u << lane) - 1u));
-      if (valid) {
-        npos[slot] = p;
-#pragma unroll
-        for (int f = 0; f < 3; ++f) nvel[f * np + slot] = v[f];
-      }
-      p = pn;
-      q = qn;
-#pragma unroll
-      for (int f = 0; f < 3; ++f) vin[f] = vn[f];
-    }
-    __syncthreads();      // every gather of this tile is done before the boxes are rebuilt; s_tile[buf ^ 1] visible
-  }
-  nslow = __reduce_add_sync(0xffffffffu, nslow);
-  if (lane == 0 && nslow) atomicAdd(stats + 3, (unsigned long long)nslow);
-  if (fmax_bits) {
-    const unsigned m = __reduce_max_sync(0xffffffffu, __float_as_uint(fmax));   // non-negative floats order like their bits
-    if (lane == 0 && m) atomicMax(fmax_bits, m);
-  }
-}
-
 template <int TS, int M, bool TMA> constexpr int paint_smem() {
   constexpr int B = (1 << TS) + 2 * M + 1;
   constexpr int NBOX = B * B * (TMA ? (((1 << TS) + kTmaMz + M + 1 + 3) & ~3) : ((B + 1) & ~1));
@@ -1225,7 +969,6 @@ extern "C" int32_t jpm_sim_create_ex(jpm_sim** out, jpm_plan* plan, int32_t nx, 
   // TMA path: needs the plan's ghost-zone meshes (jpm_sim_step only) and a supported tile/margin pair
   memset(&s->tm_rho, 0, sizeof(CUtensorMap));
   memset(&s->tm_f3, 0, sizeof(CUtensorMap));
-  memset(&s->tm_psi, 0, sizeof(CUtensorMap));
   if (plan && tma_pair(ts, m) && nx >= s->g.T && ny >= s->g.T && nz >= s->g.T) {
     int32_t rc = plan_enable_padded(plan);
     if (rc) return rc;
@@ -1265,63 +1008,9 @@ extern "C" int32_t jpm_sim_create_ex(jpm_sim** out, jpm_plan* plan, int32_t nx, 
   }
       JPM_SIM_DISPATCH_TMA(ts, m, SET_ATTR_TMA);
 #undef SET_ATTR_TMA
-      // potential path: margin 1 (the ghost zone is 4 = margin + 3 cells wide), fused FFT chain
-      if (m == 1 && plan->fft_on) {
-        const int PB = B + 4;
-        const unsigned bp[3] = {(unsigned)BZ, (unsigned)PB, (unsigned)PB};
-        if ((rc = encode_tensor_map(&s->tm_psi, plan->force3_p, 3, d3, st3, bp))) return rc;
-        int occ = 0;
-#define POT_ATTR(TS_, NT_)                                                                                 \
-  {                                                                                                         \
-    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<false, TS_, 1, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  PotGeom<TS_, 1>::smem_bytes));                                            \
-    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<true, TS_, 1, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                  PotGeom<TS_, 1>::smem_bytes));                                            \
-    JPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sim_readpot_kernel<true, TS_, 1, NT_>, NT_, \
-                                                           PotGeom<TS_, 1>::smem_bytes));                   \
-  }
-        s->pot_threads = 1024;
-        if (ts == 4) {
-          if (const char* e = getenv("JPM_POT_THREADS")) s->pot_threads = atoi(e) == 768 ? 768 : 1024;
-          if (s->pot_threads == 768) POT_ATTR(4, 768) else POT_ATTR(4, 1024)
-        } else {
-          POT_ATTR(3, 1024)
-        }
-#undef POT_ATTR
-        int dev = 0, sms = kNumSMs;
-        JPM_CUDA(cudaGetDevice(&dev));
-        JPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-        s->pot_grid = std::max(1, occ) * sms;
-        s->potfused_ok = occ > 0;
-      }
-      if (m == 1 && ts == 4) {
-        if (const char* e = getenv("JPM_READ_PERSIST")) s->read_persist = atoi(e) == 768 ? 768 : (atoi(e) == 1024 ? 1024 : 0);
-        if (s->read_persist) {
-          int occ = 0, dev = 0, sms = kNumSMs;
-#define PERSIST_ATTR(NT_)                                                                                   \
-  {                                                                                                         \
-    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<false, 4, 1, NT_, false>,                              \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PotGeom<4, 1>::smem_bytes_f3)); \
-    JPM_CUDA(cudaFuncSetAttribute(sim_readpot_kernel<true, 4, 1, NT_, false>,                               \
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, PotGeom<4, 1>::smem_bytes_f3)); \
-    JPM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sim_readpot_kernel<true, 4, 1, NT_, false>, NT_, \
-                                                           PotGeom<4, 1>::smem_bytes_f3));                  \
-  }
-          if (s->read_persist == 768) PERSIST_ATTR(768) else PERSIST_ATTR(1024)
-#undef PERSIST_ATTR
-          JPM_CUDA(cudaGetDevice(&dev));
-          JPM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-          s->persist_grid = std::max(1, occ) * sms;
-          if (occ < 1) s->read_persist = 0;
-        }
-      }
-      s->pot_ok = plan->fft_on && !plan->is_slab;
-      if (const char* e = getenv("JPM_POT_VARIANT")) s->pot_variant = atoi(e);
-      if (s->pot_variant == 1 && !s->potfused_ok) s->pot_variant = 0;
+      s->pot_ok = plan->fft_on;      // potential chain: fused FFT chain (power-of-two mesh) + gradient pass
     }
   }
-  JPM_CUDA(cudaMalloc(&s->tile_counter, sizeof(int)));
-  JPM_CUDA(cudaMemset(s->tile_counter, 0, sizeof(int)));
   JPM_CUDA(cudaMallocHost(&s->stats_host, 3 * 4 * sizeof(double)));
   for (int i = 0; i < 3; ++i) JPM_CUDA(cudaEventCreateWithFlags(&s->stats_ev[i], cudaEventDisableTiming));
   if (const char* e = getenv("JPM_FORCE_MODE")) {   // default force path of new sims (tests / A-B runs)
@@ -1352,7 +1041,6 @@ extern "C" int32_t jpm_sim_destroy(jpm_sim* s) {
   if (s->count) cudaFree(s->count);
   if (s->cursor) cudaFree(s->cursor);
   if (s->stats) cudaFree(s->stats);
-  if (s->tile_counter) cudaFree(s->tile_counter);
   if (s->stats_host) cudaFreeHost(s->stats_host);
   for (int i = 0; i < 3; ++i)
     if (s->stats_ev[i]) cudaEventDestroy(s->stats_ev[i]);
@@ -1437,31 +1125,14 @@ static int32_t sim_paint_impl(jpm_sim* s, cudaStream_t st, float* mesh, bool tma
 static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const float* fy, const float* fz,
                              float kick_coef, float drift_coef, bool tma) {
   const int nxt = s->cur ^ 1;
-  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt, s->tile_counter);
+  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt);
   JPM_LAUNCH_CHECK();
   const int ts = s->g.tshift, m = s->g.m;
   const SimGeom& g = tma ? s->gp : s->g;
-  const bool want_fmax = tma && s->force_mode == 2 && s->plan && s->plan->pot_stats;
+  // AUTO, spectral step: the read tracks max |F| (a potential step gets it from the gradient pass instead)
+  const bool want_fmax = tma && s->force_mode == 2 && s->cur_mode == 0 && s->plan && s->plan->pot_stats;
   unsigned* fmax_bits = want_fmax ? reinterpret_cast<unsigned*>(s->plan->pot_stats + 1) : nullptr;
   static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
-  if (tma && s->read_persist) {
-    // persistent flavour: one CTA per SM, tiles from an atomic counter, the next tile's boxes in flight
-    const int grid = std::min(s->persist_grid, g.nt);
-#define LAUNCH_PERSIST(REL_, NT_)                                                                          \
-  sim_readpot_kernel<REL_, 4, 1, NT_, false><<<grid, NT_, PotGeom<4, 1>::smem_bytes_f3, st>>>(             \
-      s->tm_f3, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], fx, kick_coef, drift_coef, s->np,     \
-      s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead)
-    if (s->read_persist == 768) {
-      if (s->relative) LAUNCH_PERSIST(true, 768); else LAUNCH_PERSIST(false, 768);
-    } else {
-      if (s->relative) LAUNCH_PERSIST(true, 1024); else LAUNCH_PERSIST(false, 1024);
-    }
-#undef LAUNCH_PERSIST
-    JPM_LAUNCH_CHECK();
-    s->cur = nxt;
-    s->painted = false;
-    return JPM_OK;
-  }
 #define LAUNCH_READ_T(TS_, M_, TMA_)                                                                     \
   if (TMA_ && want_fmax) {                                                                               \
     if (s->relative)                                                                                     \
@@ -1495,37 +1166,6 @@ static int32_t sim_read_impl(jpm_sim* s, cudaStream_t st, const float* fx, const
   return JPM_OK;
 }
 
-// potential flavour: psi (force3_p component 0, ghosts filled) -> kick / drift / re-sort, persistent CTAs
-static int32_t sim_readpot_impl(jpm_sim* s, cudaStream_t st, float kick_coef, float drift_coef) {
-  const int nxt = s->cur ^ 1;
-  sim_scan_kernel<<<1, 1024, 0, st>>>(s->count, s->start[nxt], s->cursor, s->g.nt, s->tile_counter);
-  JPM_LAUNCH_CHECK();
-  const SimGeom& g = s->gp;
-  jpm_plan* p = s->plan;
-  unsigned* fmax_bits = p->pot_stats ? reinterpret_cast<unsigned*>(p->pot_stats + 1) : nullptr;
-  static const int l2ahead = getenv("JPM_L2_AHEAD") ? atoi(getenv("JPM_L2_AHEAD")) : kL2Ahead;
-  const int grid = std::min(s->pot_grid, g.nt);
-#define LAUNCH_POT(REL_, TS_)                                                                              \
-  if (s->pot_threads == 768 && TS_ == 4)                                                                   \
-    sim_readpot_kernel<REL_, 4, 1, 768><<<grid, 768, PotGeom<4, 1>::smem_bytes, st>>>(                     \
-        s->tm_psi, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], p->force3_p, kick_coef, drift_coef, \
-        s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead);        \
-  else                                                                                                     \
-  sim_readpot_kernel<REL_, TS_, 1, 1024><<<grid, 1024, PotGeom<TS_, 1>::smem_bytes, st>>>(                 \
-      s->tm_psi, g, s->pos[s->cur], s->vel[s->cur], s->start[s->cur], p->force3_p, kick_coef, drift_coef,  \
-      s->np, s->cursor, s->pos[nxt], s->vel[nxt], s->stats, s->tile_counter, fmax_bits, l2ahead)
-  if (s->g.tshift == 4) {
-    if (s->relative) LAUNCH_POT(true, 4); else LAUNCH_POT(false, 4);
-  } else {
-    if (s->relative) LAUNCH_POT(true, 3); else LAUNCH_POT(false, 3);
-  }
-#undef LAUNCH_POT
-  JPM_LAUNCH_CHECK();
-  s->cur = nxt;
-  s->painted = false;
-  return JPM_OK;
-}
-
 // fp32 cancellation bound of the potential path.  Differencing psi (rms psi_rms, FFT round-off ~ 5e-7 of its
 // maximum) leaves an absolute force error ~ 5.4e-7 * max|psi|; measured against the float64 oracle on 256^3 and
 // 512^3 LCDM fields (linear a = 0.1 and clustered a = 1, tools/phi_fd_precision.py): max|psi| <= 5.3 psi_rms, so
@@ -1544,7 +1184,12 @@ static void sim_eval_stats(jpm_sim* s, long long step) {
   if (cudaEventSynchronize(s->stats_ev[i]) != cudaSuccess) return;
   s->stats_pending[i] = false;
   const double* h = s->stats_host + 4 * i;
-  const double sumsq = h[0];
+  double sumsq = h[0];
+  if (s->stats_fixed[i]) {
+    unsigned long long q;
+    memcpy(&q, &h[0], sizeof(q));
+    sumsq = (double)q / kStatsFix;
+  }
   unsigned long long bits;
   memcpy(&bits, &h[1], sizeof(bits));
   const unsigned fb = (unsigned)(bits & 0xffffffffull);
@@ -1646,20 +1291,34 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
       set_error("potential force path not available for this sim (needs the TMA tile path and the fused FFT chain)");
       return JPM_ERR_INVALID;
     }
-    if (s->force_mode == 2) sim_eval_stats(s, s->nstep - kStatsLag);
+    const bool multi = p->is_slab && p->slab.P > 1;
+    // AUTO: fixed-lag decision (one GPU: statistics of step n - 2; slab ranks: the GLOBAL statistics of step n - 3,
+    // which every rank receives in its own flag block, so that all ranks switch at the same step)
+    if (s->force_mode == 2) sim_eval_stats(s, s->nstep - (multi ? kStatsLag + 1 : kStatsLag));
     const bool want_stats = s->force_mode == 2;
     if (want_stats && !p->pot_stats) {
       JPM_CUDA(cudaMalloc(&p->pot_stats, 4 * sizeof(double)));
     }
-    if (s->force_mode != 0 && s->cur_mode == 1 && s->pot_variant == 1) {
-      // potential chain: ONE inverse transform, forces differentiated in the read kernel
-      if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f))) return rc;
-      rc = sim_readpot_impl(s, st, kick_coef, drift_coef);
-      if (tm) tm->mark(st, "tile_scan+sim_readpot_kick_drift");
-      ++s->mode_steps[1];
-    } else if (s->force_mode != 0 && s->cur_mode == 1) {
+    const bool pot = s->force_mode != 0 && s->cur_mode == 1;
+    if (multi) {
+      // first barrier of the step (every rank has painted; ghost width agreed).  Behind it the global statistics of
+      // the previous step are complete in this rank's flag block: copy them out, then clear this step's slot
+      if ((rc = slab_barrier(p, st, true, pot ? 2 : 0))) return rc;
+      if (want_stats) {
+        unsigned* fl = p->slab.flags[p->slab.rank] + kFlagStats;
+        if (s->nstep >= 1) {
+          const int i = (int)((s->nstep - 1) % 3);
+          JPM_CUDA(cudaMemcpyAsync(s->stats_host + 4 * i, fl + 4 * ((s->nstep - 1) & 1), 16, cudaMemcpyDeviceToHost, st));
+          JPM_CUDA(cudaEventRecord(s->stats_ev[i], st));
+          s->stats_pending[i] = true;
+          s->stats_fixed[i] = true;
+        }
+        JPM_CUDA(cudaMemsetAsync(fl + 4 * (s->nstep & 1), 0, 16, st));
+      }
+    }
+    if (pot) {
       // potential chain: ONE inverse transform, then one real-space pass psi -> three force meshes
-      if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f, true))) return rc;
+      if ((rc = pmfft_potential(p, st, 0.f, nullptr, 0, 0.f, true, multi))) return rc;
       if ((rc = pmfft_gradient(p, st))) return rc;
       rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
                          drift_coef, true);
@@ -1668,18 +1327,24 @@ extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float
     } else {
       if (want_stats) JPM_CUDA(cudaMemsetAsync(p->pot_stats, 0, 4 * sizeof(double), st));
       p->want_sumsq = want_stats;
-      if ((rc = plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f))) return rc;
+      rc = p->fft_on ? pmfft_forces(p, st, 0.f, nullptr, 0, 0.f, multi) : plan_padded_forces(p, st, 0.f, nullptr, 0, 0.f);
       p->want_sumsq = false;
+      if (rc) return rc;
       rc = sim_read_impl(s, st, p->force3_p, p->force3_p + p->npad, p->force3_p + 2 * p->npad, kick_coef,
                          drift_coef, true);
       if (tm) tm->mark(st, "tile_scan+sim_read3_kick_drift");
       ++s->mode_steps[0];
     }
     if (rc == JPM_OK && want_stats) {
-      const int i = (int)(s->nstep % 3);
-      JPM_CUDA(cudaMemcpyAsync(s->stats_host + 4 * i, p->pot_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
-      JPM_CUDA(cudaEventRecord(s->stats_ev[i], st));
-      s->stats_pending[i] = true;
+      if (multi) {
+        rc = slab_stats_share(p, st, (int)(s->nstep & 1));
+      } else {
+        const int i = (int)(s->nstep % 3);
+        JPM_CUDA(cudaMemcpyAsync(s->stats_host + 4 * i, p->pot_stats, 4 * sizeof(double), cudaMemcpyDeviceToHost, st));
+        JPM_CUDA(cudaEventRecord(s->stats_ev[i], st));
+        s->stats_pending[i] = true;
+        s->stats_fixed[i] = false;
+      }
     }
     ++s->nstep;
     return rc;

@@ -260,7 +260,8 @@ class ShardedStepper:
         self.sim = None
 
 
-def make_stepper(disp, vel, halo_size, sh, resident=True, tile=None, margin=None, fused=True):
+def make_stepper(disp, vel, halo_size, sh, resident=True, tile=None, margin=None, fused=True,
+                 force_mode="spectral"):
     """The fastest stepper that serves this decomposition: the peer-memory slab stepper (slab.py: halo
     reduce / FFT transposes / halo fill inside the FFT kernels, no NCCL on the data path) for a (P, 1)
     process grid on power-of-two meshes, else the NCCL stepper above."""
@@ -271,13 +272,16 @@ def make_stepper(disp, vel, halo_size, sh, resident=True, tile=None, margin=None
     # reference's (|displacement| < halo // 2 is exchanged, painting.py:192-215)
     if fused and resident and slab.slab_supported(gshape, sh.pdims, hx):
         return slab.SlabStepper(disp, vel, hx, sh.size, sh.rank, group=sh.group, tile=tile,
-                                margin=1 if margin is None else margin)
+                                margin=1 if margin is None else margin, force_mode=force_mode)
+    if force_mode != "spectral":
+        raise NotImplementedError("force_mode != 'spectral' needs the fused slab path (pdims (P, 1), power-of-two mesh)")
     return ShardedStepper(disp, vel, halo_size, sh, resident=resident, tile=tile, margin=2 if margin is None else margin)
 
 
-def nbody_kick_drift(disp, vel, d, k, mesh_shape, halo_size, sh, callback=None, resident=True, fused=True):
+def nbody_kick_drift(disp, vel, d, k, mesh_shape, halo_size, sh, callback=None, resident=True, fused=True,
+                     force_mode="spectral"):
     """Sharded drift-kick loop (the first drift has already been applied by the caller)."""
-    st = make_stepper(disp, vel, halo_size, sh, resident=resident, fused=fused)
+    st = make_stepper(disp, vel, halo_size, sh, resident=resident, fused=fused, force_mode=force_mode)
     nsteps = len(k)
     for n in range(nsteps):
         st.step(k[n], d[n + 1] if n + 1 < nsteps else 0.0)

@@ -164,7 +164,8 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
     ops.axpby(1.0, pos, d[0], vel, out=pos)
     if not _single(sharding):
         from . import halo
-        return halo.nbody_kick_drift(pos, vel, d, k, mesh_shape, halo_size, sharding, callback, resident=resident)
+        return halo.nbody_kick_drift(pos, vel, d, k, mesh_shape, halo_size, sharding, callback, resident=resident,
+                                     force_mode=force_mode)
     if not resident:
         plan = ops.get_plan(mesh_shape, pos.device)
         for n in range(nsteps):
@@ -190,6 +191,51 @@ def nbody_kick_drift(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_abs
     if info is not None:
         info.update(sim.force_info())
         info["fallbacks"] = sim.fallback_counts()
+    return pos, vel
+
+
+class _DriftKickStep(torch.autograd.Function):
+    """One drift-kick step, pos' = pos + d vel ; vel' = vel + k F(pos'), differentiable with PER-STEP RECOMPUTE:
+    only pos' (12 B per particle) is kept; the backward pass re-runs the force evaluation at pos' and pulls the
+    cotangent through the hand-written adjoint kernels of pm_forces (paint^T = read, read^T = paint, the transposed
+    k-space pass, the position gradients of the CIC weights).  What diffrax's RecursiveCheckpointAdjoint does for
+    the reference's gradient runs (tests/test_gradients.py:27-28), at checkpoint granularity one step."""
+
+    @staticmethod
+    def forward(ctx, pos, vel, d, k, mesh_shape, relative):
+        pos1 = ops.axpby(1.0, pos, d, vel)
+        with torch.no_grad():
+            F = pm_forces(pos1, mesh_shape=mesh_shape, paint_absolute_pos=not relative)
+        vel1 = ops.axpby(1.0, vel, k, F)
+        ctx.save_for_backward(pos1)
+        ctx.cfg = (float(d), float(k), mesh_shape, relative)
+        return pos1, vel1
+
+    @staticmethod
+    def backward(ctx, g_pos1, g_vel1):
+        (pos1,) = ctx.saved_tensors
+        d, k, mesh_shape, relative = ctx.cfg
+        g_vel1 = g_vel1.contiguous()
+        with torch.enable_grad():
+            x = pos1.detach().requires_grad_(True)
+            F = pm_forces(x, mesh_shape=mesh_shape, paint_absolute_pos=not relative)
+            (gx,) = torch.autograd.grad(F, x, ops.axpby(k, g_vel1))
+        g_pos = ops.axpby(1.0, gx, 1.0, g_pos1.contiguous()) if g_pos1 is not None else gx
+        g_vel = ops.axpby(1.0, g_vel1, d, g_pos)
+        return g_pos, g_vel, None, None, None, None
+
+
+def nbody_kick_drift_grad(cosmo, pos, vel, a0, a1, nsteps, mesh_shape=None, paint_absolute_pos=True,
+                          scheme="symplectic"):
+    """The fixed-step drift-kick run of `nbody_kick_drift` as a DIFFERENTIABLE function of (pos, vel): reverse mode
+    through every step with per-step recompute (memory: one position array per step).  This is the driver of
+    BASELINE.json's config 5 (gradient of the final power spectrum with respect to the initial conditions)."""
+    pos, vel = as_f32(pos), as_f32(vel)
+    relative = not paint_absolute_pos
+    mesh_shape = tuple(pos.shape[:3]) if (mesh_shape is None or relative) else tuple(mesh_shape)
+    d, k = kick_drift_coefficients(cosmo, a0, a1, nsteps, scheme)
+    for n in range(nsteps):
+        pos, vel = _DriftKickStep.apply(pos, vel, float(d[n]), float(k[n]), mesh_shape, relative)
     return pos, vel
 
 

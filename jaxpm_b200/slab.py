@@ -128,7 +128,8 @@ class SlabStepper:
     rank's ghost-zone mesh + the fused peer-memory FFT chain.  Same contract as halo.ShardedStepper:
     identical to the reference for every particle within its halo reach (|disp_x| < gx)."""
 
-    def __init__(self, disp, vel, gx, nranks, rank, group=None, tile=None, margin=1, plan=None):
+    def __init__(self, disp, vel, gx, nranks, rank, group=None, tile=None, margin=1, plan=None,
+                 force_mode="spectral"):
         d = as_f32(disp)
         lx, ny, nz = d.shape[:3]
         self.device = d.device
@@ -141,6 +142,10 @@ class SlabStepper:
             tile = 16 if min(ms) >= 64 else 8
         self.sim = ops.Sim(ms, (lx, ny, nz), True, d.device, halo=(gx, 0), tile=tile, margin=margin,
                            plan=self.plan)
+        if force_mode != "spectral":
+            # "potential": one inverse transform + the gradient pass (psi ghosts over NVLink instead of three force
+            # meshes); "auto": per step from the GLOBAL error bound, the same decision on every rank
+            self.sim.set_force_mode(force_mode)
         self.sim.load(d, as_f32(vel))
 
     def load(self, disp, vel):
@@ -160,8 +165,8 @@ class SlabStepper:
     def step_profile(self, kick, drift):
         return self.sim.step_profile(kick, drift)
 
-    def timing_summary(self):
-        return None
+    def force_info(self):
+        return self.sim.force_info()
 
     def close(self, barrier=True):
         """Ranks must have finished using each other's memory before any block is freed."""

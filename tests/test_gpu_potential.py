@@ -54,17 +54,14 @@ def test_potential_chain(cuda, shape):
             assert rel_err(fd4(psi.astype(np.float64), d), fref) < 10 * tol, (d, r_split)
 
 
-@pytest.mark.parametrize("variant", ["pass", "fused"])
 @pytest.mark.parametrize("relative", [False, True])
 @pytest.mark.parametrize("shape,tile", [((32, 32, 32), 8), ((32, 64, 32), 16), ((64, 64, 64), 16)])
-def test_sim_step_potential(cuda, monkeypatch, relative, shape, tile, variant):
-    """K resident steps with the potential force path == spectral path == oracle, including particles at the
-    periodic edges (generic stencil inside the box) and beyond the margin (global-memory fallback).
-    variant "pass": one real-space pass psi -> three force meshes, then the ordinary read kernel;
-    variant "fused": the persistent read kernel differentiates the psi box of each tile in shared memory."""
+def test_sim_step_potential(cuda, relative, shape, tile):
+    """K resident steps with the potential force path (one inverse transform, one real-space gradient pass, the
+    ordinary read kernel) == spectral path == oracle, including particles at the periodic edges (generic stencil
+    inside the box) and beyond the margin (global-memory fallback)."""
     from jaxpm_b200.cosmology import Planck15
     from jaxpm_b200.ode import nbody_kick_drift
-    monkeypatch.setenv("JPM_POT_VARIANT", "1" if variant == "fused" else "0")
     grid, disp = displaced(shape, 1.0)
     x = disp if relative else grid + disp
     vel = (0.3 * np.random.default_rng(9).standard_normal(x.shape)).astype(np.float32)

@@ -61,11 +61,13 @@ def test_slab_forces_equal_single_gpu(cuda, shape, P, gx):
         p.destroy()
 
 
+@pytest.mark.parametrize("force_mode", ["spectral", "potential", "auto"])
 @pytest.mark.parametrize("shape,P,gx,tile", [((32, 32, 32), 2, 8, 8), ((64, 64, 64), 2, 16, 16), ((64, 32, 32), 4, 8, 8),
                                              ((32, 32, 32), 1, 8, 8)])
-def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile):
+def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile, force_mode):
     """K drift-kick steps of the slab stepper (ghost-fold / transposes / ghost-fill inside the FFT kernels)
-    == the single-GPU resident stepper on the same particles."""
+    == the single-GPU resident stepper on the same particles, for the three force paths (potential: psi ghost
+    planes + gradient pass per rank; auto: the ranks share their force statistics and switch together)."""
     from jaxpm_b200.cosmology import Planck15
     from jaxpm_b200.ode import kick_drift_coefficients, nbody_kick_drift
     from jaxpm_b200.slab import SlabStepper
@@ -74,7 +76,7 @@ def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile):
     disp = np.clip(disp, -gx / 2 + 0.5, gx / 2 - 0.5).astype(np.float32)
     vel = (0.2 * np.random.default_rng(9).standard_normal(disp.shape)).astype(np.float32)
     cosmo = Planck15()
-    K = 3
+    K = 7 if force_mode == "auto" else 3      # long enough for the lagged AUTO decision to switch the ranks over
     rp, rv = nbody_kick_drift(cosmo, T(disp, cuda), T(vel, cuda), 0.5, 0.8, K, paint_absolute_pos=False,
                               resident=True, tile=tile, margin=1)
     d, k = kick_drift_coefficients(cosmo, 0.5, 0.8, K, "symplectic")
@@ -89,10 +91,14 @@ def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile):
     steppers = []
     for r in range(P):
         with torch.cuda.stream(streams[r]):
-            steppers.append(SlabStepper(dl[r], vl[r], gx, P, r, tile=tile, margin=1, plan=plans[r]))
+            steppers.append(SlabStepper(dl[r], vl[r], gx, P, r, tile=tile, margin=1, plan=plans[r],
+                                        force_mode=force_mode))
     for n in range(K):
         for r in range(P):
             with torch.cuda.stream(streams[r]):
+                # several ranks driven by ONE host thread: the lagged AUTO decision waits for an earlier step of
+                # this rank, which needs the peers' kernels of that step to have been enqueued - they have, the
+                # ranks are stepped in lock step and the lag is >= 2 steps
                 steppers[r].step(k[n], d[n + 1] if n + 1 < K else 0.0)
     for r in range(P):
         with torch.cuda.stream(streams[r]):
@@ -102,6 +108,13 @@ def test_slab_stepper_equals_single_gpu(cuda, shape, P, gx, tile):
     v = torch.cat(vl).cpu().numpy()
     assert np.abs(p - rp.cpu().numpy()).max() < 2e-4
     assert rel_err(v, rv.cpu().numpy()) < 1e-4
+    infos = [s.force_info() for s in steppers]
+    if force_mode == "potential":
+        assert all(i["steps_potential"] == K for i in infos)
+    if force_mode == "auto":
+        # every rank took the same decisions (white-noise displacements: the bound is small, they switch over)
+        assert len({(i["steps_spectral"], i["steps_potential"]) for i in infos}) == 1, infos
+        assert infos[0]["steps_potential"] >= 1, infos
     for s in steppers:
         s.close(barrier=False)
 

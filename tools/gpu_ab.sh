@@ -5,7 +5,7 @@ TAG=$1; shift
 OUT=gpurun_out/$TAG
 mkdir -p $OUT
 if [ -n "$PYTEST_ARGS" ]; then
-  timeout 900 python -m pytest $PYTEST_ARGS -q > $OUT/pytest.log 2>&1; echo "== pytest rc=$?"; tail -n 8 $OUT/pytest.log
+  timeout 1200 python -m pytest $PYTEST_ARGS -q ${PYTEST_K:+-k "$PYTEST_K"} > $OUT/pytest.log 2>&1; echo "== pytest rc=$?"; tail -n 12 $OUT/pytest.log
 fi
 for spec in "$@"; do
   label=${spec%%:*}; rest=${spec#*:}; envs=${rest%%:*}; args=${rest#*:}
