@@ -107,6 +107,7 @@ struct jpm_plan {
   TmapPack* tm_at = nullptr;    // [d]: AT of rank d as {2 nzc, ly, nx} floats, box {32, min(ly,256), 1}
   TmapPack* tm_t01 = nullptr;   // [d]: T01 of rank d as {4 nzc, ny, lx} floats, box {32, 1, min(lx,256)}
   TmapPack* tm_b3 = nullptr;    // [d]: planar B3 of rank d as {2 nzc, ny, lx, 3} floats, box {16, 1, min(lx,256), 1}
+  TmapPack* tm_b3w = nullptr;   // same with 16-column boxes {32, 1, min(lx,256), 1}
   // potential chain (pmfft_potential): [0] sum_k |psi_k|^2 of the last evaluation (= mean_x psi^2), [1] bit pattern
   // of max |F| seen by the last read (atomicMax on the float bits), [2..3] spare.  Device doubles.
   double* pot_stats = nullptr;

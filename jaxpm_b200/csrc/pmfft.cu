@@ -1023,6 +1023,7 @@ template <int NZ> constexpr size_t z_smem() { return (size_t)(NZ / 2 + kRows * (
 
 constexpr int kColsC = 16;   // kz columns per tile of the Y-fwd pass (128-byte segments)
 constexpr int kXC = 8;       // ... of the X-fused and Y-inv passes (64-byte segments; data held in registers)
+constexpr int kXCW = 16;     // ... of the potential chain's x pass across NVLink (P > 1): 128-byte remote rows
 
 #define JPM_FFT_SWITCH(n, MACRO)          \
   switch (n) {                            \
@@ -1060,6 +1061,14 @@ static int32_t set_attrs(const Slab& sl) {
                                 (int)xpot_smem<N_, kXC>()));
   JPM_FFT_SWITCH(sl.nx, ATTR_XP)
 #undef ATTR_XP
+  if (sl.nx <= 512) {
+#define ATTR_XPW(N_)                                                                                            \
+  if constexpr (N_ <= 512)                                                                                      \
+    JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXCW, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                  (int)xpot_smem<N_, kXCW>()));
+    JPM_FFT_SWITCH(sl.nx, ATTR_XPW)
+#undef ATTR_XPW
+  }
 #define ATTR_X(N_)                                                                                              \
   JPM_CUDA(cudaFuncSetAttribute(xfused_kernel<N_, kXC, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                 (int)xfused_smem<N_, kXC>()));                                                  \
@@ -1124,9 +1133,11 @@ int32_t pmfft_setup(jpm_plan* p) {
       if (!p->tm_at) p->tm_at = new TmapPack();
       if (!p->tm_t01) p->tm_t01 = new TmapPack();
       if (!p->tm_b3) p->tm_b3 = new TmapPack();
+      if (!p->tm_b3w) p->tm_b3w = new TmapPack();
       memset(p->tm_at, 0, sizeof(TmapPack));
       memset(p->tm_t01, 0, sizeof(TmapPack));
       memset(p->tm_b3, 0, sizeof(TmapPack));
+      memset(p->tm_b3w, 0, sizeof(TmapPack));
       const unsigned long long row = (unsigned long long)sl.nzc * sizeof(float2);
       for (int d = 0; d < sl.P; ++d) {
         const unsigned long long da[3] = {2ull * sl.nzc, (unsigned long long)sl.ly, (unsigned long long)sl.nx};
@@ -1138,6 +1149,8 @@ int32_t pmfft_setup(jpm_plan* p) {
           const unsigned long long sb[3] = {row, row * sl.ny, row * sl.ny * sl.lx};
           const unsigned bb[4] = {2u * fft::kXC, 1u, (unsigned)std::min(sl.lx, 256), 1u};
           if ((rc = encode_tensor_map(&p->tm_b3->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bb))) return rc;
+          const unsigned bw[4] = {2u * fft::kXCW, 1u, (unsigned)std::min(sl.lx, 256), 1u};
+          if ((rc = encode_tensor_map(&p->tm_b3w->m[d], reinterpret_cast<float*>(sl.b3[d]), 4, db, sb, bw))) return rc;
         }
         if (p->fft_pair) {
           const unsigned long long dt[3] = {4ull * sl.nzc, (unsigned long long)sl.ny, (unsigned long long)sl.lx};
@@ -1195,6 +1208,7 @@ void pmfft_destroy(jpm_plan* p) {
   delete p->tm_at; p->tm_at = nullptr;
   delete p->tm_t01; p->tm_t01 = nullptr;
   delete p->tm_b3; p->tm_b3 = nullptr;
+  delete p->tm_b3w; p->tm_b3w = nullptr;
   if (p->pot_stats) cudaFree(p->pot_stats);
   p->pot_stats = nullptr;
   void* bufs[] = {p->fft_at, p->fft_b3, p->fft_t01, p->tw_x, p->tw_y, p->tw_zh, p->tw_zfull};
@@ -1357,8 +1371,16 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   JPM_LAUNCH_CHECK();
   if ((rc = slab_barrier(p, st))) return rc;
   if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
+  // across NVLink 64-byte rows run at about half the link rate: 16 columns per tile there (128-byte rows)
+  static const bool wide_env = !(getenv("JPM_XPOT_WIDE") && getenv("JPM_XPOT_WIDE")[0] == '0');
+  const bool wide = sl.P > 1 && p->fft_tma_store && sl.nx <= 512 && wide_env;
+  const int ntxw = (nzh + kXCW - 1) / kXCW;
 #define RUN_XP(N_)                                                                                             \
-  if (p->fft_tma_store)                                                                                        \
+  if (wide) {                                                                                                  \
+    if constexpr (N_ <= 512)                                                                                   \
+      xpot_kernel<N_, kXCW, true><<<dim3(ntxw, sl.ly, 1), threads_for<N_, kXCW, 8>(), xpot_smem<N_, kXCW>(), st>>>( \
+          sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, *p->tm_b3w, p->pot_stats); \
+  } else if (p->fft_tma_store)                                                                                 \
     xpot_kernel<N_, kXC, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>(  \
         sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats); \
   else                                                                                                         \

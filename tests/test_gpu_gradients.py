@@ -46,7 +46,7 @@ def test_chained_gradient_of_final_pk_wrt_initial_conditions(cuda, order):
         dx, p, _ = OPM.lpt(ocos, ic, a=a0, order=order)
         drift, kick = OO.symplectic_ode(shape, ocos, paint_absolute_pos=False)
         pos, _ = OO.semi_implicit_euler(drift, kick, dx, p, a0, a1, K)
-        return OU.power_spectrum(OP.cic_paint_dx(pos), box_shape=box, x64=True)[1]
+        return OU.power_spectrum(OP.cic_paint_dx(pos), box_shape=box, x64=False)[1]
 
     pk0 = oracle_pk(ic0)
     gw = rng.standard_normal(pk0.shape) / pk0          # weights of the scalar: sum_b gw_b P(k_b), every bin O(1)

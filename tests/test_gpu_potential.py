@@ -3,7 +3,7 @@
 * potential chain (csrc/pmfft.cu pmfft_potential): psi = IFFT(G delta_k / k^2) vs the float64 oracle, and the
   identity it rests on: the reference's gradient kernel i (8 sin w - sin 2w) / 6 (kernels.py:62-66) is the symbol
   of the 4th-order central difference, so D_d psi == IFFT(-gradient_kernel(d) * pot_k) (pm.py:54-56);
-* resident step with force_mode = potential / auto vs spectral vs the oracle (persistent read kernel, csrc/sim.cu);
+* resident step with force_mode = potential / auto vs spectral vs the oracle (gradient pass of csrc/pmfft.cu + the read kernel);
 * pm_forces on the tile kernels (jpm_sim_forces) vs the oracle and vs the order-preserving kernels.
 Tolerances as everywhere: fields 1e-5 relative (max-norm)."""
 import numpy as np

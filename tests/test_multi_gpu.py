@@ -61,7 +61,12 @@ def _worker(rank, world, port, pdims, shape, halo):
         disp = disp.clamp(-halo / 2 + 1.5, halo / 2 - 1.5)      # stay inside the halo reach for three more steps
         p_ref, v_ref = nbody_kick_drift(cosmo, disp.clone(), vel.clone(), 0.5, 0.8, 3, paint_absolute_pos=False,
                                         resident=False)
-        for kw in (dict(resident=True), dict(resident=False)):
+        variants = [dict(resident=True), dict(resident=False)]
+        if pdims[1] == 1 and shape[2] == 32:
+            # fused slab path: the potential chain (psi ghost planes over NVLink + gradient pass per rank) and AUTO
+            # (ranks add their force statistics into each other's flag blocks with system-scope atomics)
+            variants += [dict(resident=True, force_mode="potential"), dict(resident=True, force_mode="auto")]
+        for kw in variants:
             p, v = nbody_kick_drift(cosmo, blk(disp).clone(), blk(vel).clone(), 0.5, 0.8, 3, paint_absolute_pos=False,
                                     halo_size=halo, sharding=sh, **kw)
             assert float((p - blk(p_ref)).abs().max()) < 2e-4, (pdims, kw)
