@@ -130,6 +130,15 @@ int32_t jpm_cic_readgrad_f32(void* stream, float* value, float* grad, const floa
                              float grad_scale_scalar, int64_t np, int32_t nx, int32_t ny,
                              int32_t nz, int32_t hx, int32_t hy, int32_t relative);
 
+/* Forward mode (what jax.jvp / jacfwd of the paint produces, tests/test_distributed_pm.py:313-320): the tangent of
+ * the painted mesh for a position tangent `tangent[np][3]`,
+ *     mesh[c] += w_p * sum_d tangent[p][d] * d K(x_p - c) / d x_d      (transpose of jpm_cic_readgrad_f32).
+ * ACCUMULATES into `mesh`.  The JVP of a read is jpm_cic_readgrad_f32's gradient dotted with the tangent plus a plain
+ * read of the mesh tangent, so paint / read / pm_forces have both modes from the same four kernels. */
+int32_t jpm_cic_paintgrad_f32(void* stream, float* mesh, const float* pos_or_disp, const float* tangent,
+                              const float* weight, float weight_scalar, int64_t np, int32_t nx, int32_t ny,
+                              int32_t nz, int32_t hx, int32_t hy, int32_t relative);
+
 /* 2-D CIC paint of projected particles (light-cone density planes): mesh[nx][ny] += paint(pos2[np][2]) * weight[np]
  * (weight may be NULL = 1).  Replaces jaxpm/painting.py:131-158 (cic_paint_2d), same index / weight rule. */
 int32_t jpm_cic_paint_2d_f32(void* stream, float* mesh, const float* pos2, const float* weight, int64_t np,
@@ -339,6 +348,12 @@ int32_t jpm_sim_read_kick_drift(jpm_sim* sim, void* stream, const float* fx, con
  * particle order (the order of the arrays given to jpm_sim_load). */
 int32_t jpm_sim_forces(jpm_sim* sim, void* stream, float* out, float scale, float r_split,
                        const float* filter_tab, int32_t n_tab, float filter_kmax);
+/* Batched form (what jax.vmap over a leading axis of the positions lowers to, tests/test_distributed_pm.py:335-409):
+ * positions[nbatch][np][3] -> out[nbatch][np][3], element b == jpm_sim_load(pos_b) + jpm_sim_forces.  The batch
+ * shares the sim's meshes and plans (sequential on the stream; a batch element is a full-GPU workload). */
+int32_t jpm_sim_forces_batched(jpm_sim* sim, void* stream, const float* positions, float* out, int32_t nbatch,
+                               float scale, float r_split, const float* filter_tab, int32_t n_tab,
+                               float filter_kmax);
 /* One PM step on the resident state: memset, paint, R2C, greens-grad, 3x C2R, read+kick+drift. */
 int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_coef);
 /* One step end to end through HOST buffers (pinned or pageable) on the tile kernels: H2D pos / vel [np][3], tile sort,
@@ -373,6 +388,24 @@ int32_t jpm_sim_stats_host(jpm_sim* sim, void* stream, int64_t* out4_host);
 
 /* Number of kernels of THIS library launched since process start (for bench accounting). */
 int64_t jpm_kernel_launch_count(void);
+
+/* ------------------------------------------------------------------------
+ * Gaussian initial conditions on the device
+ *   replaces jaxpm/distributed.py:193-223 `normal_field` and jaxpm/pm.py:129-144 `linear_field`
+ * ---------------------------------------------------------------------- */
+/* N(0,1) white noise, local block [lx][ly][nz] at offset (ox, oy) of a global mesh with global_ny rows:
+ * Philox4x32-10 keyed by `seed`, counter = global index of the 4-cell group, Box-Muller.  The value of a cell
+ * depends only on (seed, stream_id, global cell index): a sharded call draws the single-device field (the reference
+ * draws one independent stream per device).  Not JAX's threefry stream. */
+int32_t jpm_normal_field_f32(void* stream, float* out, int32_t lx, int32_t ly, int32_t nz, int32_t ox, int32_t oy,
+                             int32_t global_ny, uint64_t seed, uint32_t stream_id);
+/* pm.py:134-143 on the fused FFT chain (power-of-two meshes): out = IFFT( FFT(white) * amp(|k_phys|) ) / Nc with
+ * k_phys^2 = sum_d (w_d kscale_d)^2 and amp tabulated linearly in log10 k on [log10_kmin, log10_kmax]
+ * (values sqrt(P(k) Nc / V)); the k = 0 mode is multiplied by dc_amp (sqrt(P(0) Nc / V), 0 for a power law).
+ * Three forward passes, the table multiply inside the x pass, three inverse passes: 40 B/cell of HBM traffic. */
+int32_t jpm_linear_field_f32(jpm_plan* plan, void* stream, const float* white, float* out, const float* tab,
+                             int32_t n_tab, float log10_kmin, float log10_kmax, float kscale_x, float kscale_y,
+                             float kscale_z, float dc_amp);
 
 /* ------------------------------------------------------------------------
  * small elementwise helpers (keep host-side glue off third-party ops)

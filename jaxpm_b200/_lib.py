@@ -22,6 +22,7 @@ SIGNATURES = {
     "jpm_device_info": ([C.c_char_p, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)], i32),
     "jpm_cic_paint_f32": ([vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint_dx_f32": ([vp, vp, vp, vp, f32, i32, i32, i32, i32, i32], i32),
+    "jpm_cic_paintgrad_f32": ([vp, vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint_2d_f32": ([vp, vp, vp, vp, i64, i32, i32], i32),
     "jpm_density_plane_f32": ([vp, vp, vp, i64, f32, C.c_double, C.c_double, i32], i32),
     "jpm_cic_cell_index_i32": ([vp, vp, vp, i64, i32, i32, i32, i32, i32, i32], i32),
@@ -72,6 +73,7 @@ SIGNATURES = {
     "jpm_sim_paint": ([vp, vp, vp], i32),
     "jpm_sim_read_kick_drift": ([vp, vp, vp, vp, vp, f32, f32], i32),
     "jpm_sim_forces": ([vp, vp, vp, f32, f32, vp, i32, f32], i32),
+    "jpm_sim_forces_batched": ([vp, vp, vp, vp, i32, f32, f32, vp, i32, f32], i32),
     "jpm_sim_step": ([vp, vp, f32, f32], i32),
     "jpm_sim_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32], i32),
     "jpm_sim_step_profile": ([vp, vp, f32, f32, C.POINTER(C.c_char_p), C.POINTER(f32), i32, C.POINTER(i32)], i32),
@@ -79,6 +81,8 @@ SIGNATURES = {
     "jpm_sim_set_force_mode": ([vp, i32], i32),
     "jpm_sim_force_info": ([vp, vp, C.POINTER(C.c_double)], i32),
     "jpm_kernel_launch_count": ([], i64),
+    "jpm_normal_field_f32": ([vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint32], i32),
+    "jpm_linear_field_f32": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),
     "jpm_axpby_f32": ([vp, vp, f32, vp, f32, vp, i64], i32),
     "jpm_grid_plus_disp_f32": ([vp, vp, vp, i32, i32, i32, i32, i32], i32),
     "jpm_fft1d_create": ([C.POINTER(vp), i32, i64, i32], i32),

@@ -56,6 +56,82 @@ box_kernel(float* __restrict__ mesh, float* __restrict__ buf, int ny, int nz, in
   }
 }
 
+// ---- counter-based Gaussian field generator ------------------------------------------------------------------
+// N(0,1) white noise for linear_field (jaxpm/pm.py:129-144 draws it with normal_field, distributed.py:193-223).
+// Philox4x32-10 (Salmon et al. 2011) keyed by the 64-bit seed, counter = (index of the 4-cell group, stream id):
+// cell c of the GLOBAL mesh always gets the same number, whatever the launch shape or the decomposition - a sharded
+// run therefore draws exactly the single-device field (the reference does not: one key per device,
+// distributed.py:204-215).  NOT JAX's threefry stream: a seed does not reproduce a JAX run (parity runs share the
+// IC array).  Box-Muller on (x + 0.5) 2^-32: no 0 / 1 arguments, |z| <= 6.66.
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0,
+                                              unsigned k1, unsigned out[4]) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(256)
+normal_field_kernel(float* __restrict__ out, int lx, int ly, int nz, int ox, int oy, int gny, unsigned seed_lo,
+                    unsigned seed_hi, unsigned stream_id) {
+  // local block [lx][ly][nz] of the global [*][gny][nz] mesh starting at (ox, oy, 0); 4 consecutive z cells per thread
+  const long long n4 = (long long)lx * ly * (nz / 4);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n4; t += stride) {
+    const int k4 = (int)(t % (nz / 4));
+    const long long r = t / (nz / 4);
+    const int j = (int)(r % ly), i = (int)(r / ly);
+    const unsigned long long g4 = ((unsigned long long)(i + ox) * gny + (j + oy)) * (nz / 4) + k4;   // global group index
+    unsigned x[4];
+    philox4x32_10((unsigned)g4, (unsigned)(g4 >> 32), stream_id, 0u, seed_lo, seed_hi, x);
+    float4 z;
+    {
+      const float u1 = ((float)(x[0] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(x[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z.x = rad * cs; z.y = rad * sn;
+    }
+    {
+      const float u1 = ((float)(x[2] >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(x[3] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+      const float rad = sqrtf(-2.0f * logf(u1));
+      float sn, cs;
+      sincospif(2.0f * u2, &sn, &cs);
+      z.z = rad * cs; z.w = rad * sn;
+    }
+    reinterpret_cast<float4*>(out)[t] = z;
+  }
+}
+
+// same numbers for row lengths that are not a multiple of 4: one cell per thread (group = global flat index / 4)
+__global__ void __launch_bounds__(256)
+normal_field_cell_kernel(float* __restrict__ out, int lx, int ly, int nz, int ox, int oy, int gny, unsigned seed_lo,
+                         unsigned seed_hi, unsigned stream_id) {
+  const long long n = (long long)lx * ly * nz;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const int k = (int)(t % nz);
+    const long long r = t / nz;
+    const int j = (int)(r % ly), i = (int)(r / ly);
+    const unsigned long long flat = ((unsigned long long)(i + ox) * gny + (j + oy)) * nz + k;
+    const unsigned long long g4 = flat >> 2;
+    const int e = (int)(flat & 3);
+    unsigned x[4];
+    philox4x32_10((unsigned)g4, (unsigned)(g4 >> 32), stream_id, 0u, seed_lo, seed_hi, x);
+    const unsigned a = x[e & 2], b = x[(e & 2) + 1];
+    const float u1 = ((float)(a >> 8) + 0.5f) * (1.0f / 16777216.0f), u2 = ((float)(b >> 8) + 0.5f) * (1.0f / 16777216.0f);
+    const float rad = sqrtf(-2.0f * logf(u1));
+    float sn, cs;
+    sincospif(2.0f * u2, &sn, &cs);
+    out[t] = rad * ((e & 1) ? sn : cs);
+  }
+}
+
 static int ew_grid(long long n) {
   long long blocks = (n + 255) / 256;
   const long long cap = (long long)kNumSMs * 16;
@@ -67,6 +143,23 @@ static int ew_grid(long long n) {
 using namespace jpm;
 
 extern "C" int32_t jpm_abi_version(void) { return JPM_ABI_VERSION; }
+
+extern "C" int32_t jpm_normal_field_f32(void* stream, float* out, int32_t lx, int32_t ly, int32_t nz, int32_t ox,
+                                        int32_t oy, int32_t global_ny, uint64_t seed, uint32_t stream_id) {
+  JPM_CHECK_ARG(out && lx > 0 && ly > 0 && nz > 0, "bad arguments");
+  JPM_CHECK_ARG(ox >= 0 && oy >= 0 && oy + ly <= global_ny, "block outside the global mesh");
+  const unsigned slo = (unsigned)(seed & 0xffffffffull), shi = (unsigned)(seed >> 32);
+  if (nz % 4 == 0) {
+    const long long n4 = (long long)lx * ly * (nz / 4);
+    normal_field_kernel<<<ew_grid(n4), 256, 0, (cudaStream_t)stream>>>(out, lx, ly, nz, ox, oy, global_ny, slo, shi,
+                                                                      stream_id);
+  } else {
+    normal_field_cell_kernel<<<ew_grid((long long)lx * ly * nz), 256, 0, (cudaStream_t)stream>>>(
+        out, lx, ly, nz, ox, oy, global_ny, slo, shi, stream_id);
+  }
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
 extern "C" const char* jpm_last_error_string(void) { return g_err; }
 extern "C" int64_t jpm_kernel_launch_count(void) { return g_launches.load(); }
 

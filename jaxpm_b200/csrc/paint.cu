@@ -46,6 +46,46 @@ paint_direct_kernel(float* __restrict__ mesh, const float* __restrict__ pos,
   }
 }
 
+// Forward mode of the paint with respect to the positions (what jax.jvp / jacfwd of painting.py:15-45 produces,
+// the transpose of readgrad_kernel): mesh[c] += w_p * sum_d v_{p,d} * dK/dx_d(p, c), dK/dx_d = -sign(x_d - c_d)
+// prod_{e != d} (1 - |x_e - c_e|), sign(0) = 0.  One particle per thread, 8 REDG.E.ADD.F32.
+template <bool REL>
+__global__ void __launch_bounds__(256)
+paintgrad_kernel(float* __restrict__ mesh, const float* __restrict__ pos, const float* __restrict__ tangent,
+                 const float* __restrict__ weight, float wscalar, long long np, int nx, int ny, int nz, int pny,
+                 int pnz, int hx, int hy) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+    int bi = 0, bj = 0, bk = 0;
+    if (REL) {
+      bk = (int)(p % pnz);
+      const long long t = p / pnz;
+      bj = (int)(t % pny) + hy;
+      bi = (int)(t / pny) + hx;
+    }
+    const Cic1 cx = cic_1d<REL, true>(bi, ld_stream(pos + 3 * p + 0), nx);
+    const Cic1 cy = cic_1d<REL, true>(bj, ld_stream(pos + 3 * p + 1), ny);
+    const Cic1 cz = cic_1d<REL, true>(bk, ld_stream(pos + 3 * p + 2), nz);
+    const float w = weight ? weight[p] : wscalar;
+    const float vx = w * ld_stream(tangent + 3 * p + 0), vy = w * ld_stream(tangent + 3 * p + 1),
+                vz = w * ld_stream(tangent + 3 * p + 2);
+    const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
+    const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
+    const float sx[2] = {cx.s0, cx.s1}, sy[2] = {cy.s0, cy.s1}, sz[2] = {cz.s0, cz.s1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
+          const float k = vx * ((sx[a] * wy[b]) * wz[c]) + vy * ((wx[a] * sy[b]) * wz[c]) +
+                          vz * ((wx[a] * wy[b]) * sz[c]);
+          atomicAdd(mesh + ((long long)ix[a] * ny + iy[b]) * nz + iz[c], k);
+        }
+  }
+}
+
 // 2-D CIC paint of a projected particle set (the density planes of a light cone): 4 REDG.E.ADD.F32 per particle.
 //   reference: jaxpm/painting.py:131-158 (cic_paint_2d): floor, +{0,1}, kernel = (1-|dx|)(1-|dy|) * weight,
 //   int32 cast, python mod.  A plane (<= a few MB) lives in L2, so the global reductions stay on chip.
@@ -166,6 +206,25 @@ extern "C" int32_t jpm_cic_paint_dx_f32(void* stream, float* mesh, const float* 
   JPM_CHECK_ARG((int64_t)mx * my * nz < (1ll << 31), "mesh too large for int32 cell ids");
   return launch_paint<true>((cudaStream_t)stream, mesh, disp, weight, weight_scalar,
                             (long long)nx * ny * nz, mx, my, nz, nx, ny, nz, hx, hy);
+}
+
+extern "C" int32_t jpm_cic_paintgrad_f32(void* stream, float* mesh, const float* pos_or_disp, const float* tangent,
+                                         const float* weight, float weight_scalar, int64_t np, int32_t nx,
+                                         int32_t ny, int32_t nz, int32_t hx, int32_t hy, int32_t relative) {
+  JPM_CHECK_ARG(mesh && pos_or_disp && tangent && np >= 0, "null pointer");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && hx >= 0 && hy >= 0, "bad shape / halo");
+  if (relative) JPM_CHECK_ARG((int64_t)(nx - 2 * hx) * (ny - 2 * hy) * nz == np, "np != particle grid");
+  if (np == 0) return JPM_OK;
+  long long blocks = (np + 255) / 256;
+  if (blocks > kNumSMs * 32) blocks = kNumSMs * 32;
+  if (relative)
+    paintgrad_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mesh, pos_or_disp, tangent, weight, weight_scalar,
+                                                                         np, nx, ny, nz, ny - 2 * hy, nz, hx, hy);
+  else
+    paintgrad_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mesh, pos_or_disp, tangent, weight, weight_scalar,
+                                                                          np, nx, ny, nz, ny, nz, hx, hy);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
 }
 
 extern "C" int32_t jpm_cic_cell_index_i32(void* stream, int32_t* out, const float* pos_or_disp,

@@ -417,6 +417,29 @@ extern "C" int32_t jpm_density_to_potential_fused(jpm_plan* p, void* stream, con
   return JPM_OK;
 }
 
+extern "C" int32_t jpm_linear_field_f32(jpm_plan* p, void* stream, const float* white, float* out, const float* tab,
+                                        int32_t n_tab, float log10_kmin, float log10_kmax, float kscale_x,
+                                        float kscale_y, float kscale_z, float dc_amp) {
+  JPM_CHECK_ARG(!(p && p->is_slab), "not available on a multi-GPU slab plan");
+  JPM_CHECK_ARG(p && white && out && tab && n_tab >= 2 && log10_kmax > log10_kmin, "bad arguments");
+  int32_t rc = plan_enable_padded(p);
+  if (rc) return rc;
+  JPM_CHECK_ARG(p->G > 0 && p->fft_on, "linear_field on the fused chain needs a power-of-two mesh");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = p->ncell / 4;
+  const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
+  JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
+  pad_copy_kernel<true><<<dim3(blocks, 1), 256, 0, st>>>(p->density_p, const_cast<float*>(white), p->nx, p->ny,
+                                                        p->nz / 4, p->nyp, p->nzp, p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  if ((rc = pmfft_linear_field(p, st, tab, n_tab, log10_kmin, log10_kmax, kscale_x, kscale_y, kscale_z, dc_amp)))
+    return rc;
+  pad_copy_kernel<false><<<dim3(blocks, 1), 256, 0, st>>>(p->psi_p, out, p->nx, p->ny, p->nz / 4, p->nyp, p->nzp,
+                                                         p->G, p->npad, p->ncell);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
 extern "C" int32_t jpm_plan_create(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz) {
   JPM_CHECK_ARG(out, "null plan pointer");
   JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0, "bad mesh shape");

@@ -135,8 +135,13 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t stream, float r_split, const floa
 int32_t slab_stats_share(jpm_plan* p, cudaStream_t stream, int slot);
 // to_psi = false: psi lands in force3_p component 0 (read by sim_readpot_kernel); true: in the separate psi mesh,
 // from which pmfft_gradient forms the three force meshes (4th-order differences) in force3_p.
+namespace fft { struct KColour; }
+// colour != nullptr: the x pass multiplies by the tabulated amplitude of linear_field instead of the Green's function
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t stream, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax, bool to_psi = false, bool skip_first_barrier = false);
+                        float filter_kmax, bool to_psi = false, bool skip_first_barrier = false,
+                        const fft::KColour* colour = nullptr);
+int32_t pmfft_linear_field(jpm_plan* p, cudaStream_t stream, const float* tab, int n_tab, float lkmin, float lkmax,
+                           float sx, float sy, float sz, float dc_amp);
 int32_t pmfft_gradient(jpm_plan* p, cudaStream_t stream);
 void pmfft_destroy(jpm_plan* p);
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no libcuda link dependency).

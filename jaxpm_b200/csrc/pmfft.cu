@@ -435,12 +435,15 @@ xfused_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, c
 // the tile box: one inverse transform instead of three, 40 instead of 72 B/cell through the five passes.
 // `sumsq` (nullable) accumulates sum_k |psi_k|^2 over the full spectrum = mean_x psi^2 (Parseval), the
 // numerator of the fp32 cancellation bound that decides between this chain and the three-transform one.
-template <int N, int C, bool TMAST>
+// KMODE 1 (linear_field, pm.py:134-143): the multiplier is amp(|k_phys|) * norm instead, k_phys^2 = sum_d (w_d s_d)^2,
+// amp tabulated linearly in log10 k (`ftab`, `ntab` entries from col.lkmin in steps of 1 / col.inv), k = 0 -> col.dc.
+struct KColour { float lkmin, inv, sx, sy, sz, dc; };
+template <int N, int C, bool TMAST, int KMODE = 0>
 __global__ void __launch_bounds__(threads_for<N, C, 8>(), (threads_for<N, C, 8>() <= 512 ? 2 : 1))
 xpot_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, const float* __restrict__ wx,
             const float* __restrict__ wy, const float* __restrict__ wz, float norm, float r_split2,
             const float* __restrict__ ftab, int ntab, float fscale, const __grid_constant__ TmapPack tp,
-            double* __restrict__ sumsq) {
+            double* __restrict__ sumsq, const KColour col) {
   constexpr int NT = threads_for<N, C, 8>();
   constexpr int L = radix_count(N);
   constexpr int RL = radix_at(N, L - 1, false);
@@ -471,16 +474,27 @@ xpot_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twg, con
 #pragma unroll
       for (int r = 0; r < RL; ++r) {
         const float kx = swx[j + r * (N / RL)];
-        const float kxy2 = kx * kx + ky * ky;
-        const float kk = kxy2 + kz * kz;
-        float g = (kk == 0.f) ? 0.f : __frcp_rn(kk);
-        g *= norm;
-        if (r_split2 != 0.f) g *= expf(-kk * r_split2);
-        if (ftab) {
-          const float t = sqrtf(kk) * fscale;
+        float g;
+        if constexpr (KMODE == 1) {
+          const float px = kx * col.sx, py = ky * col.sy, pz = kz * col.sz;
+          const float kk = (px * px + py * py) + pz * pz;
+          float t = (kk > 0.f) ? (0.5f * log10f(kk) - col.lkmin) * col.inv : 0.f;
+          t = fminf(fmaxf(t, 0.f), (float)(ntab - 1));
           const int ti = min((int)t, ntab - 2);
-          const float fr = fminf(t - (float)ti, 1.0f);
-          g *= ftab[ti] + fr * (ftab[ti + 1] - ftab[ti]);
+          const float fr = t - (float)ti;
+          g = (kk > 0.f) ? (ftab[ti] + fr * (ftab[ti + 1] - ftab[ti])) * norm : col.dc * norm;
+        } else {
+          const float kxy2 = kx * kx + ky * ky;
+          const float kk = kxy2 + kz * kz;
+          g = (kk == 0.f) ? 0.f : __frcp_rn(kk);
+          g *= norm;
+          if (r_split2 != 0.f) g *= expf(-kk * r_split2);
+          if (ftab) {
+            const float t = sqrtf(kk) * fscale;
+            const int ti = min((int)t, ntab - 2);
+            const float fr = fminf(t - (float)ti, 1.0f);
+            g *= ftab[ti] + fr * (ftab[ti + 1] - ftab[ti]);
+          }
         }
         keep[i][r].x *= g;
         keep[i][r].y *= g;
@@ -871,57 +885,66 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 // in y and z are periodic images inside the padded array (index -/+ n), in x too when P == 1; the x planes of a
 // slab beyond what the neighbours filled hold nothing a particle within the halo reach reads.
 // HBM: 4 B/cell read + 12 B/cell written; the +-2 planes / rows are L2 / L1 hits.
+constexpr int kGradPlanes = 8;      // x planes per thread: the +-2 x neighbours slide through registers
 __global__ void __launch_bounds__(256)
 fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi, unsigned* __restrict__ fmax_bits) {
   const int nzp = sl.nzp, nyp = sl.nyp, nz4 = nzp / 4;
   const int z4 = blockIdx.x * 32 + (threadIdx.x & 31);
   const int yp = blockIdx.y * 8 + (threadIdx.x >> 5);
-  const int xp = x_lo + blockIdx.z;
+  int xb = x_lo + blockIdx.z * kGradPlanes, xe = min(xb + kGradPlanes, x_hi);
+  const int nxl = sl.lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
   if (sl.P > 1) {
     // planes the particles of this step reach: the slab + ghost_width planes per side (+-2 more hold psi)
     const int ge = ghost_width(sl);
-    if (xp < sl.gx - ge || xp >= sl.gx + sl.lx + ge) return;
+    xb = max(xb, sl.gx - ge);
+    xe = min(xe, sl.gx + sl.lx + ge);
   }
-  if (z4 >= nz4 || yp >= nyp) return;       // whole warps: z4 is the lane index, nz4 - 32 * blockIdx.x is checked per lane
-  const float* __restrict__ ps = sl.psi[sl.rank];
-  const long long sx = (long long)nyp * nzp;
-  const int nxl = sl.lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
-  auto wrapy = [&](int j) { return j < 0 ? j + sl.ny : (j >= nyp ? j - sl.ny : j); };
+  if (z4 >= nz4 || yp >= nyp || xb >= xe) return;   // lanes run along z: a warp exits (or shrinks) as a unit per row
+  const float4* __restrict__ ps = reinterpret_cast<const float4*>(sl.psi[sl.rank]);
+  const long long sx4 = (long long)nyp * nz4;        // plane stride in float4
+  // periodic images inside the padded array: index -/+ n (x too when P == 1; a slab's outermost planes hold
+  // nothing a particle within the halo reach reads, clamp there)
+  const int ym1 = yp >= 1 ? yp - 1 : yp - 1 + sl.ny, ym2 = yp >= 2 ? yp - 2 : yp - 2 + sl.ny;
+  const int yp1 = yp + 1 < nyp ? yp + 1 : yp + 1 - sl.ny, yp2 = yp + 2 < nyp ? yp + 2 : yp + 2 - sl.ny;
+  const int zl = z4 > 0 ? z4 - 1 : z4 - 1 + sl.nz / 4, zh = z4 + 1 < nz4 ? z4 + 1 : z4 + 1 - sl.nz / 4;
   auto wrapx = [&](int i) {
     if (sl.P == 1) return i < 0 ? i + sl.nx : (i >= nxl ? i - sl.nx : i);
     return min(max(i, 0), nxl - 1);
   };
-  const float* row = ps + (long long)xp * sx + (long long)yp * nzp;
-  const float4 c = *reinterpret_cast<const float4*>(row + 4 * z4);
-  // z neighbours: the float4 below / above (periodic images inside the padded row)
-  const int zl = z4 > 0 ? z4 - 1 : z4 - 1 + sl.nz / 4, zh = z4 + 1 < nz4 ? z4 + 1 : z4 + 1 - sl.nz / 4;
-  const float4 a = *reinterpret_cast<const float4*>(row + 4 * zl);
-  const float4 b = *reinterpret_cast<const float4*>(row + 4 * zh);
+  const long long o_c = (long long)yp * nz4 + z4;
+  const long long o_ym1 = (long long)ym1 * nz4 + z4, o_ym2 = (long long)ym2 * nz4 + z4;
+  const long long o_yp1 = (long long)yp1 * nz4 + z4, o_yp2 = (long long)yp2 * nz4 + z4;
+  const long long o_zl = (long long)yp * nz4 + zl, o_zh = (long long)yp * nz4 + zh;
   constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
-  float4 fz;
-  fz.x = c8 * (c.y - a.w) - c1 * (c.z - a.z);
-  fz.y = c8 * (c.z - c.x) - c1 * (c.w - a.w);
-  fz.z = c8 * (c.w - c.y) - c1 * (b.x - c.x);
-  fz.w = c8 * (b.x - c.z) - c1 * (b.y - c.y);
-  auto ld = [&](int i, int j) {
-    return *reinterpret_cast<const float4*>(ps + (long long)i * sx + (long long)j * nzp + 4 * z4);
-  };
-  const float4 y1 = ld(xp, wrapy(yp + 1)), y_1 = ld(xp, wrapy(yp - 1)), y2 = ld(xp, wrapy(yp + 2)), y_2 = ld(xp, wrapy(yp - 2));
-  const float4 x1 = ld(wrapx(xp + 1), yp), x_1 = ld(wrapx(xp - 1), yp), x2 = ld(wrapx(xp + 2), yp), x_2 = ld(wrapx(xp - 2), yp);
-  float4 fx, fy;
-  fx.x = c8 * (x1.x - x_1.x) - c1 * (x2.x - x_2.x); fx.y = c8 * (x1.y - x_1.y) - c1 * (x2.y - x_2.y);
-  fx.z = c8 * (x1.z - x_1.z) - c1 * (x2.z - x_2.z); fx.w = c8 * (x1.w - x_1.w) - c1 * (x2.w - x_2.w);
-  fy.x = c8 * (y1.x - y_1.x) - c1 * (y2.x - y_2.x); fy.y = c8 * (y1.y - y_1.y) - c1 * (y2.y - y_2.y);
-  fy.z = c8 * (y1.z - y_1.z) - c1 * (y2.z - y_2.z); fy.w = c8 * (y1.w - y_1.w) - c1 * (y2.w - y_2.w);
-  float* out = sl.force[sl.rank] + (long long)xp * sx + (long long)yp * nzp + 4 * z4;
-  __stcs(reinterpret_cast<float4*>(out), fx);
-  __stcs(reinterpret_cast<float4*>(out + sl.npad), fy);
-  __stcs(reinterpret_cast<float4*>(out + 2 * sl.npad), fz);
+  float4 x_2 = ps[wrapx(xb - 2) * sx4 + o_c], x_1 = ps[wrapx(xb - 1) * sx4 + o_c];
+  float4 c = ps[xb * sx4 + o_c], x1 = ps[wrapx(xb + 1) * sx4 + o_c];
+  float m = 0.f;
+  float* outp = sl.force[sl.rank] + 4 * ((long long)xb * sx4 + o_c);
+  for (int xp = xb; xp < xe; ++xp) {
+    const float4* pl = ps + xp * sx4;
+    const float4 x2 = ps[wrapx(xp + 2) * sx4 + o_c];
+    const float4 y1 = pl[o_yp1], y_1 = pl[o_ym1], y2 = pl[o_yp2], y_2 = pl[o_ym2];
+    const float4 a = pl[o_zl], b = pl[o_zh];
+    float4 fx, fy, fz;
+    fx.x = c8 * (x1.x - x_1.x) - c1 * (x2.x - x_2.x); fx.y = c8 * (x1.y - x_1.y) - c1 * (x2.y - x_2.y);
+    fx.z = c8 * (x1.z - x_1.z) - c1 * (x2.z - x_2.z); fx.w = c8 * (x1.w - x_1.w) - c1 * (x2.w - x_2.w);
+    fy.x = c8 * (y1.x - y_1.x) - c1 * (y2.x - y_2.x); fy.y = c8 * (y1.y - y_1.y) - c1 * (y2.y - y_2.y);
+    fy.z = c8 * (y1.z - y_1.z) - c1 * (y2.z - y_2.z); fy.w = c8 * (y1.w - y_1.w) - c1 * (y2.w - y_2.w);
+    fz.x = c8 * (c.y - a.w) - c1 * (c.z - a.z);
+    fz.y = c8 * (c.z - c.x) - c1 * (c.w - a.w);
+    fz.z = c8 * (c.w - c.y) - c1 * (b.x - c.x);
+    fz.w = c8 * (b.x - c.z) - c1 * (b.y - c.y);
+    __stcs(reinterpret_cast<float4*>(outp), fx);
+    __stcs(reinterpret_cast<float4*>(outp + sl.npad), fy);
+    __stcs(reinterpret_cast<float4*>(outp + 2 * sl.npad), fz);
+    outp += 4 * sx4;
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(fx.x), fabsf(fx.y)), fmaxf(fabsf(fx.z), fabsf(fx.w))),
+                       fmaxf(fmaxf(fabsf(fy.x), fabsf(fy.y)), fmaxf(fabsf(fy.z), fabsf(fy.w)))));
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(fz.x), fabsf(fz.y)), fmaxf(fabsf(fz.z), fabsf(fz.w))));
+    x_2 = x_1; x_1 = c; c = x1; x1 = x2;
+  }
   if (fmax_bits) {
     // largest force component on the mesh: denominator of the fp32 cancellation bound (csrc/sim.cu, AUTO mode)
-    float m = fmaxf(fmaxf(fmaxf(fabsf(fx.x), fabsf(fx.y)), fmaxf(fabsf(fx.z), fabsf(fx.w))),
-                    fmaxf(fmaxf(fabsf(fy.x), fabsf(fy.y)), fmaxf(fabsf(fy.z), fabsf(fy.w))));
-    m = fmaxf(m, fmaxf(fmaxf(fabsf(fz.x), fabsf(fz.y)), fmaxf(fabsf(fz.z), fabsf(fz.w))));
     const unsigned act = __activemask();
     const unsigned mb = __reduce_max_sync(act, __float_as_uint(m));
     if ((threadIdx.x & 31) == (__ffs(act) - 1) && mb > *fmax_bits) atomicMax(fmax_bits, mb);
@@ -1058,6 +1081,8 @@ static int32_t set_attrs(const Slab& sl) {
   JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,       \
                                 (int)xpot_smem<N_, kXC>()));                                                    \
   JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,        \
+                                (int)xpot_smem<N_, kXC>()));                                                    \
+  JPM_CUDA(cudaFuncSetAttribute(xpot_kernel<N_, kXC, false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,    \
                                 (int)xpot_smem<N_, kXC>()));
   JPM_FFT_SWITCH(sl.nx, ATTR_XP)
 #undef ATTR_XP
@@ -1331,7 +1356,7 @@ int32_t slab_stats_share(jpm_plan* p, cudaStream_t st, int slot) {
 // (+2 planes for the read kernel's difference stencil).  Same passes / barriers as pmfft_forces with ONE
 // spectrum through the inverse half: 8 + 8 + 8 + 8 + 8 = 40 B/cell instead of 72.
 int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float* filter_tab, int n_tab,
-                        float filter_kmax, bool to_psi, bool skip_first_barrier) {
+                        float filter_kmax, bool to_psi, bool skip_first_barrier, const fft::KColour* colour) {
   using namespace fft;
   JPM_CHECK_ARG(p->fft_on, "pmfft not enabled for this plan");
   if (to_psi && !p->slab.psi[p->slab.rank]) {
@@ -1373,19 +1398,23 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   if (p->timer) p->timer->mark(st, "fft_y_fwd+transpose");
   // across NVLink 64-byte rows run at about half the link rate: 16 columns per tile there (128-byte rows)
   static const bool wide_env = !(getenv("JPM_XPOT_WIDE") && getenv("JPM_XPOT_WIDE")[0] == '0');
-  const bool wide = sl.P > 1 && p->fft_tma_store && sl.nx <= 512 && wide_env;
+  const bool wide = sl.P > 1 && p->fft_tma_store && sl.nx <= 512 && wide_env && !colour;
+  const KColour kc = colour ? *colour : KColour{0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int ntxw = (nzh + kXCW - 1) / kXCW;
 #define RUN_XP(N_)                                                                                             \
   if (wide) {                                                                                                  \
     if constexpr (N_ <= 512)                                                                                   \
       xpot_kernel<N_, kXCW, true><<<dim3(ntxw, sl.ly, 1), threads_for<N_, kXCW, 8>(), xpot_smem<N_, kXCW>(), st>>>( \
-          sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, *p->tm_b3w, p->pot_stats); \
-  } else if (p->fft_tma_store)                                                                                 \
+          sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, *p->tm_b3w, p->pot_stats, kc); \
+  } else if (colour)                                                                                           \
+    xpot_kernel<N_, kXC, false, 1><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>( \
+        sl, p->tw_x, p->wx, p->wy, p->wz, norm, 0.f, filter_tab, n_tab, 0.f, tb3, p->pot_stats, kc);           \
+  else if (p->fft_tma_store)                                                                                   \
     xpot_kernel<N_, kXC, true><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>(  \
-        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats); \
+        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats, kc); \
   else                                                                                                         \
     xpot_kernel<N_, kXC, false><<<dim3(ntx, sl.ly, 1), threads_for<N_, kXC, 8>(), xpot_smem<N_, kXC>(), st>>>( \
-        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats);
+        sl, p->tw_x, p->wx, p->wy, p->wz, norm, r_split * r_split, filter_tab, n_tab, fscale, tb3, p->pot_stats, kc);
   JPM_FFT_SWITCH(sl.nx, RUN_XP)
 #undef RUN_XP
   JPM_LAUNCH_CHECK();
@@ -1409,13 +1438,21 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   return JPM_OK;
 }
 
+// density_p (holding white noise) -> psi mesh = IFFT(FFT(white) amp(|k_phys|)) / Nc: linear_field on the chain
+int32_t pmfft_linear_field(jpm_plan* p, cudaStream_t st, const float* tab, int n_tab, float lkmin, float lkmax,
+                           float sx, float sy, float sz, float dc_amp) {
+  const fft::KColour kc{lkmin, (float)(n_tab - 1) / (lkmax - lkmin), sx, sy, sz, dc_amp};
+  return pmfft_potential(p, st, 0.f, tab, n_tab, 0.f, true, false, &kc);
+}
+
 // psi mesh (ghosts filled by pmfft_potential(to_psi)) -> force3_p, ghost cells included.
 int32_t pmfft_gradient(jpm_plan* p, cudaStream_t st) {
   const Slab& sl = p->slab;
   JPM_CHECK_ARG(sl.psi[sl.rank], "no psi mesh (run pmfft_potential(to_psi) first)");
   const int nxl = sl.lx + 2 * sl.gx;
   unsigned* fmax_bits = p->pot_stats ? reinterpret_cast<unsigned*>(p->pot_stats + 1) : nullptr;
-  fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, nxl), 256, 0, st>>>(sl, 0, nxl, fmax_bits);
+  fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, (nxl + fft::kGradPlanes - 1) / fft::kGradPlanes), 256, 0, st>>>(
+      sl, 0, nxl, fmax_bits);
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "fd_gradient");
   return JPM_OK;

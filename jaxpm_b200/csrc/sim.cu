@@ -1272,6 +1272,20 @@ extern "C" int32_t jpm_sim_forces(jpm_sim* s, void* stream, float* out, float sc
   return JPM_OK;
 }
 
+extern "C" int32_t jpm_sim_forces_batched(jpm_sim* s, void* stream, const float* positions, float* out,
+                                          int32_t nbatch, float scale, float r_split, const float* filter_tab,
+                                          int32_t n_tab, float filter_kmax) {
+  JPM_CHECK_ARG(s && positions && out && nbatch >= 0, "bad arguments");
+  JPM_CHECK_ARG(s->pos_only, "jpm_sim_forces_batched takes a JPM_SIM_POSITIONS_ONLY sim");
+  for (int b = 0; b < nbatch; ++b) {
+    int32_t rc = jpm_sim_load(s, stream, positions + (size_t)b * 3 * s->np, nullptr);
+    if (rc) return rc;
+    if ((rc = jpm_sim_forces(s, stream, out + (size_t)b * 3 * s->np, scale, r_split, filter_tab, n_tab, filter_kmax)))
+      return rc;
+  }
+  return JPM_OK;
+}
+
 extern "C" int32_t jpm_sim_step(jpm_sim* s, void* stream, float kick_coef, float drift_coef) {
   JPM_CHECK_ARG(s && s->plan, "sim has no FFT plan attached");
   JPM_CHECK_ARG(!s->pos_only, "a JPM_SIM_POSITIONS_ONLY sim cannot step");

@@ -154,15 +154,23 @@ def uniform_particles(mesh_shape, sharding=None, device="cuda"):
     return ops.grid_plus_disp(zeros, (ox, oy))
 
 
-def normal_field(seed, shape, sharding=None, dtype=torch.float32, device="cuda"):
-    """N(0,1) field (local block when sharded).  As in the reference (distributed.py:204-215)
-    a sharded call draws one independent stream per rank, so the same seed gives different
-    fields for different process grids; parity runs must share one IC array."""
+def normal_field(seed, shape, sharding=None, dtype=torch.float32, device="cuda", stream_id=0):
+    """N(0,1) field (local block when sharded) from the device generator jpm_normal_field_f32: counter-based
+    (Philox4x32-10 keyed by `seed`, counter = global cell group), so the value of a cell depends only on
+    (seed, global cell index).  Unlike the reference (distributed.py:204-215: one independent key per device) a
+    sharded call draws exactly the single-device field.  Not JAX's threefry stream: the same seed does not
+    reproduce a JAX run; parity runs share the IC array (`white_noise=` of linear_field)."""
+    from ._lib import call, ptr, stream
+    shape = tuple(int(n) for n in shape)
+    if len(shape) != 3:
+        raise NotImplementedError("normal_field: 3-D meshes (the force-loop path)")
     loc = get_local_shape(shape, sharding)
-    g = torch.Generator(device=device)
-    rank = 0 if _single(sharding) else sharding.rx + sharding.ry * sharding.pdims[0]
-    g.manual_seed(int(seed) * 1000003 + rank)
-    return torch.randn(loc, generator=g, dtype=dtype, device=device)
+    ox = 0 if _single(sharding) else sharding.rx * loc[0]
+    oy = 0 if _single(sharding) else sharding.ry * loc[1]
+    out = torch.empty(tuple(loc), dtype=torch.float32, device=device)
+    call("jpm_normal_field_f32", stream(), ptr(out), loc[0], loc[1], loc[2], ox, oy, shape[1],
+         int(seed) & 0xFFFFFFFFFFFFFFFF, int(stream_id))
+    return out if dtype == torch.float32 else out.to(dtype)
 
 
 # ---- halo protocol (multi-GPU; implemented in jaxpm_b200/halo.py) -----------------------

@@ -294,6 +294,16 @@ def kfilter_logtab(spec, plan, tab, log10_kmin, log10_kmax, kscale, norm=1.0):
     return out
 
 
+def linear_field_fused(white, plan, tab, log10_kmin, log10_kmax, kscale, dc_amp):
+    """pm.py:134-143 on the fused FFT chain: IFFT(FFT(white) * tab(|k_phys|)) / Nc, k = 0 times dc_amp."""
+    w = as_f32(white)
+    t = as_f32(tab, w.device).reshape(-1)
+    out = torch.empty(plan.shape, dtype=torch.float32, device=w.device)
+    call("jpm_linear_field_f32", plan.handle, stream(), ptr(w), ptr(out), ptr(t), t.numel(), float(log10_kmin),
+         float(log10_kmax), float(kscale[0]), float(kscale[1]), float(kscale[2]), float(dc_amp))
+    return out
+
+
 def axpby(a, x, b=0.0, y=None, out=None):
     x = as_f32(x)
     y = None if y is None else as_f32(y, x.device)

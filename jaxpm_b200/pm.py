@@ -230,13 +230,21 @@ def linear_field(mesh_shape, box_size, pk, seed, sharding=None, white_noise=None
     kmax = np.sqrt(sum((np.pi * s)**2 for s in kscale)) * 1.001
     kmin = 2 * np.pi / max(box_size) * 0.999
     lk = np.linspace(np.log10(kmin), np.log10(kmax), 16384)
-    amp = np.sqrt(np.asarray(pk(10.0**lk), dtype=np.float64) * np.prod(mesh_shape) / np.prod(box_size))
+    scale = np.prod(mesh_shape) / np.prod(box_size)
+    amp = np.sqrt(np.asarray(pk(10.0**lk), dtype=np.float64) * scale)
+    # the k = 0 mode is multiplied by sqrt(P(0) Nc / V) like every other mode (pm.py:141-143); 0 where P(0) is not finite
+    with np.errstate(all="ignore"):
+        p0 = np.asarray(pk(np.zeros(1)), dtype=np.float64).reshape(-1)[0]
+    dc = float(np.sqrt(p0 * scale)) if np.isfinite(p0) and p0 >= 0 else 0.0
+    if ops.fast_path_shape(mesh_shape) and _FAST_API:
+        # three forward passes, the amplitude table inside the x pass, three inverse passes (csrc/pmfft.cu)
+        return ops.linear_field_fused(field, plan, amp.astype(np.float32), lk[0], lk[-1], kscale, dc)
     spec = ops.rfft3(field, plan)
-    spec = ops.kfilter_logtab(spec, plan, amp.astype(np.float32), lk[0], lk[-1], kscale,
-                              1.0 / plan.ncell)
-    # k = 0 takes the table's first entry; the reference multiplies the DC mode by sqrt(P(0));
-    # white noise has DC ~ N(0, Nc) so this only shifts the mean — set it from pk(0) if finite.
-    return ops.irfft3_(spec, plan, 1)
+    spec = ops.kfilter_logtab(spec, plan, amp.astype(np.float32), lk[0], lk[-1], kscale, 1.0 / plan.ncell)
+    out = ops.irfft3_(spec, plan, 1)
+    # the table pass gives k = 0 the first table entry: put sqrt(P(0) Nc / V) there instead (a constant shift)
+    mean = field.mean()
+    return out + (dc - float(amp[0])) * mean
 
 
 def pgd_correction(pos, mesh_shape, params):
