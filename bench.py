@@ -430,6 +430,59 @@ def run_gpu(args):
         }))
 
 
+def run_grad(args):
+    """BASELINE.json config 5: reverse-mode gradient of the final matter power spectrum with respect to the initial
+    conditions (SIZE^3 particles / mesh, default 256^3): ic -> lpt -> K drift-kick steps (per-step recompute) ->
+    cic_paint_dx -> power_spectrum -> scalar -> backward.  One JSON line: forward+backward particle-steps/s."""
+    import numpy as np
+    import torch
+    from jaxpm_b200 import _lib
+    from jaxpm_b200.cosmology import Planck15, linear_matter_power
+    from jaxpm_b200.ode import nbody_kick_drift_grad
+    from jaxpm_b200.painting import cic_paint_dx
+    from jaxpm_b200.pm import linear_field, lpt
+    from jaxpm_b200.utils import power_spectrum
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback)"
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    N, K = args.size, args.steps
+    shape, box = (N, N, N), (float(N),) * 3
+    cosmo = Planck15()
+    ic0 = linear_field(shape, box, lambda k: linear_matter_power(cosmo, k), seed=0, device=dev)
+
+    def run():
+        ic = ic0.clone().requires_grad_(True)
+        dx, p, _ = lpt(cosmo, ic, a=0.1, order=args.lpt_order)
+        pos, vel = nbody_kick_drift_grad(cosmo, dx, p, 0.1, 1.0, K, paint_absolute_pos=False)
+        _, pk = power_spectrum(cic_paint_dx(pos), box_shape=box)
+        loss = pk.log().sum()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        loss.backward()
+        torch.cuda.synchronize()
+        return ic.grad, float(loss), t1
+
+    run()   # warm
+    torch.cuda.reset_peak_memory_stats()
+    l0 = _lib.launch_count()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    grad, loss, t1 = run()
+    t2 = time.perf_counter()
+    npart = N**3
+    print(json.dumps({
+        "metric": "reverse_mode_pm_particle_steps_per_sec", "value": npart * K / (t2 - t0), "unit": UNIT, "n_gpus": 1,
+        "steps": K, "forward_ms": (t1 - t0) * 1e3, "backward_ms": (t2 - t1) * 1e3, "higher_is_better": True,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"d sum_b log P(k_b) / d initial_conditions: {N}^3 particles on {N}^3 mesh, "
+                               f"{args.lpt_order}LPT at a=0.1, {K} drift-kick steps to a=1 (per-step recompute), "
+                               "cic_paint_dx, power_spectrum; adjoint kernels: readgrad, weighted paint, transposed "
+                               "k-space passes, 2LPT source VJP, P(k) adjoint"},
+        "gpu_launches": _lib.launch_count() - l0, "loss": loss, "grad_rms": float(grad.square().mean().sqrt()),
+        "grad_finite": bool(torch.isfinite(grad).all()), "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
+    }))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -443,6 +496,8 @@ def main():
                          "difference stencil, or per step by the measured fp32 error bound")
     ap.add_argument("--lpt-order", type=int, default=2, choices=[1, 2], help="LPT order of the initial state")
     ap.add_argument("--no-parity", action="store_true", help="skip the P(k) parity leg")
+    ap.add_argument("--grad", action="store_true",
+                    help="BASELINE.json config 5 instead: reverse-mode gradient of the final P(k) w.r.t. the ICs (use --size 256)")
     ap.add_argument("--no-e2e-run", dest="e2e_run", action="store_false", help="skip the run-level end-to-end leg")
     ap.add_argument("--tile", type=int, default=16)
     ap.add_argument("--margin", type=int, default=1)
@@ -460,6 +515,8 @@ def main():
         args.warmup = 3
     if args.impl == "reference":
         return run_reference(args)
+    if args.grad:
+        return run_grad(args)
     return run_gpu(args)
 
 

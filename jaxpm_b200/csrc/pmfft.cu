@@ -956,7 +956,8 @@ fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi, unsigned* __r
 // waits until its own slots all reach `epoch`.  One CTA, one thread per peer.  A lost peer trips the
 // timeout (~4 s) and raises the error word instead of hanging the GPU.
 template <bool GHOSTW>
-__global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch, int reach_extra) {
+__global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned epoch, int reach_extra,
+                                    long long timeout_cycles) {
   const int t = threadIdx.x;
   __threadfence_system();
   if (t < sl.P) {
@@ -982,7 +983,7 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
     do {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
       if ((int)(v - epoch) >= 0) break;
-      if (clock64() - t0 > 8000000000ll) {   // ~4 s at 2 GHz
+      if (clock64() - t0 > timeout_cycles) {   // JPM_SLAB_TIMEOUT_S (default 4 s): a lost peer must not hang the GPU
         sl.flags[sl.rank][kFlagErr] = 1u;    // error word
         break;
       }
@@ -1245,8 +1246,14 @@ void pmfft_destroy(jpm_plan* p) {
 
 int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width, int reach_extra) {
   if (p->slab.P == 1) return JPM_OK;
-  if (exchange_ghost_width) fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, reach_extra);
-  else fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch, 0);
+  // a rank may legitimately lag (snapshot I/O in a callback, a slow first launch): the watchdog is configurable, and
+  // jpm_slab_check reports a trip instead of letting later kernels consume incomplete peer data silently
+  static const long long timeout_cycles =
+      (long long)((getenv("JPM_SLAB_TIMEOUT_S") ? std::max(0.1, atof(getenv("JPM_SLAB_TIMEOUT_S"))) : 4.0) * 2.0e9);
+  if (exchange_ghost_width)
+    fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, reach_extra, timeout_cycles);
+  else
+    fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch, 0, timeout_cycles);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }

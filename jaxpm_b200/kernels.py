@@ -34,8 +34,10 @@ def fftk(k_array):
 def gradient_kernel(kvec, direction, order=1):
     w = kvec[direction]
     if order == 0:
+        # kernels.py:56-61 zeroes index len // 2 of a FULL-length frequency axis, i.e. the Nyquist mode |w| = pi.  The z
+        # axis here is the R2C half axis (length nz // 2 + 1), where that mode is the LAST entry: zero by value
         wts = (1j * w).reshape(-1).clone()
-        wts[len(wts) // 2] = 0
+        wts[w.reshape(-1).abs() >= np.pi * (1 - 1e-6)] = 0
         return wts.reshape(w.shape)
     a = 1 / 6.0 * (8 * torch.sin(w) - torch.sin(2 * w))
     return a * 1j

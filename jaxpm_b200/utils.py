@@ -136,3 +136,26 @@ def power_spectrum(mesh, mesh2=None, box_shape=None, kedges=None, multipoles=0, 
         psum = (out[:nl]**2 + out[nl:2 * nl]**2).sqrt()
         pk = ((psum / g.kcount)[:, 1:-1] * g.cellvol).to(torch.float32)
     return (g.kavg, pk[0]) if scalar else (g.kavg, pk)
+
+
+def transfer(mesh0, mesh1, box_shape, kedges=None):
+    """sqrt(P1 / P0) - jaxpm/utils.py:131-135."""
+    ks, pk0 = power_spectrum(mesh0, box_shape=box_shape, kedges=kedges)
+    ks, pk1 = power_spectrum(mesh1, box_shape=box_shape, kedges=kedges)
+    return ks, (pk1 / pk0)**.5
+
+
+def coherence(mesh0, mesh1, box_shape, kedges=None):
+    """P01 / sqrt(P0 P1) - jaxpm/utils.py:138-143."""
+    ks, pk01 = power_spectrum(mesh0, mesh1, box_shape=box_shape, kedges=kedges)
+    ks, pk0 = power_spectrum(mesh0, box_shape=box_shape, kedges=kedges)
+    ks, pk1 = power_spectrum(mesh1, box_shape=box_shape, kedges=kedges)
+    return ks, pk01 / (pk0 * pk1)**.5
+
+
+def pktranscoh(mesh0, mesh1, box_shape, kedges=None):
+    """(k, P0, P1, transfer, coherence) - jaxpm/utils.py:146-151."""
+    ks, pk01 = power_spectrum(mesh0, mesh1, box_shape=box_shape, kedges=kedges)
+    ks, pk0 = power_spectrum(mesh0, box_shape=box_shape, kedges=kedges)
+    ks, pk1 = power_spectrum(mesh1, box_shape=box_shape, kedges=kedges)
+    return ks, pk0, pk1, (pk1 / pk0)**.5, pk01 / (pk0 * pk1)**.5

@@ -41,3 +41,19 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", txt, flags=re.M), f
+
+
+def test_xla_ffi_handlers_type_check():
+    """jaxpm_b200/csrc/xla_ffi.cc (the jax.ffi binding of INTEGRATION.md section 3) compiles against the C ABI: every
+    handler body is type-checked with the stand-in for jaxlib's header (tools/xla_ffi_stub; JAX is not installable
+    here), so a changed entry-point signature breaks this test instead of a maintainer's build."""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run(["make", "-C", os.path.join(root, "jaxpm_b200", "csrc"), "ffi-check"], capture_output=True,
+                       text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    src = open(os.path.join(root, "jaxpm_b200", "csrc", "xla_ffi.cc")).read()
+    for name in ("JpmCicPaint", "JpmCicRead", "JpmCicPaintDx", "JpmCicRead3", "JpmRead3KickDrift",
+                 "JpmDensityToForceMeshes", "JpmSimForces", "JpmSimStep", "JpmCicReadGrad", "JpmCicPaintGrad",
+                 "JpmGreensDiv", "JpmSlabForces", "JpmNormalField"):
+        assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({name}," in src, name
