@@ -361,6 +361,8 @@ def run_gpu(args):
     # ---- end to end through the host-buffer C-ABI entry on the SAME tile kernels (pinned host state, H2D + D2H of
     #      the full particle state every step): PCIe-bound by construction (24 B in + 24 B out per particle-step)
     e2e_steps = max(1, args.e2e_steps)
+    bytes_state = 2 * npart * 12
+    # (a) one state at a time (latency form): H2D -> sort -> step -> un-sort -> D2H, serial
     ph = torch.empty(disp.shape, dtype=torch.float32).pin_memory()
     vh = torch.empty(vel.shape, dtype=torch.float32).pin_memory()
     ph.copy_(disp)
@@ -368,16 +370,40 @@ def run_gpu(args):
     sim.step_host(ph, vh, disp, vel, 0.0, 0.0)  # warm
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for n in range(e2e_steps):
+    for n in range(min(e2e_steps, 3)):
         sim.step_host(ph, vh, disp, vel, 1e-6, 1e-6)
     torch.cuda.synchronize()
+    t_serial = (time.perf_counter() - t0) / min(e2e_steps, 3)
+    # (b) a stream of host-resident states (throughput form, the headline): the same per-step work and bytes, the
+    #     upload of state b + 1, the step of state b and the download of state b - 1 overlapped on three streams
+    #     (jpm_sim_steps_host_f32); a ring of three pinned host state buffers
+    ring_p = [ph] + [torch.empty_like(ph).pin_memory() for _ in range(2)]
+    ring_v = [vh] + [torch.empty_like(vh).pin_memory() for _ in range(2)]
+    for t in ring_p[1:]:
+        t.copy_(ph)
+    for t in ring_v[1:]:
+        t.copy_(vh)
+    del disp, vel
+    torch.cuda.empty_cache()
+    sim.steps_host(ring_p[:2], ring_v[:2], [0.0] * 2, [0.0] * 2)  # warm (allocates the staging buffers)
+    torch.cuda.synchronize()
+    lp0 = _lib.launch_count()
+    t0 = time.perf_counter()
+    sim.steps_host([ring_p[i % 3] for i in range(e2e_steps)], [ring_v[i % 3] for i in range(e2e_steps)],
+                   [1e-6] * e2e_steps, [1e-6] * e2e_steps)
+    torch.cuda.synchronize()
     t_e2e = time.perf_counter() - t0
-    bytes_state = 2 * npart * 12
     e2e = {"value": npart * e2e_steps / t_e2e, "unit": UNIT, "h2d_bytes_per_step": bytes_state,
            "d2h_bytes_per_step": bytes_state, "steps": e2e_steps,
-           "entry": "jpm_sim_step_host_f32 (pinned host pos/vel in -> tile sort, resident step, un-sort -> pos/vel out)",
-           "pcie_GBps_each_way": round(bytes_state * e2e_steps / t_e2e / 1e9, 1)}
-    del ph, vh
+           "entry": "jpm_sim_steps_host_f32: a stream of pinned host (pos, vel) states, each H2D -> tile sort -> resident "
+                    "step -> un-sort -> D2H; the three legs of consecutive states overlap (two copy streams + compute)",
+           "pcie_GBps_each_way": round(bytes_state * e2e_steps / t_e2e / 1e9, 1),
+           "gpu_launches": _lib.launch_count() - lp0,
+           "serial_one_state": {"value": npart / t_serial, "ms": round(t_serial * 1e3, 2),
+                                "entry": "jpm_sim_step_host_f32 (no overlap: latency of one state)"}}
+    disp = torch.empty(ph.shape, dtype=torch.float32, device=dev)
+    vel = torch.empty(vh.shape, dtype=torch.float32, device=dev)
+    del ph, vh, ring_p, ring_v
     # run-level end to end, the call a user of the reference makes (notebooks/05-MultiHost_PM.py:85-135): host ICs in,
     # LPT + the whole step schedule on the device, host particle state out
     e2e_run = None

@@ -360,6 +360,15 @@ int32_t jpm_sim_step(jpm_sim* sim, void* stream, float kick_coef, float drift_co
  * jpm_sim_step, un-sort, D2H.  pos_dev / vel_dev: device staging [np][3].  Synchronises `stream`. */
 int32_t jpm_sim_step_host_f32(jpm_sim* sim, void* stream, float* pos_host, float* vel_host, float* pos_dev,
                               float* vel_dev, float kick_coef, float drift_coef);
+/* A batch of independent particle states, each taken through the sequence of jpm_sim_step_host_f32 (what jax.vmap of a
+ * one-step function over host-resident states, or a caller streaming states from host memory, issues).  The legs of
+ * consecutive elements overlap: element b + 1 uploads on a copy stream while element b computes on `stream` and
+ * element b - 1 downloads on a second copy stream, through double-buffered device staging owned by the sim (4 x
+ * np x 24 bytes, allocated at the first call).  pos_hosts / vel_hosts: nbatch host pointers ([np][3] each, updated in
+ * place; pinned memory for overlap; a pointer may repeat - an upload waits for the last download into the same
+ * buffer).  kick_coefs / drift_coefs: nbatch HOST floats.  Synchronises `stream` and both copy streams. */
+int32_t jpm_sim_steps_host_f32(jpm_sim* sim, void* stream, int32_t nbatch, float* const* pos_hosts,
+                               float* const* vel_hosts, const float* kick_coefs, const float* drift_coefs);
 /* One jpm_sim_step with a CUDA event recorded on `stream` at every stage boundary (memset, paint, each
  * FFT pass, read).  Synchronises the stream; fills names_out[i] (static strings) and ms_out[i] for the
  * *n_out <= cap stages.  This is how bench.py measures the per-kernel roofline live. */

@@ -76,6 +76,7 @@ SIGNATURES = {
     "jpm_sim_forces_batched": ([vp, vp, vp, vp, i32, f32, f32, vp, i32, f32], i32),
     "jpm_sim_step": ([vp, vp, f32, f32], i32),
     "jpm_sim_step_host_f32": ([vp, vp, vp, vp, vp, vp, f32, f32], i32),
+    "jpm_sim_steps_host_f32": ([vp, vp, i32, C.POINTER(vp), C.POINTER(vp), C.POINTER(f32), C.POINTER(f32)], i32),
     "jpm_sim_step_profile": ([vp, vp, f32, f32, C.POINTER(C.c_char_p), C.POINTER(f32), i32, C.POINTER(i32)], i32),
     "jpm_sim_stats_host": ([vp, vp, C.POINTER(i64)], i32),
     "jpm_sim_set_force_mode": ([vp, i32], i32),

@@ -31,6 +31,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <vector>
 
 #include "plan_internal.cuh"
 
@@ -78,6 +79,12 @@ struct jpm_sim {
   long long nstep = 0;
   double last_bound = -1.0;            // last evaluated error bound (auto), < 0 = none yet
   long long mode_steps[2] = {0, 0};    // steps run in spectral / potential mode
+  // ---- jpm_sim_steps_host_f32: copy streams, double-buffered device staging (allocated at the first call) ----
+  cudaStream_t st_h2d = nullptr, st_d2h = nullptr;
+  float* stage_in[2] = {nullptr, nullptr};    // [2][np][3]: pos | vel
+  float* stage_out[2] = {nullptr, nullptr};
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_out_ready[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
 };
 
 namespace jpm {
@@ -1044,6 +1051,14 @@ extern "C" int32_t jpm_sim_destroy(jpm_sim* s) {
   if (s->stats_host) cudaFreeHost(s->stats_host);
   for (int i = 0; i < 3; ++i)
     if (s->stats_ev[i]) cudaEventDestroy(s->stats_ev[i]);
+  for (int i = 0; i < 2; ++i) {
+    if (s->stage_in[i]) cudaFree(s->stage_in[i]);
+    if (s->stage_out[i]) cudaFree(s->stage_out[i]);
+    for (cudaEvent_t e : {s->ev_in_ready[i], s->ev_in_free[i], s->ev_out_ready[i], s->ev_out_free[i]})
+      if (e) cudaEventDestroy(e);
+  }
+  if (s->st_h2d) cudaStreamDestroy(s->st_h2d);
+  if (s->st_d2h) cudaStreamDestroy(s->st_d2h);
   delete s;
   return JPM_OK;
 }
@@ -1392,6 +1407,80 @@ extern "C" int32_t jpm_sim_step_host_f32(jpm_sim* s, void* stream, float* pos_ho
   JPM_CUDA(cudaMemcpyAsync(vel_host, vel_dev, bytes, cudaMemcpyDeviceToHost, st));
   JPM_CUDA(cudaStreamSynchronize(st));
   return JPM_OK;
+}
+
+// A batch of independent particle states, each taken through jpm_sim_step_host_f32's sequence (H2D, tile sort, one
+// resident step, un-sort, D2H) - what a caller holding its states in host memory (or jax.vmap over host-resident
+// states) issues.  The three legs of consecutive batch elements overlap: element b + 1 uploads on a copy stream while
+// element b computes on `stream` and element b - 1 downloads on a second copy stream (PCIe is full duplex), through
+// double-buffered device staging owned by the sim.  Per element the bytes are the same as the unpipelined entry; the
+// rate tends to max(H2D, compute, D2H) instead of their sum.  Host buffers may repeat in the lists (a ring): an upload
+// from a buffer waits for the last download into it.  Synchronises all three streams before returning.
+extern "C" int32_t jpm_sim_steps_host_f32(jpm_sim* s, void* stream, int32_t nbatch, float* const* pos_hosts,
+                                          float* const* vel_hosts, const float* kick_coefs,
+                                          const float* drift_coefs) {
+  JPM_CHECK_ARG(s && pos_hosts && vel_hosts && kick_coefs && drift_coefs && nbatch >= 0, "bad arguments");
+  JPM_CHECK_ARG(s->plan && !s->pos_only, "sim has no FFT plan attached / holds no velocities");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n3 = (size_t)s->np * 3, bytes = n3 * sizeof(float);
+  if (!s->st_h2d) {
+    JPM_CUDA(cudaStreamCreateWithFlags(&s->st_h2d, cudaStreamNonBlocking));
+    JPM_CUDA(cudaStreamCreateWithFlags(&s->st_d2h, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      JPM_CUDA(cudaMalloc(&s->stage_in[i], 2 * bytes));
+      JPM_CUDA(cudaMalloc(&s->stage_out[i], 2 * bytes));
+      JPM_CUDA(cudaEventCreateWithFlags(&s->ev_in_ready[i], cudaEventDisableTiming));
+      JPM_CUDA(cudaEventCreateWithFlags(&s->ev_in_free[i], cudaEventDisableTiming));
+      JPM_CUDA(cudaEventCreateWithFlags(&s->ev_out_ready[i], cudaEventDisableTiming));
+      JPM_CUDA(cudaEventCreateWithFlags(&s->ev_out_free[i], cudaEventDisableTiming));
+    }
+  }
+  std::vector<cudaEvent_t> done(nbatch, nullptr);     // download of element b finished (host ring reuse)
+  int32_t rc = JPM_OK;
+  auto fail = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == JPM_OK) {
+      set_error("%s failed: %s", what, cudaGetErrorString(e));
+      rc = JPM_ERR_CUDA;
+    }
+    return e != cudaSuccess;
+  };
+  for (int b = 0; b < nbatch && rc == JPM_OK; ++b) {
+    const int i = b & 1;
+    if (!pos_hosts[b] || !vel_hosts[b]) { set_error("null host buffer in batch element %d", b); rc = JPM_ERR_INVALID; break; }
+    // ---- upload (copy stream 1): staging slot free (element b - 2 sorted out of it), host buffer not being written
+    if (b >= 2 && fail(cudaStreamWaitEvent(s->st_h2d, s->ev_in_free[i], 0), "cudaStreamWaitEvent")) break;
+    for (int c = b - 1; c >= 0; --c)
+      if (pos_hosts[c] == pos_hosts[b] || vel_hosts[c] == vel_hosts[b] || pos_hosts[c] == vel_hosts[b] ||
+          vel_hosts[c] == pos_hosts[b]) {
+        if (fail(cudaStreamWaitEvent(s->st_h2d, done[c], 0), "cudaStreamWaitEvent")) break;
+        break;
+      }
+    if (rc) break;
+    if (fail(cudaMemcpyAsync(s->stage_in[i], pos_hosts[b], bytes, cudaMemcpyHostToDevice, s->st_h2d), "H2D")) break;
+    if (fail(cudaMemcpyAsync(s->stage_in[i] + n3, vel_hosts[b], bytes, cudaMemcpyHostToDevice, s->st_h2d), "H2D")) break;
+    if (fail(cudaEventRecord(s->ev_in_ready[i], s->st_h2d), "cudaEventRecord")) break;
+    // ---- compute (caller's stream)
+    if (fail(cudaStreamWaitEvent(st, s->ev_in_ready[i], 0), "cudaStreamWaitEvent")) break;
+    if ((rc = jpm_sim_load(s, stream, s->stage_in[i], s->stage_in[i] + n3))) break;
+    if (fail(cudaEventRecord(s->ev_in_free[i], st), "cudaEventRecord")) break;
+    if ((rc = jpm_sim_step(s, stream, kick_coefs[b], drift_coefs[b]))) break;
+    if (b >= 2 && fail(cudaStreamWaitEvent(st, s->ev_out_free[i], 0), "cudaStreamWaitEvent")) break;
+    if ((rc = jpm_sim_store(s, stream, s->stage_out[i], s->stage_out[i] + n3))) break;
+    if (fail(cudaEventRecord(s->ev_out_ready[i], st), "cudaEventRecord")) break;
+    // ---- download (copy stream 2)
+    if (fail(cudaStreamWaitEvent(s->st_d2h, s->ev_out_ready[i], 0), "cudaStreamWaitEvent")) break;
+    if (fail(cudaMemcpyAsync(pos_hosts[b], s->stage_out[i], bytes, cudaMemcpyDeviceToHost, s->st_d2h), "D2H")) break;
+    if (fail(cudaMemcpyAsync(vel_hosts[b], s->stage_out[i] + n3, bytes, cudaMemcpyDeviceToHost, s->st_d2h), "D2H")) break;
+    if (fail(cudaEventRecord(s->ev_out_free[i], s->st_d2h), "cudaEventRecord")) break;
+    if (fail(cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming), "cudaEventCreate")) break;
+    if (fail(cudaEventRecord(done[b], s->st_d2h), "cudaEventRecord")) break;
+  }
+  fail(cudaStreamSynchronize(s->st_h2d), "cudaStreamSynchronize");
+  fail(cudaStreamSynchronize(st), "cudaStreamSynchronize");
+  fail(cudaStreamSynchronize(s->st_d2h), "cudaStreamSynchronize");
+  for (cudaEvent_t e : done)
+    if (e) cudaEventDestroy(e);
+  return rc;
 }
 
 // One jpm_sim_step with a CUDA event at every stage boundary.  Synchronises the stream.  names_out

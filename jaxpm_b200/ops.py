@@ -408,6 +408,18 @@ class Sim:
         call("jpm_sim_step_host_f32", self.handle, stream(), pos_host.data_ptr(), vel_host.data_ptr(),
              ptr(pos_dev, torch.float32), ptr(vel_dev, torch.float32), float(kick), float(drift))
 
+    def steps_host(self, pos_hosts, vel_hosts, kicks, drifts):
+        """A batch of independent host-resident states, one step each, with upload / compute / download of consecutive
+        elements overlapped (jpm_sim_steps_host_f32).  pos_hosts / vel_hosts: lists of pinned CPU tensors, updated in place."""
+        n = len(pos_hosts)
+        assert len(vel_hosts) == n and len(kicks) == n and len(drifts) == n
+        assert all(not t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() for t in (*pos_hosts, *vel_hosts))
+        pp = (C.c_void_p * n)(*[t.data_ptr() for t in pos_hosts])
+        vv = (C.c_void_p * n)(*[t.data_ptr() for t in vel_hosts])
+        kk = (C.c_float * n)(*[float(x) for x in kicks])
+        dd = (C.c_float * n)(*[float(x) for x in drifts])
+        call("jpm_sim_steps_host_f32", self.handle, stream(), n, pp, vv, kk, dd)
+
     def step_profile(self, kick, drift):
         """One step with per-stage CUDA-event timing: [(stage name, milliseconds), ...]."""
         names = (C.c_char_p * 24)()

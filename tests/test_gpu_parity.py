@@ -308,6 +308,42 @@ def test_host_step_entry_matches_device_step(cuda):
     assert rel_err(ph.numpy(), pos_d.cpu().numpy()) < 1e-6 and rel_err(vh.numpy(), vel_d.cpu().numpy()) < 1e-5
 
 
+def test_pipelined_host_batch_equals_loop_of_single_calls(cuda):
+    """jpm_sim_steps_host_f32 (upload / step / download of consecutive host-resident states overlapped on three
+    streams, double-buffered staging, host buffers reused as a ring) == a loop of jpm_sim_step_host_f32 (to the fp32 merge order of tile margins) -
+    the 'batched call == loop of single calls' rule of tests/test_distributed_pm.py:335-409."""
+    from jaxpm_b200 import ops
+    shape = (32, 32, 32)
+    nb = 7
+    rng = np.random.default_rng(11)
+    states = [(displaced(shape, 0.5 + 0.2 * b)[1], (0.02 * rng.standard_normal((*shape, 3))).astype(np.float32))
+              for b in range(nb)]
+    kicks = [0.01 * (b + 1) for b in range(nb)]
+    drifts = [0.02 * (b + 1) for b in range(nb)]
+    sim = ops.Sim(shape, shape, True, cuda, tile=8, margin=2)
+    pd, vd = torch.empty((*shape, 3), device=cuda), torch.empty((*shape, 3), device=cuda)
+    ref = []
+    for (x, v), kk, dd in zip(states, kicks, drifts):
+        ph, vh = torch.as_tensor(x.copy()).pin_memory(), torch.as_tensor(v.copy()).pin_memory()
+        sim.step_host(ph, vh, pd, vd, kk, dd)
+        ref.append((ph.numpy().copy(), vh.numpy().copy()))
+    # distinct host buffers
+    hp = [torch.as_tensor(x.copy()).pin_memory() for x, _ in states]
+    hv = [torch.as_tensor(v.copy()).pin_memory() for _, v in states]
+    sim.steps_host(hp, hv, kicks, drifts)
+    for b in range(nb):
+        assert rel_err(hp[b].numpy(), ref[b][0]) < 2e-6 and rel_err(hv[b].numpy(), ref[b][1]) < 2e-6, b
+    # a ring of two host buffers: element b + 2 reads what element b wrote (a two-step trajectory per buffer)
+    rp = [torch.as_tensor(states[i][0].copy()).pin_memory() for i in range(2)]
+    rv = [torch.as_tensor(states[i][1].copy()).pin_memory() for i in range(2)]
+    sim.steps_host([rp[0], rp[1], rp[0], rp[1]], [rv[0], rv[1], rv[0], rv[1]], kicks[:4], drifts[:4])
+    for i in range(2):
+        ph, vh = torch.as_tensor(states[i][0].copy()).pin_memory(), torch.as_tensor(states[i][1].copy()).pin_memory()
+        sim.step_host(ph, vh, pd, vd, kicks[i], drifts[i])
+        sim.step_host(ph, vh, pd, vd, kicks[i + 2], drifts[i + 2])
+        assert rel_err(rp[i].numpy(), ph.numpy()) < 4e-6 and rel_err(rv[i].numpy(), vh.numpy()) < 4e-6, i
+
+
 # ---- tile-sorted resident state (jaxpm_b200/csrc/sim.cu) ---------------------------------------
 @pytest.mark.parametrize("relative", [False, True])
 @pytest.mark.parametrize("shape,tile,margin,sigma", [((32, 32, 32), 8, 2, 0.5), ((32, 32, 64), 16, 2, 3.0),

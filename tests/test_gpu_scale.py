@@ -91,7 +91,24 @@ def test_config2_256_against_oracle_run(cuda, force_mode):
         assert (np.any(i_ref[:, 0] != i_got[:, 0], axis=-1)).mean() < 1e-4
     # ---- one force evaluation at the LPT state (fast functional API) ---------------------------------------
     F = pm_forces(dx, mesh_shape=shape, paint_absolute_pos=False)
-    assert np.abs(_sample(F, ids) - g["force0"]).max() / float(g["force0_max"]) < FIELD_TOL
+    # (a) fast functional API == order-preserving kernels + cuFFT on the SAME displacement: every particle, strict
+    from jaxpm_b200 import pm as jpm_pm
+    jpm_pm._FAST_API = False
+    try:
+        F_slow = pm_forces(dx, mesh_shape=shape, paint_absolute_pos=False)
+    finally:
+        jpm_pm._FAST_API = True
+    assert float((F - F_slow).abs().max()) / float(g["force0_max"]) < FIELD_TOL
+    del F_slow
+    # (b) against the oracle's run.  Its displacement differs from the CUDA one by fp32 rounding, so a particle within
+    # that distance of the reference's dropped-corner window at the periodic edge (see test_nbody_config1: for
+    # coordinates in (-ulp(N)/2, 0) the reference paints nothing) can take the other branch in ONE of the two runs and
+    # move one particle mass in one cell: with 1.7e7 particles ~1 such event per paint, felt by its neighbourhood only
+    err = np.abs(_sample(F, ids) - g["force0"]).max(-1) / float(g["force0_max"])
+    nbad = int((err > FIELD_TOL).sum())
+    print(f"[config2 {force_mode}] force0: median {np.median(err):.2e}, q99.9 {np.quantile(err, 0.999):.2e}, "
+          f"max {err.max():.2e}, {nbad} of {err.size} sampled particles above {FIELD_TOL}")
+    assert np.quantile(err, 0.999) < FIELD_TOL and nbad <= max(8, err.size // 1000)
     assert abs(float(F.abs().max()) / float(g["force0_max"]) - 1) < 1e-4
     del F
     rho = cic_paint_dx(dx)

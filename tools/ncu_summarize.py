@@ -45,10 +45,15 @@ if os.path.exists(lp):
     out.append("")
 
 for f in sorted(os.listdir(src)):
-    if not f.endswith(".ncu-rep"):
+    # either the report itself or its `--page raw --csv` export made on the GPU box (reports are ~40 MB each and
+    # gpurun brings back at most 64 MiB per call)
+    if f.endswith("_raw.csv"):
+        raw = open(os.path.join(src, f)).read()
+    elif f.endswith(".ncu-rep") and not os.path.exists(os.path.join(src, f[:-8] + "_raw.csv")):
+        raw = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True,
+                             text=True).stdout
+    else:
         continue
-    raw = subprocess.run(["ncu", "-i", os.path.join(src, f), "--page", "raw", "--csv"], capture_output=True,
-                         text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     ix = {h: i for i, h in enumerate(hdr)}
