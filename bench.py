@@ -531,7 +531,7 @@ def main():
                     help="number of equal steps in a from 0.1 to 1 (the timed steps are the last K of them)")
     ap.add_argument("--halo", type=int, default=64, help="halo width of the sharded path (N > 1)")
     ap.add_argument("--no-resident", action="store_true", help="N > 1: order-preserving kernels")
-    ap.add_argument("--pdims", default=None, help="N > 1: process grid PXxPY (default Nx1 slabs; PY > 1 = pencils over NCCL)")
+    ap.add_argument("--pdims", default=None, help="N > 1: process grid PXxPY (default Nx1 slabs; PY > 1 = pencil particle domains; both on the fused peer-memory path unless --nccl)")
     ap.add_argument("--nccl", action="store_true", help="N > 1: NCCL halo / all-to-all path instead of the fused slab path")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
     ap.add_argument("--direct", action="store_true",

@@ -24,8 +24,6 @@ def run_multi(args, world, rank, dev):
     if getattr(args, "pdims", None):
         pdims = tuple(int(v) for v in args.pdims.lower().split("x"))
         assert pdims[0] * pdims[1] == world, f"--pdims {args.pdims} needs {pdims[0] * pdims[1]} ranks"
-        if pdims[1] > 1:
-            args.nccl = True            # pencils: NCCL halo exchange + all-to-all transposes (halo.py, pfft.py)
     sh = Sharding(pdims)
     h = args.halo
     shape = (N, N, N)
@@ -158,11 +156,25 @@ def run_multi(args, world, rank, dev):
         nspec = 2 if pot else 3                                  # AT (1 spectrum) + psi (1) | + T01 (2 spectra)
         transposes = (lxl * N * nzc * 8) * remote * nspec
         ge = timing["ghost_planes_used"]
-        plane = (N + 8) * (N + 8) * 4
-        # ghost planes written to the two neighbours: three force meshes, or psi with 2 more planes for the stencil
-        ghosts_out = (2 * min(ge + 2, h) * plane) if pot else (3 * 2 * ge * plane)
-        ghosts_in = 2 * ge * plane                               # density ghost planes read from them
-        sent = transposes + ghosts_out
+        ncomp = 1 if pot else 3
+        geo = min(ge + 2, h) if pot else ge
+        if pdims[1] == 1:
+            plane = (N + 8) * (N + 8) * 4
+            # ghost planes written to the two neighbours: three force meshes, or psi with 2 more planes for the stencil
+            ghosts_out = ncomp * 2 * geo * plane
+            ghosts_in = 2 * ge * plane                           # density ghost planes read from them
+            regroup_in = regroup_out = 0
+        else:
+            # pencil grid: the z passes also move the slab's rows between the pencils of the row group (the first
+            # transpose of a pencil FFT, done in real space), and the ghost frame has four sides + corners
+            Lx, Ly = N // pdims[0], N // pdims[1]
+            frame = lambda g: ((Lx + 2 * g) * (Ly + 2 * g) - Lx * Ly) * (N + 8) * 4
+            ghosts_out = ncomp * frame(geo)
+            ghosts_in = frame(ge)
+            regroup_in = lxl * N * N * 4 * (pdims[1] - 1) / pdims[1]
+            regroup_out = ncomp * regroup_in
+        sent = transposes + ghosts_out + regroup_out
+        ghosts_in = ghosts_in + regroup_in
         nvlink = {"sent_bytes_per_rank_per_step": int(sent), "read_bytes_per_rank_per_step": int(ghosts_in),
                   "sent_GBps_over_whole_step": sent * K / t_dev / 1e9, "peak_GBps_per_direction": 770.0,
                   "frac_of_link_if_not_overlapped": sent / 770e9 / (t_dev / K)}
@@ -181,7 +193,9 @@ def run_multi(args, world, rank, dev):
                        "force_mode": force_mode,
                        "resident": not args.no_resident,
                        "exchange": ("halo reduce / FFT transposes / halo fill inside the FFT kernels over NVLink peer "
-                                    "memory (slab.py), 4 flag barriers per step, no NCCL on the data path") if fused
+                                    "memory (slab.py), 4 flag barriers per step, no NCCL on the data path"
+                                    + ("; pencil particle domain, x-slab FFT chain, row-group transpose inside the z passes"
+                                       if pdims[1] > 1 else "")) if fused
                        else "NCCL send/recv halos + all-to-all FFT transposes (halo.py, pfft.py)"},
             "roofline": {"bound": "hbm", "kernel": "whole step (per-GPU share of 124 B/particle-step)",
                          "achieved": step_alg_bytes * K / t_dev / 1e9 / world, "peak": peak, "peak_kind": peak_kind,

@@ -287,6 +287,16 @@ int32_t jpm_plan_padded_get_f32(jpm_plan* plan, void* stream, int32_t which, flo
  * Allocates ONE device block holding the rank's density / force / spectrum buffers and barrier flags. */
 int32_t jpm_slab_create(jpm_plan** plan, int32_t nx, int32_t ny, int32_t nz, int32_t nranks, int32_t rank,
                         int32_t gx);
+/* Pencil process grids (px, py), px py <= 8 ranks, rank = a py + b as in jax.make_mesh(pdims) (jaxpm/distributed.py:
+ * 116-129, 168-190; tests/test_distributed_pm.py:28 pdims (4,2), (2,4), (1,8)): rank (a, b) owns the particles and the
+ * real meshes of x in [a nx/px, (a+1) nx/px), y in [b ny/py, (b+1) ny/py) plus gx ghost planes / gy ghost rows per
+ * side (the reference's halo per sharded axis).  The FFT chain keeps the x slabs of the px py ranks: the z passes do
+ * the row-group transpose while they load / store (pull the density rows of the slab from the pencils of the row
+ * group with their x / y / corner ghosts folded in, push the force rows back with the ghost images), so the exchange
+ * volume equals that of a two-transpose pencil FFT and no NCCL call is on the data path.  py == 1: jpm_slab_create.
+ * Needs ny / py % 16 == 0.  Every jpm_slab_* entry below serves both; "interior" is the rank's [nx/px][ny/py][nz]. */
+int32_t jpm_slab_create_ex(jpm_plan** plan, int32_t nx, int32_t ny, int32_t nz, int32_t px, int32_t py, int32_t rank,
+                           int32_t gx, int32_t gy);
 /* cudaIpcMemHandle_t (64 bytes) of the rank's block: gather them over the ranks (any transport), then */
 int32_t jpm_slab_ipc_handle(jpm_plan* plan, void* handle_out, int32_t handle_bytes);
 /* map every peer's block: handles[nranks][64] in rank order (other processes, cudaIpcOpenMemHandle) ... */

@@ -55,6 +55,7 @@ SIGNATURES = {
     "jpm_kseparable_c64": ([vp, vp, vp, vp, vp, vp, i32, i32, i32, f32], i32),
     "jpm_plan_padded_get_f32": ([vp, vp, i32, vp, C.POINTER(i32)], i32),
     "jpm_slab_create": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32], i32),
+    "jpm_slab_create_ex": ([C.POINTER(vp), i32, i32, i32, i32, i32, i32, i32, i32], i32),
     "jpm_slab_ipc_handle": ([vp, vp, i32], i32),
     "jpm_slab_attach_ipc": ([vp, vp, i32], i32),
     "jpm_slab_attach_ptrs": ([vp, C.POINTER(vp), i32], i32),

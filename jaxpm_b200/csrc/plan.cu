@@ -714,20 +714,34 @@ static void slab_point(Slab& sl, int r, void* base_v) {
 
 extern "C" int32_t jpm_slab_create(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz, int32_t nranks,
                                    int32_t rank, int32_t gx) {
+  return jpm_slab_create_ex(out, nx, ny, nz, nranks, 1, rank, gx, 0);
+}
+
+extern "C" int32_t jpm_slab_create_ex(jpm_plan** out, int32_t nx, int32_t ny, int32_t nz, int32_t px, int32_t py,
+                                      int32_t rank, int32_t gx, int32_t gy) {
   JPM_CHECK_ARG(out, "null plan pointer");
+  JPM_CHECK_ARG(px >= 1 && py >= 1, "bad process grid");
+  const int nranks = px * py;
   JPM_CHECK_ARG(nranks >= 1 && nranks <= 8 && rank >= 0 && rank < nranks, "bad rank / nranks (1..8 GPUs of one box)");
   JPM_CHECK_ARG(pmfft_shape_ok(nx, ny, nz), "slab plan: mesh sides must be powers of two in [16, 1024]");
   JPM_CHECK_ARG(nx % nranks == 0 && ny % nranks == 0, "slab plan: nx and ny must divide by the rank count");
   const int lx = nx / nranks, ly = ny / nranks;
-  JPM_CHECK_ARG(gx >= 1 && gx <= lx, "slab plan: ghost width must be in [1, nx / nranks]");
+  const int Lx = nx / px, Ly = ny / py;
+  JPM_CHECK_ARG(gx >= 1 && gx <= Lx, "slab plan: ghost width must be in [1, nx / px]");
+  if (py > 1) {
+    JPM_CHECK_ARG(gy >= 1 && gy <= Ly, "pencil plan: ghost width in y must be in [1, ny / py]");
+    JPM_CHECK_ARG(Ly % 16 == 0, "pencil plan: ny / py must be a multiple of 16 (row tiles of the z passes)");
+  } else {
+    gy = 0;
+  }
   jpm_plan* p = new jpm_plan();
   p->is_slab = true;
-  // the particle kernels see the rank's local mesh INCLUDING its x ghost planes as their logical mesh
-  p->nx = lx + 2 * gx; p->ny = ny; p->nz = nz; p->nzh = nz / 2 + 1;
-  p->ncell = (long long)p->nx * ny * nz;
+  // the particle kernels see the rank's local mesh INCLUDING its ghost planes / rows as their logical mesh
+  p->nx = Lx + 2 * gx; p->ny = Ly + 2 * gy; p->nz = nz; p->nzh = nz / 2 + 1;
+  p->ncell = (long long)p->nx * p->ny * nz;
   p->nspec = 0;
   p->G = kGhost;
-  p->nxp = p->nx + 2 * kGhost; p->nyp = ny + 2 * kGhost; p->nzp = nz + 2 * kGhost;
+  p->nxp = p->nx + 2 * kGhost; p->nyp = p->ny + 2 * kGhost; p->nzp = nz + 2 * kGhost;
   p->npad = (long long)p->nxp * p->nyp * p->nzp;
   if (p->npad >= (1ll << 31)) {
     delete p;
@@ -739,6 +753,7 @@ extern "C" int32_t jpm_slab_create(jpm_plan** out, int32_t nx, int32_t ny, int32
   sl.P = nranks; sl.rank = rank;
   sl.nx = nx; sl.ny = ny; sl.nz = nz;
   sl.lx = lx; sl.ly = ly; sl.gx = gx; sl.G = kGhost;
+  sl.px = px; sl.py = py; sl.Lx = Lx; sl.Ly = Ly; sl.gy = gy;
   sl.nxp = p->nx; sl.nyp = p->nyp; sl.nzp = p->nzp; sl.npad = p->npad;   // npad: component stride of force[]
   sl.nzh = p->nzh; sl.nzc = (p->nzh + 7) & ~7;
   std::vector<float> w, a;
@@ -755,7 +770,8 @@ extern "C" int32_t jpm_slab_create(jpm_plan** out, int32_t nx, int32_t ny, int32
   JPM_CUDA(cudaMemset(p->sym_base, 0, L.total));
   slab_point(sl, rank, p->sym_base);
   {
-    const int init[3] = {0x7fffffff, (int)0x80000000, gx};   // touched x range unknown, ghost width = all of it
+    // touched x / y range unknown, ghost width = all of it
+    const int init[5] = {0x7fffffff, (int)0x80000000, std::max(gx, gy), 0x7fffffff, (int)0x80000000};
     JPM_CUDA(cudaMemcpy(sl.flags[rank] + kFlagXmin, init, sizeof(init), cudaMemcpyHostToDevice));
   }
   JPM_CUDA(cudaDeviceSynchronize());
@@ -822,10 +838,10 @@ extern "C" int32_t jpm_slab_get_interior_f32(jpm_plan* p, void* stream, int32_t 
   JPM_CHECK_ARG(p && p->is_slab && dst && which >= 0 && which <= 3, "bad arguments");
   const Slab& sl = p->slab;
   float* src = (which == 0 ? p->density_p : p->force3_p + (long long)(which - 1) * p->npad) +
-               (long long)sl.gx * sl.nyp * sl.nzp;   // pad_copy skips the kGhost spare planes itself
-  const long long total = (long long)sl.lx * sl.ny * sl.nz / 4;
+               (long long)sl.gx * sl.nyp * sl.nzp + (long long)sl.gy * sl.nzp;   // pad_copy skips the kGhost spare planes / rows itself
+  const long long total = (long long)sl.Lx * sl.Ly * sl.nz / 4;
   const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
-  pad_copy_kernel<false><<<dim3(blocks, 1), 256, 0, (cudaStream_t)stream>>>(src, dst, sl.lx, sl.ny, sl.nz / 4, sl.nyp,
+  pad_copy_kernel<false><<<dim3(blocks, 1), 256, 0, (cudaStream_t)stream>>>(src, dst, sl.Lx, sl.Ly, sl.nz / 4, sl.nyp,
                                                                           sl.nzp, sl.G, 0, 0);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
@@ -838,10 +854,12 @@ extern "C" int32_t jpm_slab_set_density_f32(jpm_plan* p, void* stream, const flo
   JPM_CUDA(cudaMemsetAsync(p->density_p, 0, p->npad * sizeof(float), st));
   JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagXmin, 0x7f, sizeof(int), st));   // 0x7f7f7f7f > any plane: unknown
   JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagXmax, 0x80, sizeof(int), st));   // 0x80808080 < 0
-  float* dstp = p->density_p + (long long)sl.gx * sl.nyp * sl.nzp;
-  const long long total = (long long)sl.lx * sl.ny * sl.nz / 4;
+  JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagYmin, 0x7f, sizeof(int), st));
+  JPM_CUDA(cudaMemsetAsync(sl.flags[sl.rank] + kFlagYmax, 0x80, sizeof(int), st));
+  float* dstp = p->density_p + (long long)sl.gx * sl.nyp * sl.nzp + (long long)sl.gy * sl.nzp;
+  const long long total = (long long)sl.Lx * sl.Ly * sl.nz / 4;
   const unsigned blocks = (unsigned)std::min<long long>((total + 255) / 256, kNumSMs * 16);
-  pad_copy_kernel<true><<<dim3(blocks, 1), 256, 0, st>>>(dstp, const_cast<float*>(src), sl.lx, sl.ny, sl.nz / 4, sl.nyp,
+  pad_copy_kernel<true><<<dim3(blocks, 1), 256, 0, st>>>(dstp, const_cast<float*>(src), sl.Lx, sl.Ly, sl.nz / 4, sl.nyp,
                                                         sl.nzp, sl.G, 0, 0);
   JPM_LAUNCH_CHECK();
   return JPM_OK;

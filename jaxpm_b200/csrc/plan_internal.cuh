@@ -23,12 +23,21 @@ struct StageTimer {
 // Geometry + (peer) pointers of the x-slab decomposition the pmfft kernels work on.  One rank = one GPU of
 // the box; rank r owns global x planes [r lx, (r+1) lx).  P == 1 describes the ordinary single-GPU plan.
 // Passed to the kernels by value (__grid_constant__).
+//
+// Pencil process grids (px, py), py > 1 (jaxpm/distributed.py:116-129, rank = a py + b): the PARTICLE domain of
+// rank (a, b) - its real arrays - is the pencil x in [a Lx, (a+1) Lx), y in [b Ly, (b+1) Ly) with gx / gy ghost planes
+// / rows per side, while the FFT chain keeps the x slabs of the P = px py ranks: slab r = a py + b lies inside pencil
+// row a, so the z passes do the row-group transpose while they load / store (the rows of slab r at y in column b'
+// live in the arrays of rank (a, b')) and every other pass is unchanged.
 struct Slab {
   int P, rank;
   int nx, ny, nz;        // GLOBAL mesh
-  int lx, ly;            // nx / P, ny / P
-  int gx, G;             // ghost planes per side in x (images of the neighbour slabs); ghost cells in y, z
-  int nxp, nyp, nzp;     // local padded real arrays: lx + 2 gx, ny + 2 G, nz + 2 G
+  int lx, ly;            // nx / P, ny / P (FFT slabs / transposed rows)
+  int px, py;            // process grid; slabs: (P, 1)
+  int Lx, Ly;            // particle-domain block: nx / px, ny / py (slabs: lx, ny)
+  int gx, gy, G;         // ghost planes per side in x, ghost rows per side in y (0 for slabs: the G periodic images
+                         // serve), spare / periodic ghost cells in y, z
+  int nxp, nyp, nzp;     // local padded real arrays: Lx + 2 gx, Ly + 2 gy + 2 G, nz + 2 G
   long long npad;        // nxp * nyp * nzp
   int nzh, nzc;          // nz / 2 + 1 and its pitch (multiple of 8)
   float* dens[8];        // [nxp][nyp][nzp]       density (painted into, ghosts not folded)
@@ -48,6 +57,8 @@ constexpr int kFlagReach = 65;     // set when a rank's particles touched its ou
 constexpr int kFlagXmin = 96;      // int: lowest / highest local x plane touched by the last paint (atomicMin / Max by
 constexpr int kFlagXmax = 97;      //      sim_paint_kernel; INT_MAX / INT_MIN = unknown)
 constexpr int kFlagGe = 98;        // int: ghost planes per side in use this step = max over ranks of what each needs
+constexpr int kFlagYmin = 99;      // int: lowest / highest local y row touched by the last paint (pencil grids)
+constexpr int kFlagYmax = 100;
 constexpr int kFlagGeSlots = 128;  // [P] the ranks' needs, written by the peers in the first barrier of a step
 // global force statistics of a step (AUTO force mode, csrc/sim.cu): two slots (step parity) of 4 words each, every
 // rank adds its share into EVERY rank's block (system-scope atomics over NVLink), so that all ranks read the same

@@ -648,8 +648,39 @@ __device__ __forceinline__ int ghost_width(const Slab& sl);
 __device__ __forceinline__ int z_pass_plane(const Slab& sl, int by) {
   return (sl.P > 1 && sl.lx >= 16) ? ((by * 37) & (sl.lx - 1)) : by;
 }
-template <int NZ>
-__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>(), (threads_for<NZ / 2, kRows>() <= 256 ? kZPassCtas : 1))
+// The (up to 3 x 3) arrays a row tile of a z pass touches on a pencil grid: the pencil that owns the rows, the x
+// neighbours whose ghost planes image the plane, the y neighbours whose ghost rows image the rows, and the corners.
+struct PencilTargets {
+  int nxs, nys;
+  int xr[3], xp[3];                 // grid row of the array, plane inside it
+  int yc[3], yr[3], r0[3], r1[3];   // grid column, array row of tile row 0, tile rows [r0, r1) that exist there
+};
+// plane xl of this rank's slab, rows y0 .. y0 + 15 (global); ge = ghost planes / rows in use this step
+__device__ __forceinline__ PencilTargets pencil_targets(const Slab& sl, int xl, int y0, int ge) {
+  PencilTargets t;
+  const int a = sl.rank / sl.py, b = sl.rank - a * sl.py;
+  const int xq = b * sl.lx + xl;                          // plane inside pencil row a
+  const int by = y0 / sl.Ly, yl0 = y0 - by * sl.Ly;       // column that owns the rows, first row inside it
+  const int gex = min(sl.gx, ge), gey = min(sl.gy, ge);
+  t.nxs = 0;
+  t.xr[t.nxs] = a; t.xp[t.nxs++] = sl.gx + xq;
+  if (xq < gex) { t.xr[t.nxs] = (a + sl.px - 1) % sl.px; t.xp[t.nxs++] = sl.gx + sl.Lx + xq; }            // its high ghost
+  if (xq >= sl.Lx - gex) { t.xr[t.nxs] = (a + 1) % sl.px; t.xp[t.nxs++] = xq - (sl.Lx - sl.gx); }         // its low ghost
+  t.nys = 0;
+  t.yc[t.nys] = by; t.yr[t.nys] = sl.G + sl.gy + yl0; t.r0[t.nys] = 0; t.r1[t.nys++] = kRows;
+  if (yl0 < gey) {
+    t.yc[t.nys] = (by + sl.py - 1) % sl.py; t.yr[t.nys] = sl.G + sl.gy + sl.Ly + yl0;
+    t.r0[t.nys] = 0; t.r1[t.nys++] = min(kRows, gey - yl0);
+  }
+  if (yl0 + kRows > sl.Ly - gey) {
+    t.yc[t.nys] = (by + 1) % sl.py; t.yr[t.nys] = sl.G + sl.gy + yl0 - sl.Ly;
+    t.r0[t.nys] = max(0, sl.Ly - gey - yl0); t.r1[t.nys++] = kRows;
+  }
+  return t;
+}
+
+template <int NZ, bool PEN = false>
+__global__ void __launch_bounds__(threads_for<NZ / 2, kRows>(), (threads_for<NZ / 2, kRows>() <= 256 && !PEN ? kZPassCtas : 1))
 zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull, int x0) {
   constexpr int NH = NZ / 2, NT = threads_for<NH, kRows>();
   extern __shared__ __align__(16) float2 sm[];
@@ -659,6 +690,56 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   const int xl = z_pass_plane(sl, x0 + blockIdx.y), y0 = blockIdx.x * kRows;
   const int G = sl.G, gx = sl.gx, lx = sl.lx, ny = sl.ny, nyp = sl.nyp, nzp = sl.nzp;
   const int GH = G / 2;       // ghost width in float2 units
+  if constexpr (PEN) {
+    // pencil grid: the rows live in the arrays of the row group (the row-group transpose happens in this load), ghost
+    // planes / rows of the x / y / corner neighbours fold in as further sources; every load is branch-free per source
+    constexpr int ITER = kRows * NH / NT, ZB = ITER < 8 ? ITER : 8;
+    static_assert(kRows * NH % NT == 0 && ITER % ZB == 0, "row tile must divide evenly over the threads");
+    const PencilTargets t = pencil_targets(sl, xl, y0, ghost_width(sl));
+    const int rowp = nzp / 2;
+    bool first = true;
+    for (int ix = 0; ix < t.nxs; ++ix)
+      for (int iy = 0; iy < t.nys; ++iy) {
+        const float* plane = sl.dens[t.xr[ix] * sl.py + t.yc[iy]] + (long long)t.xp[ix] * nyp * nzp;
+        const float2* base = reinterpret_cast<const float2*>(plane + (long long)t.yr[iy] * nzp) + GH;
+        const int ra = t.r0[iy], rb = t.r1[iy];
+#pragma unroll 1
+        for (int b = 0; b < ITER; b += ZB) {
+          float2 acc[ZB];
+#pragma unroll
+          for (int i = 0; i < ZB; ++i) {
+            const int e = threadIdx.x + (b + i) * NT;
+            const int r = e / NH, m = e - r * NH;
+            acc[i] = (r >= ra && r < rb) ? __ldcs(base + r * rowp + m) : make_float2(0.f, 0.f);
+          }
+#pragma unroll
+          for (int i = 0; i < ZB; ++i) {
+            const int e = threadIdx.x + (b + i) * NT;
+            const int r = e / NH, m = e - r * NH;
+            float2 v = acc[i];
+            if (!first) v = cadd(v, s[LayRows<NH>::idx(m, r)]);
+            s[LayRows<NH>::idx(m, r)] = v;
+          }
+        }
+        first = false;
+      }
+    __syncthreads();
+    // z ghost cells of every source: high ghost -> first cells, low ghost -> last cells (2 GH pairs per row)
+    for (int e = threadIdx.x; e < kRows * 2 * GH; e += NT) {
+      const int r = e / (2 * GH), g = e - r * (2 * GH);
+      const int m = g < GH ? g : NH - 2 * GH + g;
+      const int off = g < GH ? NH : -NH;
+      float2 v = s[LayRows<NH>::idx(m, r)];
+      for (int ix = 0; ix < t.nxs; ++ix)
+        for (int iy = 0; iy < t.nys; ++iy) {
+          if (r < t.r0[iy] || r >= t.r1[iy]) continue;
+          const float* plane = sl.dens[t.xr[ix] * sl.py + t.yc[iy]] + (long long)t.xp[ix] * nyp * nzp;
+          const float2* base = reinterpret_cast<const float2*>(plane + (long long)t.yr[iy] * nzp) + GH;
+          v = cadd(v, __ldcs(base + r * rowp + m + off));
+        }
+      s[LayRows<NH>::idx(m, r)] = v;
+    }
+  } else {
   // x planes that fold onto interior plane xl: this rank's own, the left neighbour's high ghost, the right
   // neighbour's low ghost
   const float* src[3] = {sl.dens[sl.rank] + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
@@ -738,6 +819,7 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
       s[LayRows<NH>::idx(m, r)] = acc;
     }
   }
+  }   // !PEN
   __syncthreads();
   SmemIO<LayRows<NH>> io{s};
   run_stages<NH, kRows, NT, false, false, false, false, LayRows<NH>, 0>(s, tw, kRows, io, io, nullptr);
@@ -761,7 +843,7 @@ zfwd_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 // grid: (ny / 16, lx, 3).  Output is unnormalised (the 1/Nc lives in the k-space factor).  Component 2
 // still carries the factor i a_z(kz) (see X-fused / Y-inv).  Every row is written to this rank's interior
 // plane, to its y / z ghost images and to the x ghost planes of the neighbour slabs that image it.
-template <int NZ>
+template <int NZ, bool PEN = false>
 __global__ void __launch_bounds__(threads_for<NZ / 2, kRows>())
 zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, const float2* __restrict__ twfull,
             const float* __restrict__ az, int x0, int variant, int ge_extra, int to_psi) {
@@ -828,6 +910,26 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
   // destinations in x: own interior plane, left neighbour's high ghost, right neighbour's low ghost
   const long long cofs = (long long)comp * sl.npad;
   float* const* const dmesh = to_psi ? sl.psi : sl.force;      // potential chain: the psi mesh (one component)
+  if constexpr (PEN) {
+    // pencil grid: the pencil that owns the rows (row-group transpose in this store) + the ghost images of the
+    // x / y / corner neighbours
+    const PencilTargets t = pencil_targets(sl, xl, y0, ghost_width(sl) + ge_extra);
+    const int GHp = G / 2;
+    for (int ix = 0; ix < t.nxs; ++ix)
+      for (int iy = 0; iy < t.nys; ++iy) {
+        float* plane = dmesh[t.xr[ix] * sl.py + t.yc[iy]] + cofs + (long long)t.xp[ix] * nyp * nzp;
+        const int ra = t.r0[iy], rb = t.r1[iy];
+        for (int e = threadIdx.x + ra * NH; e < rb * NH; e += NT) {
+          const int r = e / NH, m = e - r * NH;
+          const float2 v = s[LayRows<NH>::idx(m, r)];
+          float2* row = reinterpret_cast<float2*>(plane + (long long)(t.yr[iy] + r) * nzp);
+          row[GHp + m] = v;
+          if (m < GHp) row[NH + GHp + m] = v;
+          if (m >= NH - GHp) row[m - (NH - GHp)] = v;
+        }
+      }
+    return;
+  }
   float* dstp[3] = {dmesh[sl.rank] + cofs + (long long)(gx + xl) * nyp * nzp, nullptr, nullptr};
   // ge_extra: the potential chain's mesh is differentiated by a +-2 stencil after the read box is staged
   const int ge = min(gx, ghost_width(sl) + ge_extra);
@@ -892,20 +994,28 @@ fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi, unsigned* __r
   const int z4 = blockIdx.x * 32 + (threadIdx.x & 31);
   const int yp = blockIdx.y * 8 + (threadIdx.x >> 5);
   int xb = x_lo + blockIdx.z * kGradPlanes, xe = min(xb + kGradPlanes, x_hi);
-  const int nxl = sl.lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
+  const int nxl = sl.Lx + 2 * sl.gx;                 // planes the FFT kernels index (P == 1: nx + 2 G)
+  const bool pen = sl.py > 1;
   if (sl.P > 1) {
     // planes the particles of this step reach: the slab + ghost_width planes per side (+-2 more hold psi)
     const int ge = ghost_width(sl);
-    xb = max(xb, sl.gx - ge);
-    xe = min(xe, sl.gx + sl.lx + ge);
+    xb = max(xb, sl.gx - min(ge, sl.gx));
+    xe = min(xe, sl.gx + sl.Lx + min(ge, sl.gx));
+    if (pen) {   // same for the rows of a pencil
+      const int gey = min(ge, sl.gy);
+      if (yp < sl.G + sl.gy - gey || yp >= sl.G + sl.gy + sl.Ly + gey) return;
+    }
   }
   if (z4 >= nz4 || yp >= nyp || xb >= xe) return;   // lanes run along z: a warp exits (or shrinks) as a unit per row
   const float4* __restrict__ ps = reinterpret_cast<const float4*>(sl.psi[sl.rank]);
   const long long sx4 = (long long)nyp * nz4;        // plane stride in float4
   // periodic images inside the padded array: index -/+ n (x too when P == 1; a slab's outermost planes hold
   // nothing a particle within the halo reach reads, clamp there)
-  const int ym1 = yp >= 1 ? yp - 1 : yp - 1 + sl.ny, ym2 = yp >= 2 ? yp - 2 : yp - 2 + sl.ny;
-  const int yp1 = yp + 1 < nyp ? yp + 1 : yp + 1 - sl.ny, yp2 = yp + 2 < nyp ? yp + 2 : yp + 2 - sl.ny;
+  // (rows of a pencil: ghost rows come from the y neighbours, nothing wraps - clamp like the x planes of a slab)
+  const int ym1 = pen ? max(yp - 1, 0) : (yp >= 1 ? yp - 1 : yp - 1 + sl.ny);
+  const int ym2 = pen ? max(yp - 2, 0) : (yp >= 2 ? yp - 2 : yp - 2 + sl.ny);
+  const int yp1 = pen ? min(yp + 1, nyp - 1) : (yp + 1 < nyp ? yp + 1 : yp + 1 - sl.ny);
+  const int yp2 = pen ? min(yp + 2, nyp - 1) : (yp + 2 < nyp ? yp + 2 : yp + 2 - sl.ny);
   const int zl = z4 > 0 ? z4 - 1 : z4 - 1 + sl.nz / 4, zh = z4 + 1 < nz4 ? z4 + 1 : z4 + 1 - sl.nz / 4;
   auto wrapx = [&](int i) {
     if (sl.P == 1) return i < 0 ? i + sl.nx : (i >= nxl ? i - sl.nx : i);
@@ -966,12 +1076,18 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
       // peer gets the number, the step then uses the maximum over the ranks.  Unknown range -> all gx.
       const int* mine = reinterpret_cast<const int*>(sl.flags[sl.rank]);
       const int xmin = mine[kFlagXmin], xmax = mine[kFlagXmax];
-      int need = sl.gx;
-      if (xmin <= xmax) {
-        const int raw = max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.lx - 1)));
+      int need = max(sl.gx, sl.gy);
+      if (xmin <= xmax && reach_extra < 1000) {      // reach_extra >= 1000 (JPM_SLAB_FULL_GHOST=1): always exchange every ghost plane
+        const int raw = max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.Lx - 1)));
         need = min(sl.gx, raw);
         // the outermost ghost plane was touched: some particle is at (or wrapped past) the reach of the halo
         if (raw + reach_extra >= sl.gx && t == 0) sl.flags[sl.rank][kFlagReach] = 1u;
+        if (sl.py > 1) {   // pencil grid: the rows too; one width serves both axes (clamped per axis by its users)
+          const int ymin = mine[kFlagYmin], ymax = mine[kFlagYmax];
+          const int rawy = (ymin <= ymax) ? max(0, max(sl.gy - ymin, ymax - (sl.gy + sl.Ly - 1))) : sl.gy;
+          need = max(need, min(sl.gy, rawy));
+          if (rawy + reach_extra >= sl.gy && t == 0) sl.flags[sl.rank][kFlagReach] = 1u;
+        }
       }
       asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(sl.flags[t] + kFlagGeSlots + sl.rank), "r"(need) : "memory");
     }
@@ -998,9 +1114,11 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
       ge = max(ge, (int)v);
     }
     int* mine = reinterpret_cast<int*>(sl.flags[sl.rank]);
-    mine[kFlagGe] = min(ge, sl.gx);
+    mine[kFlagGe] = min(ge, max(sl.gx, sl.gy));
     mine[kFlagXmin] = 0x7fffffff;          // the next paint starts a new range
     mine[kFlagXmax] = (int)0x80000000;
+    mine[kFlagYmin] = 0x7fffffff;
+    mine[kFlagYmax] = (int)0x80000000;
   }
   __threadfence_system();
 }
@@ -1019,7 +1137,7 @@ __global__ void slab_stats_kernel(const __grid_constant__ Slab sl, const double*
 // ghost planes per side in use this step (see slab_barrier_kernel); P == 1: the periodic images, always gx
 __device__ __forceinline__ int ghost_width(const Slab& sl) {
   if (sl.P == 1) return sl.gx;
-  return min(sl.gx, reinterpret_cast<const int*>(sl.flags[sl.rank])[kFlagGe]);
+  return min(max(sl.gx, sl.gy), reinterpret_cast<const int*>(sl.flags[sl.rank])[kFlagGe]);
 }
 
 static void make_twiddles(int n, int count, std::vector<float2>& out) {
@@ -1112,7 +1230,9 @@ static int32_t set_attrs(const Slab& sl) {
 #undef ATTR_X
 #define ATTR_Z(N_)                                                                                              \
   JPM_CUDA(cudaFuncSetAttribute(zfwd_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>())); \
-  JPM_CUDA(cudaFuncSetAttribute(zinv_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>()));
+  JPM_CUDA(cudaFuncSetAttribute(zinv_kernel<N_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>())); \
+  JPM_CUDA(cudaFuncSetAttribute(zfwd_kernel<N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>())); \
+  JPM_CUDA(cudaFuncSetAttribute(zinv_kernel<N_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)z_smem<N_>()));
   JPM_FFT_SWITCH(sl.nz, ATTR_Z)
 #undef ATTR_Z
   return JPM_OK;
@@ -1209,6 +1329,7 @@ int32_t pmfft_enable(jpm_plan* p) {
   sl.P = 1; sl.rank = 0;
   sl.nx = p->nx; sl.ny = p->ny; sl.nz = p->nz;
   sl.lx = p->nx; sl.ly = p->ny; sl.gx = p->G; sl.G = p->G;
+  sl.px = sl.py = 1; sl.Lx = p->nx; sl.Ly = p->ny; sl.gy = 0;
   sl.nxp = p->nxp; sl.nyp = p->nyp; sl.nzp = p->nzp; sl.npad = p->npad;
   sl.nzh = p->nzh; sl.nzc = (p->nzh + 7) & ~7;
   const long long na = (long long)sl.nx * sl.ny * sl.nzc;
@@ -1250,8 +1371,9 @@ int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width, in
   // jpm_slab_check reports a trip instead of letting later kernels consume incomplete peer data silently
   static const long long timeout_cycles =
       (long long)((getenv("JPM_SLAB_TIMEOUT_S") ? std::max(0.1, atof(getenv("JPM_SLAB_TIMEOUT_S"))) : 4.0) * 2.0e9);
+  static const bool full_ghost = getenv("JPM_SLAB_FULL_GHOST") && getenv("JPM_SLAB_FULL_GHOST")[0] == '1';
   if (exchange_ghost_width)
-    fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, reach_extra, timeout_cycles);
+    fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, full_ghost ? 1000 : reach_extra, timeout_cycles);
   else
     fft::slab_barrier_kernel<false><<<1, 32, 0, st>>>(p->slab, ++p->epoch, 0, timeout_cycles);
   JPM_LAUNCH_CHECK();
@@ -1284,8 +1406,12 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
   for (int x0 = 0; x0 < sl.lx; x0 += cx) {
     const int nxl = std::min(cx, sl.lx - x0);
 #define RUN_ZF(N_)                                                                                             \
-  zfwd_kernel<N_><<<dim3(sl.ny / kRows, nxl, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
-      sl, p->tw_zh, p->tw_zfull, x0);
+  if (sl.py > 1)                                                                                               \
+    zfwd_kernel<N_, true><<<dim3(sl.ny / kRows, nxl, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(    \
+        sl, p->tw_zh, p->tw_zfull, x0);                                                                        \
+  else                                                                                                         \
+    zfwd_kernel<N_><<<dim3(sl.ny / kRows, nxl, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
+        sl, p->tw_zh, p->tw_zfull, x0);
     JPM_FFT_SWITCH(sl.nz, RUN_ZF)
 #undef RUN_ZF
     JPM_LAUNCH_CHECK();
@@ -1341,8 +1467,12 @@ int32_t pmfft_forces(jpm_plan* p, cudaStream_t st, float r_split, const float* f
     JPM_LAUNCH_CHECK();
     if (p->timer && !chunked) p->timer->mark(st, "ifft_y_x3");
 #define RUN_ZI(N_)                                                                                             \
-  zinv_kernel<N_><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(            \
-      sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0, 0);
+  if (sl.py > 1)                                                                                               \
+    zinv_kernel<N_, true><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(    \
+        sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0, 0);                                          \
+  else                                                                                                         \
+    zinv_kernel<N_><<<dim3(sl.ny / kRows, nxl, 3), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
+        sl, p->tw_zh, p->tw_zfull, p->az, x0, p->fft_zvariant, 0, 0);
     JPM_FFT_SWITCH(sl.nz, RUN_ZI)
 #undef RUN_ZI
     JPM_LAUNCH_CHECK();
@@ -1385,8 +1515,12 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   int32_t rc;
   if (!skip_first_barrier && (rc = slab_barrier(p, st, true, 2))) return rc;
 #define RUN_ZF(N_)                                                                                             \
-  zfwd_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
-      sl, p->tw_zh, p->tw_zfull, 0);
+  if (sl.py > 1)                                                                                               \
+    zfwd_kernel<N_, true><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(  \
+        sl, p->tw_zh, p->tw_zfull, 0);                                                                         \
+  else                                                                                                         \
+    zfwd_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(        \
+        sl, p->tw_zh, p->tw_zfull, 0);
   JPM_FFT_SWITCH(sl.nz, RUN_ZF)
 #undef RUN_ZF
   JPM_LAUNCH_CHECK();
@@ -1435,8 +1569,12 @@ int32_t pmfft_potential(jpm_plan* p, cudaStream_t st, float r_split, const float
   JPM_LAUNCH_CHECK();
   if (p->timer) p->timer->mark(st, "ifft_y");
 #define RUN_ZP(N_)                                                                                             \
-  zinv_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(          \
-      sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2, to_psi ? 1 : 0);
+  if (sl.py > 1)                                                                                               \
+    zinv_kernel<N_, true><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(  \
+        sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2, to_psi ? 1 : 0);                              \
+  else                                                                                                         \
+    zinv_kernel<N_><<<dim3(sl.ny / kRows, sl.lx, 1), threads_for<N_ / 2, kRows>(), z_smem<N_>(), st>>>(        \
+        sl, p->tw_zh, p->tw_zfull, p->az, 0, p->fft_zvariant, 2, to_psi ? 1 : 0);
   JPM_FFT_SWITCH(sl.nz, RUN_ZP)
 #undef RUN_ZP
   JPM_LAUNCH_CHECK();
@@ -1456,7 +1594,7 @@ int32_t pmfft_linear_field(jpm_plan* p, cudaStream_t st, const float* tab, int n
 int32_t pmfft_gradient(jpm_plan* p, cudaStream_t st) {
   const Slab& sl = p->slab;
   JPM_CHECK_ARG(sl.psi[sl.rank], "no psi mesh (run pmfft_potential(to_psi) first)");
-  const int nxl = sl.lx + 2 * sl.gx;
+  const int nxl = sl.Lx + 2 * sl.gx;
   unsigned* fmax_bits = p->pot_stats ? reinterpret_cast<unsigned*>(p->pot_stats + 1) : nullptr;
   fft::fdgrad_kernel<<<dim3((sl.nzp / 4 + 31) / 32, (sl.nyp + 7) / 8, (nxl + fft::kGradPlanes - 1) / fft::kGradPlanes), 256, 0, st>>>(
       sl, 0, nxl, fmax_bits);

@@ -442,7 +442,7 @@ template <bool REL, int TS, int M, bool TMA>
 __global__ void __launch_bounds__(256, JPM_PAINT_CTAS)
 sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4* __restrict__ spos,
                  const int* __restrict__ start, float* __restrict__ mesh, int* __restrict__ count,
-                 unsigned long long* __restrict__ stats, int* __restrict__ xrange) {
+                 unsigned long long* __restrict__ stats, int* __restrict__ xrange, int track_y) {
   // TMA boxes must start on a 16-byte boundary of the innermost (z) axis (misaligned coordinates raise
   // "illegal instruction", tools/tma_probe.cu): the z margin below the tile is kTmaMz = 4 cells there.
   constexpr int T = 1 << TS, B = T + 2 * M + 1, MZ = TMA ? kTmaMz : M;
@@ -453,8 +453,9 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
   unsigned* const lo = sbox;
   unsigned* const hi = sbox + NBOX;
   __shared__ int scnt[28];                             // 27 neighbour tiles + generic-stencil count
-  __shared__ int sxr[2];                               // lowest / highest x plane touched (slab plans: ghost width)
+  __shared__ int sxr[4];                               // lowest / highest x plane (and y row) touched (slab plans: ghost width)
   int xlo = 0x7fffffff, xhi = (int)0x80000000;
+  int ylo = 0x7fffffff, yhi = (int)0x80000000;        // pencil grids: the rows too (xrange[3], xrange[4])
   const int t = blockIdx.x;
   const int beg = start[t], end = start[t + 1];
   if (beg == end) return;
@@ -475,7 +476,7 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
     if (threadIdx.x < NW - 4 * NW4) sbox[4 * NW4 + threadIdx.x] = 0u;
   }
   if (threadIdx.x < 28) scnt[threadIdx.x] = 0;
-  if (threadIdx.x < 2) sxr[threadIdx.x] = threadIdx.x ? (int)0x80000000 : 0x7fffffff;
+  if (threadIdx.x < 4) sxr[threadIdx.x] = (threadIdx.x & 1) ? (int)0x80000000 : 0x7fffffff;
   __syncthreads();
   for (int qb = beg + (threadIdx.x & ~31); qb < end; qb += blockDim.x) {   // warp-uniform trip count
     const bool valid = q < end;
@@ -513,6 +514,7 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
         }
         ti = s.i0 >> TS; tj = s.j0 >> TS; tk = s.k0 >> TS;
         xlo = min(xlo, s.i0); xhi = max(xhi, s.i0 + 1);
+        if (track_y) { ylo = min(ylo, s.j0); yhi = max(yhi, s.j0 + 1); }
       } else {
         Cic1 cx, cy, cz;
         sim_stencil<REL>(g, p.x, p.y, p.z, __float_as_int(p.w), cx, cy, cz);
@@ -535,6 +537,10 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
         if (c.inside) ++nslow; else atomicAdd(stats, 1ull);
         if (cx.i0 >= 0) { xlo = min(xlo, cx.i0); xhi = max(xhi, cx.i0); }
         if (cx.i1 >= 0) { xlo = min(xlo, cx.i1); xhi = max(xhi, cx.i1); }
+        if (track_y) {
+          if (cy.i0 >= 0) { ylo = min(ylo, cy.i0); yhi = max(yhi, cy.i0); }
+          if (cy.i1 >= 0) { ylo = min(ylo, cy.i1); yhi = max(yhi, cy.i1); }
+        }
         ti = max(cx.i0, 0) >> TS; tj = max(cy.i0, 0) >> TS; tk = max(cz.i0, 0) >> TS;
       }
     }
@@ -562,11 +568,18 @@ sim_paint_kernel(const __grid_constant__ CUtensorMap tm, SimGeom g, const float4
     xlo = __reduce_min_sync(0xffffffffu, xlo);
     xhi = __reduce_max_sync(0xffffffffu, xhi);
     if (lane == 0) { atomicMin(sxr, xlo); atomicMax(sxr + 1, xhi); }
+    if (track_y) {
+      ylo = __reduce_min_sync(0xffffffffu, ylo);
+      yhi = __reduce_max_sync(0xffffffffu, yhi);
+      if (lane == 0) { atomicMin(sxr + 2, ylo); atomicMax(sxr + 3, yhi); }
+    }
   }
   __syncthreads();
-  if (xrange && threadIdx.x < 2) {
+  if (xrange && threadIdx.x < 4) {
     if (threadIdx.x == 0) atomicMin(xrange, sxr[0]);
-    else atomicMax(xrange + 1, sxr[1]);
+    else if (threadIdx.x == 1) atomicMax(xrange + 1, sxr[1]);
+    else if (track_y && threadIdx.x == 2) atomicMin(xrange + (kFlagYmin - kFlagXmin), sxr[2]);
+    else if (track_y) atomicMax(xrange + (kFlagYmax - kFlagXmin), sxr[3]);
   }
   if (threadIdx.x == 27 && scnt[27]) atomicAdd(stats + 2, (unsigned long long)scnt[27]);
   if (threadIdx.x < 27 && scnt[threadIdx.x]) {
@@ -1116,14 +1129,15 @@ static int32_t sim_paint_impl(jpm_sim* s, cudaStream_t st, float* mesh, bool tma
   // slab plans: record the x planes the particles touch, the first barrier of the step turns it into the ghost width
   int* xrange = (tma && s->plan && s->plan->is_slab && s->plan->slab.P > 1)
                     ? reinterpret_cast<int*>(s->plan->slab.flags[s->plan->slab.rank]) + kFlagXmin : nullptr;
+  const int track_y = (xrange && s->plan->slab.py > 1) ? 1 : 0;
 #define LAUNCH_PAINT_T(TS_, M_, TMA_)                                                                    \
   {                                                                                                      \
     if (s->relative)                                                                                     \
       sim_paint_kernel<true, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(             \
-          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange);             \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange, track_y);    \
     else                                                                                                 \
       sim_paint_kernel<false, TS_, M_, TMA_><<<g.nt, 256, paint_smem<TS_, M_, TMA_>(), st>>>(            \
-          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange);             \
+          s->tm_rho, g, s->pos[s->cur], s->start[s->cur], mesh, s->count, s->stats, xrange, track_y);    \
   }
 #define LAUNCH_PAINT(TS_, M_) LAUNCH_PAINT_T(TS_, M_, false)
 #define LAUNCH_PAINT_TMA(TS_, M_) LAUNCH_PAINT_T(TS_, M_, true)

@@ -262,19 +262,23 @@ class ShardedStepper:
 
 def make_stepper(disp, vel, halo_size, sh, resident=True, tile=None, margin=None, fused=True,
                  force_mode="spectral"):
-    """The fastest stepper that serves this decomposition: the peer-memory slab stepper (slab.py: halo
-    reduce / FFT transposes / halo fill inside the FFT kernels, no NCCL on the data path) for a (P, 1)
-    process grid on power-of-two meshes, else the NCCL stepper above."""
+    """The fastest stepper that serves this decomposition: the peer-memory stepper (slab.py: halo reduce / FFT
+    transposes / halo fill inside the FFT kernels, no NCCL on the data path) for slab (P, 1) and pencil (px, py)
+    process grids on power-of-two meshes, else the NCCL stepper above."""
     from . import slab
-    hx, _ = _halos(halo_size, sh)
+    hx, hy = _halos(halo_size, sh)
     gshape = sh.global_shape(tuple(disp.shape[:3]))
     # the slab stepper's ghost planes play the role of the reference's halo; its validity limit is the
-    # reference's (|displacement| < halo // 2 is exchanged, painting.py:192-215)
-    if fused and resident and slab.slab_supported(gshape, sh.pdims, hx):
+    # reference's (|displacement| < halo // 2 is exchanged, painting.py:192-215).  A grid with px == 1 has no halo in x
+    # in the reference (get_halo_size zeroes it): its x ghost planes are the rank's own periodic images, any width does
+    if sh.pdims[1] > 1 and sh.pdims[0] == 1 and hx < 1:
+        hx = max(hy, 4)
+    if fused and resident and slab.slab_supported(gshape, sh.pdims, hx, hy):
         return slab.SlabStepper(disp, vel, hx, sh.size, sh.rank, group=sh.group, tile=tile,
-                                margin=1 if margin is None else margin, force_mode=force_mode)
+                                margin=1 if margin is None else margin, force_mode=force_mode, pdims=sh.pdims, gy=hy)
     if force_mode != "spectral":
-        raise NotImplementedError("force_mode != 'spectral' needs the fused slab path (pdims (P, 1), power-of-two mesh)")
+        raise NotImplementedError("force_mode != 'spectral' needs the fused peer-memory path (power-of-two mesh, "
+                                  "nx, ny divisible by the rank count, ny / py a multiple of 16)")
     return ShardedStepper(disp, vel, halo_size, sh, resident=resident, tile=tile, margin=2 if margin is None else margin)
 
 

@@ -1,4 +1,6 @@
-"""Multi-GPU x-slab force loop over NVLink peer memory (pdims = (P, 1), one process per GPU).
+"""Multi-GPU force loop over NVLink peer memory: x slabs (pdims = (P, 1)) and pencil grids (px, py), one process per
+GPU.  On a pencil grid the particle domain is the pencil, the FFT chain keeps x slabs and the z passes do the
+row-group transpose while they load / store (include/jaxpm_b200.h: jpm_slab_create_ex).
 
 What the reference does with three library collectives per force evaluation — halo_exchange after the
 paint, [ext] jaxdecomp.pfft3d / pifft3d all-to-alls, halo_exchange before the read
@@ -20,32 +22,43 @@ from ._lib import as_f32, call, ptr, stream
 _HANDLE_BYTES = 64
 
 
-def slab_supported(global_shape, pdims, halo_x):
-    """True when the fused slab path can serve this decomposition."""
+def slab_supported(global_shape, pdims, halo_x, halo_y=None):
+    """True when the fused peer-memory path can serve this decomposition: x slabs (P, 1) or a pencil grid (px, py)."""
     nx, ny, nz = (int(s) for s in global_shape)
     px, py = pdims
+    P = px * py
     pow2 = lambda n: 16 <= n <= 1024 and (n & (n - 1)) == 0
-    if py != 1 or px < 1 or px > 8 or not (pow2(nx) and pow2(ny) and pow2(nz)):
+    if px < 1 or py < 1 or P > 8 or not (pow2(nx) and pow2(ny) and pow2(nz)):
         return False
-    if nx % px or ny % px:
+    if nx % P or ny % P:
         return False
-    lx = nx // px
-    return 1 <= halo_x <= lx and lx + 2 * halo_x >= 16
+    Lx, Ly = nx // px, ny // py
+    if not (1 <= halo_x <= Lx and Lx + 2 * halo_x >= 16):
+        return False
+    if py > 1:
+        hy = halo_x if halo_y is None else halo_y
+        if not (1 <= hy <= Ly and Ly % 16 == 0):
+            return False
+    return True
 
 
 class SlabPlan:
-    """One rank's jpm_plan of the slab decomposition (buffers + peer mappings)."""
+    """One rank's jpm_plan of the slab / pencil decomposition (buffers + peer mappings).  `nranks` is the rank count
+    of an x-slab grid, or pass `pdims=(px, py)` (rank = a py + b) with the y ghost width `gy` for a pencil grid."""
 
-    def __init__(self, global_shape, nranks, rank, gx, device):
+    def __init__(self, global_shape, nranks, rank, gx, device, pdims=None, gy=0):
         self.global_shape = tuple(int(s) for s in global_shape)
-        self.nranks, self.rank, self.gx, self.device = int(nranks), int(rank), int(gx), torch.device(device)
+        self.pdims = (int(nranks), 1) if pdims is None else (int(pdims[0]), int(pdims[1]))
+        self.nranks, self.rank, self.gx, self.device = self.pdims[0] * self.pdims[1], int(rank), int(gx), torch.device(device)
+        self.gy = int(gy) if self.pdims[1] > 1 else 0
         nx, ny, nz = self.global_shape
-        self.lx = nx // self.nranks
-        self.local_shape = (self.lx, ny, nz)
-        self.mesh_shape = (self.lx + 2 * self.gx, ny, nz)     # what the particle kernels see
+        self.lx = nx // self.nranks                            # FFT slab of this rank
+        self.Lx, self.Ly = nx // self.pdims[0], ny // self.pdims[1]
+        self.local_shape = (self.Lx, self.Ly, nz)              # the rank's particle / mesh block
+        self.mesh_shape = (self.Lx + 2 * self.gx, self.Ly + 2 * self.gy, nz)     # what the particle kernels see
         h = C.c_void_p()
         with torch.cuda.device(self.device):
-            call("jpm_slab_create", C.byref(h), nx, ny, nz, self.nranks, self.rank, self.gx)
+            call("jpm_slab_create_ex", C.byref(h), nx, ny, nz, self.pdims[0], self.pdims[1], self.rank, self.gx, self.gy)
         self.handle = h
         self.attached = False
 
@@ -129,19 +142,21 @@ class SlabStepper:
     identical to the reference for every particle within its halo reach (|disp_x| < gx)."""
 
     def __init__(self, disp, vel, gx, nranks, rank, group=None, tile=None, margin=1, plan=None,
-                 force_mode="spectral"):
+                 force_mode="spectral", pdims=None, gy=0):
         d = as_f32(disp)
-        lx, ny, nz = d.shape[:3]
+        Lx, Ly, nz = d.shape[:3]
         self.device = d.device
         self.group = group
-        self.plan = plan if plan is not None else SlabPlan((lx * nranks, ny, nz), nranks, rank, gx, d.device)
+        pd = (int(nranks), 1) if pdims is None else (int(pdims[0]), int(pdims[1]))
+        self.plan = plan if plan is not None else SlabPlan((Lx * pd[0], Ly * pd[1], nz), nranks, rank, gx, d.device,
+                                                           pdims=pd, gy=gy)
         if not self.plan.attached and plan is None:
             connect(self.plan, group)
         ms = self.plan.mesh_shape
         if tile is None:
             tile = 16 if min(ms) >= 64 else 8
-        self.sim = ops.Sim(ms, (lx, ny, nz), True, d.device, halo=(gx, 0), tile=tile, margin=margin,
-                           plan=self.plan)
+        self.sim = ops.Sim(ms, (Lx, Ly, nz), True, d.device, halo=(self.plan.gx, self.plan.gy), tile=tile,
+                           margin=margin, plan=self.plan)
         if force_mode != "spectral":
             # "potential": one inverse transform + the gradient pass (psi ghosts over NVLink instead of three force
             # meshes); "auto": per step from the GLOBAL error bound, the same decision on every rank

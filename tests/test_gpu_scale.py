@@ -100,19 +100,60 @@ def test_config2_256_against_oracle_run(cuda, force_mode):
         jpm_pm._FAST_API = True
     assert float((F - F_slow).abs().max()) / float(g["force0_max"]) < FIELD_TOL
     del F_slow
-    # (b) against the oracle's run.  Its displacement differs from the CUDA one by fp32 rounding, so a particle within
-    # that distance of the reference's dropped-corner window at the periodic edge (see test_nbody_config1: for
-    # coordinates in (-ulp(N)/2, 0) the reference paints nothing) can take the other branch in ONE of the two runs and
-    # move one particle mass in one cell: with 1.7e7 particles ~1 such event per paint, felt by its neighbourhood only
+    # (b) against the oracle's run.  Its displacement differs from the CUDA one by fp32 rounding, and the reference's
+    # relative-mode rule (painting_utils.py:48-65) is DISCONTINUOUS in two kinds of places, where a particle can take
+    # the other branch in ONE of the two runs and move up to one particle mass:
+    #   * the dropped-corner window at the periodic edge (+ mode='drop'): a corner coordinate in (-ulp(N)/2, 0) wraps
+    #     to N in fp32 and is dropped (see test_nbody_config1);
+    #   * just below every power of two 2^k: pp and pp + 1 lie in different binades, pp + 1 rounds UP to 2^k + 1, the
+    #     second corner lands one cell too far with weight ~ -ulp and the particle paints (almost) nothing.
+    # Such particles are found here explicitly; every sampled particle must then agree to 1e-5 PLUS the field of a
+    # unit point mass at each of them (1 / 4 pi r^2 - at 1e-5 of max|F| = 3.5 one flipped particle is felt out to
+    # r ~ 48 cells), and strictly to 1e-5 when there is none.
+    w = float(np.spacing(np.float32(n))) / 2
+    grid_i = [torch.arange(m, device=cuda, dtype=torch.float32) for m in shape]
+    border = torch.zeros(shape, dtype=torch.bool, device=cuda)
+    for ax in range(3):
+        view = [1, 1, 1]
+        view[ax] = -1
+        x = grid_i[ax].view(view) + dx[..., ax]
+        for edge in (0.0, -w, -1.0, -1.0 - w):
+            border |= (x - edge).abs() < 5e-6
+        for kpow in range(0, int(np.log2(n)) + 1):
+            e2 = float(2 ** kpow)
+            border |= ((x - e2) > -(float(np.spacing(np.float32(e2))) + 3e-6)) & ((x - e2) < 3e-6)
+    bpos = border.nonzero().to(torch.float32)                     # Lagrangian sites; |dx| << the radii that matter
     err = np.abs(_sample(F, ids) - g["force0"]).max(-1) / float(g["force0_max"])
+    allow = np.full(err.shape, FIELD_TOL)
+    if bpos.shape[0]:
+        spos = torch.as_tensor(np.stack(np.unravel_index(ids, shape), -1), device=cuda, dtype=torch.float32)
+        dd = (spos[:, None, :] - bpos[None, :, :]).abs()
+        dd = torch.minimum(dd, float(n) - dd)
+        r2 = (dd * dd).sum(-1).clamp_min(1.0)
+        allow = allow + (2.0 / (4 * np.pi * r2) / float(g["force0_max"])).sum(-1).cpu().numpy()
     nbad = int((err > FIELD_TOL).sum())
-    print(f"[config2 {force_mode}] force0: median {np.median(err):.2e}, q99.9 {np.quantile(err, 0.999):.2e}, "
-          f"max {err.max():.2e}, {nbad} of {err.size} sampled particles above {FIELD_TOL}")
-    assert np.quantile(err, 0.999) < FIELD_TOL and nbad <= max(8, err.size // 1000)
+    print(f"[config2 {force_mode}] force0: median {np.median(err):.2e}, max {err.max():.2e}, {nbad} of {err.size} sampled "
+          f"particles above {FIELD_TOL}; {bpos.shape[0]} particle(s) within 5e-6 of a discontinuity of the reference rule: "
+          f"{bpos.cpu().numpy().astype(int).tolist()[:4]}; worst err / allowance {float((err / allow).max()):.2f}")
+    assert (err <= allow).all()
+    assert bpos.shape[0] <= 64
     assert abs(float(F.abs().max()) / float(g["force0_max"]) - 1) < 1e-4
     del F
     rho = cic_paint_dx(dx)
-    assert np.abs(_block_sums(rho) - g["lpt_rho_blocks"]).max() / np.abs(g["lpt_rho_blocks"]).max() < FIELD_TOL
+    # density block sums (8^3 cells per block): to 1e-5 of the largest block everywhere, except in the blocks a particle
+    # found above paints into (its Lagrangian block and the neighbours |dx| < 8 away), where up to ONE particle mass
+    # per such particle may differ
+    dblk = np.abs(_block_sums(rho) - g["lpt_rho_blocks"])
+    bw = n // 32
+    may = np.zeros(dblk.shape, dtype=bool)
+    for site in bpos.cpu().numpy().astype(int):
+        c = site // bw
+        for o in np.ndindex(3, 3, 3):
+            may[tuple((c + np.array(o) - 1) % 32)] = True
+    tol_blk = FIELD_TOL * np.abs(g["lpt_rho_blocks"]).max()
+    print(f"[config2 {force_mode}] density blocks: max diff {dblk.max():.3f} particle masses, {(dblk > tol_blk).sum()} blocks above "
+          f"{tol_blk:.4f}, all next to a flagged particle: {bool(may[dblk > tol_blk].all())}")
+    assert (dblk[~may] < tol_blk).all() and dblk.max() < 1.01 and (dblk > tol_blk).sum() <= 2 * max(1, bpos.shape[0])
     _, pk = power_spectrum(rho, box_shape=box)
     assert np.abs(pk.cpu().numpy() / g["lpt_pk"] - 1).max() < 1e-4
     del rho
