@@ -226,6 +226,28 @@ def gen_distributed_slab():
     save("distributed_slab", **out)
 
 
+def gen_distributed_pencil():
+    """Pencil decompositions (pdims (px, py), tests/test_distributed_pm.py:28) of a power-of-two mesh in the shapes the
+    fused peer-memory path serves (ny / py a multiple of 16): the reference's own sharded paint / pm_forces /
+    uniform_particles (two grids, to keep the fixture small)."""
+    shape, halo = (32, 64, 16), 8
+    rng = np.random.default_rng(29)
+    lim = 3.5
+    disp = (lim * np.tanh(1.4 * rng.standard_normal((*shape, 3)) / lim)).astype(np.float32)
+    out = dict(disp=disp, halo=np.int32(halo))
+    clear_mesh()
+    out["single_paint"] = painting.cic_paint_dx(jnp.asarray(disp))
+    for pd in ((2, 2), (2, 4)):
+        tag = f"p{pd[0]}{pd[1]}"
+        sh = NamedSharding(make_mesh(pd), P('x', 'y'))
+        out[f"{tag}_paint"] = painting.cic_paint_dx(jnp.asarray(disp), halo_size=(halo, halo), sharding=sh)
+        out[f"{tag}_forces"] = pm.pm_forces(jnp.asarray(disp), mesh_shape=shape, paint_absolute_pos=False,
+                                            halo_size=(halo, halo), sharding=sh)
+        out[f"{tag}_particles"] = np.asarray(distributed.uniform_particles(shape, sharding=sh)).astype(np.int16)
+        clear_mesh()
+    save("distributed_pencil", **out)
+
+
 def gen_power_spectrum():
     rng = np.random.default_rng(17)
     shape, box = (16, 16, 24), (100.0, 100.0, 150.0)
@@ -263,7 +285,7 @@ def gen_widened():
 if __name__ == "__main__":
     only = sys.argv[1:]
     for fn in (gen_paint_read_abs, gen_paint_read_rel, gen_kernels, gen_pm_forces, gen_lpt, gen_growth_ode,
-               gen_distributed, gen_distributed_slab, gen_power_spectrum, gen_widened):
+               gen_distributed, gen_distributed_slab, gen_distributed_pencil, gen_power_spectrum, gen_widened):
         if only and fn.__name__ not in only:
             continue
         fn()

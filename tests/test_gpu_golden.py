@@ -227,9 +227,65 @@ def test_golden_slab_path(cuda, P):
         s_.close(barrier=False)
 
 
+@pytest.mark.parametrize("pdims", [(2, 2), (2, 4)])
+def test_golden_pencil_path(cuda, pdims):
+    """The fused peer-memory path on PENCIL process grids (pencil particle domains, x-slab FFT chain, row-group transpose
+    inside the z passes; jaxpm_b200/slab.py, csrc/pmfft.cu) with px py ranks in this process, fed the inputs of
+    tests/golden/distributed_pencil.npz and compared DIRECTLY with what the reference's own sharded cic_paint_dx /
+    pm_forces computed for these pdims, halo 8 (jaxpm/painting.py:192-215, pm.py:12-58, distributed.py:45-129;
+    tests/test_distributed_pm.py:28): the painted density (per-rank ghost-zone arrays folded on the host) and the
+    force on every particle (one kick of unit coefficient from zero velocity)."""
+    from jaxpm_b200.slab import SlabPlan, SlabStepper
+    g = gold("distributed_pencil")
+    disp, h = g["disp"], int(g["halo"])
+    shape = disp.shape[:3]
+    nx, ny, nz = shape
+    px, py = pdims
+    P = px * py
+    Lx, Ly = nx // px, ny // py
+    blk = lambda a_: [a_[rx * Lx:(rx + 1) * Lx, ry * Ly:(ry + 1) * Ly] for rx in range(px) for ry in range(py)]
+    plans = [SlabPlan(shape, P, r, h, cuda, pdims=pdims, gy=h) for r in range(P)]
+    for p in plans:
+        p.attach_local(plans)
+    streams = [torch.cuda.Stream(cuda) for _ in range(P)]
+    dl = [T(b, cuda) for b in blk(disp)]
+    vl = [torch.zeros_like(d) for d in dl]
+    torch.cuda.synchronize()
+    st = []
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            st.append(SlabStepper(dl[r], vl[r], h, P, r, tile=8, margin=1, plan=plans[r], pdims=pdims, gy=h))
+    for r in range(P):
+        with torch.cuda.stream(streams[r]):
+            st[r].step(1.0, 0.0)                     # vel = 0 + 1 * F(disp); no drift
+    G = 4
+    rho = np.zeros(shape, np.float64)
+    for r in range(P):
+        rx, ry = divmod(r, py)
+        with torch.cuda.stream(streams[r]):
+            st[r].store(dl[r], vl[r])
+            a = N(_padded_density(plans[r], cuda)).astype(np.float64)
+        # local (xl, yl) of the rank's mesh (its pencil + h ghost planes / rows per side) is global
+        # (rx Lx - h + xl, ry Ly - h + yl); z carries G periodic ghost cells per side; the G spare planes / rows stay empty
+        xs = (rx * Lx - h + np.arange(Lx + 2 * h)) % nx
+        ys = (ry * Ly - h + np.arange(Ly + 2 * h)) % ny
+        zs = (np.arange(nz + 2 * G) - G) % nz
+        assert a[:G].sum() == 0 and a[G + Lx + 2 * h:].sum() == 0 and a[:, :G].sum() == 0 and a[:, G + Ly + 2 * h:].sum() == 0
+        np.add.at(rho, (xs[:, None, None], ys[None, :, None], zs[None, None, :]), a[G:G + Lx + 2 * h, G:G + Ly + 2 * h])
+    torch.cuda.synchronize()
+    tag = f"p{px}{py}"
+    assert rel_err(rho, g[f"{tag}_paint"]) < FIELD_TOL
+    join = lambda l: np.concatenate([np.concatenate([N(t) for t in l[rx * py:(rx + 1) * py]], axis=1) for rx in range(px)])
+    assert rel_err(join(vl), g[f"{tag}_forces"]) < FIELD_TOL
+    np.testing.assert_array_equal(join(dl), disp)       # zero drift: positions untouched
+    for s_ in st:
+        s_.close(barrier=False)
+
+
 @pytest.mark.parametrize("fixture,pdims", [("distributed", (2, 2)), ("distributed", (1, 4)), ("distributed", (4, 1)),
                                            ("distributed", (2, 4)), ("distributed_slab", (2, 1)),
-                                           ("distributed_slab", (4, 1))])
+                                           ("distributed_slab", (4, 1)), ("distributed_pencil", (2, 2)),
+                                           ("distributed_pencil", (2, 4))])
 def test_golden_particle_to_rank_assignment(cuda, fixture, pdims):
     """uniform_particles(sharding=Sharding(pdims, rank=r)) of the PRODUCT == the block of the reference's sharded
     uniform_particles (jaxpm/distributed.py:168-190) that rank r owns: bit-exact (integers), every rank."""

@@ -143,6 +143,22 @@ def test_sharded_protocol(pd):
     np.testing.assert_array_equal(ry, g[f"{tag}_particles"][:, :, 0, 1].astype(int) // ly)
 
 
+@pytest.mark.parametrize("pd", [(2, 2), (2, 4)])
+def test_sharded_protocol_pencil_fixture(pd):
+    """The oracle's sharded paint against the pencil fixture the GPU pencil path is judged on
+    (tests/golden/distributed_pencil.npz, 32 x 64 x 16, halo 8; tests/test_gpu_golden.py::test_golden_pencil_path)."""
+    g = gold("distributed_pencil")
+    tag, halo = f"p{pd[0]}{pd[1]}", int(g["halo"])
+    mesh, _ = D.cic_paint_dx(g["disp"], (halo, halo), pd)
+    assert rel_err(mesh, g[f"{tag}_paint"]) < TOL
+    assert rel_err(g[f"{tag}_paint"], g["single_paint"]) < 1e-5
+    shape = g["disp"].shape[:3]
+    i, j = np.meshgrid(np.arange(shape[0]), np.arange(shape[1]), indexing="ij")
+    rx, ry = D.owner_rank(i, j, shape, pd)
+    np.testing.assert_array_equal(rx, g[f"{tag}_particles"][:, :, 0, 0].astype(int) // (shape[0] // pd[0]))
+    np.testing.assert_array_equal(ry, g[f"{tag}_particles"][:, :, 0, 1].astype(int) // (shape[1] // pd[1]))
+
+
 def test_slice_unpad_rule():
     g = gold("distributed")
     np.testing.assert_allclose(D.slice_unpad_impl(g["unpad_in"], ((4, 4), (4, 4), (0, 0))), g["unpad_out_h44"],
