@@ -255,7 +255,7 @@ def run_gpu(args):
         "ifft_z_c2r_x3+ghost_fill": 24 * nc,
         # potential chain: one spectrum through the inverse half, one mesh box per tile in the read
         "fft_x_fwd+greens+ifft_x+transpose": 8 * nc, "ifft_y": 8 * nc, "ifft_z_c2r+ghost_fill": 8 * nc,
-        "tile_scan+sim_readpot_kick_drift": 48 * npart + 4 * nc,
+        "tile_scan+sim_readpot_kick_drift": 48 * npart + 4 * nc, "fd_gradient": 16 * nc,
         "fft_z_r2c+ghost_fold|fft_y_fwd (chunked pairs)": 16 * nc, "ifft_y_x3|ifft_z_c2r_x3 (chunked pairs)": 44 * nc,
         "ghost_fold": 0, "ghost_fill": 0, "fft_r2c(cuFFT)": 8 * nc, "greens_grad": 16 * nc,
         "ifft_c2r_x3(cuFFT)": 24 * nc,
@@ -295,7 +295,7 @@ def run_gpu(args):
                  "fft_z_r2c+ghost_fold": "zfwd_kernel", "fft_y_fwd+transpose": "yfwd_kernel",
                  "fft_x_fwd+greens_grad+ifft_x_x2+transpose": "xfused_kernel", "ifft_y_x3": "yinv_kernel",
                  "ifft_z_c2r_x3+ghost_fill": "zinv_kernel", "fft_x_fwd+greens+ifft_x+transpose": "xpot_kernel",
-                 "ifft_y": "ypot_kernel", "ifft_z_c2r+ghost_fill": "zinv_kernel(potential)"}
+                 "ifft_y": "ypot_kernel", "ifft_z_c2r+ghost_fill": "zinv_kernel(potential)", "fd_gradient": "fdgrad_kernel"}
         traffic = {stage: tj[kern]["traffic"] for stage, kern in names.items() if kern in tj}
     except Exception:
         pass

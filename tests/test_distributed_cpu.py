@@ -196,14 +196,19 @@ def test_slab_handle_exchange(world):
 
 
 def test_slab_routing_rule():
-    """Which decompositions take the fused peer-memory stepper (slab.slab_supported): (P, 1) grids on power-of-two
-    meshes with the halo inside one slab; everything else stays on the NCCL path."""
+    """Which decompositions take the fused peer-memory stepper (slab.slab_supported): slab (P, 1) and pencil (px, py)
+    grids on power-of-two meshes with the halo inside one block and ny / py a multiple of 16; everything else stays on
+    the NCCL path."""
     from jaxpm_b200.slab import slab_supported
     assert slab_supported((512, 512, 512), (8, 1), 64)
     assert slab_supported((1024, 1024, 1024), (8, 1), 64)
     assert slab_supported((32, 32, 32), (2, 1), 8)
-    assert not slab_supported((512, 512, 512), (1, 8), 64)        # y slabs
-    assert not slab_supported((512, 512, 512), (4, 2), 64)        # pencils
+    assert slab_supported((512, 512, 512), (1, 8), 64, 64)        # y slabs = a (1, P) pencil grid
+    assert slab_supported((512, 512, 512), (4, 2), 64)            # pencils (tests/test_distributed_pm.py:28)
+    assert slab_supported((512, 512, 512), (2, 4), 64, 32)
+    assert not slab_supported((64, 64, 64), (1, 8), 8, 8)         # ny / py = 8 rows: below the 16-row tiles of the z passes
+    assert not slab_supported((512, 512, 512), (2, 4), 64, 129)   # halo wider than a pencil
+    assert not slab_supported((512, 512, 512), (4, 4), 64)        # more than the 8 GPUs of a box
     assert not slab_supported((32, 32, 24), (2, 1), 8)            # not a power of two
     assert not slab_supported((512, 512, 512), (8, 1), 65)        # halo wider than a slab
     assert not slab_supported((64, 64, 64), (8, 1), 0)
