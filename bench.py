@@ -502,8 +502,9 @@ def run_grad(args):
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"d sum_b log P(k_b) / d initial_conditions: {N}^3 particles on {N}^3 mesh, "
                                f"{args.lpt_order}LPT at a=0.1, {K} drift-kick steps to a=1 (per-step recompute), "
-                               "cic_paint_dx, power_spectrum; adjoint kernels: readgrad, weighted paint, transposed "
-                               "k-space passes, 2LPT source VJP, P(k) adjoint"},
+                               "cic_paint_dx, power_spectrum; adjoint passes per step: force meshes recomputed on the fused "
+                               "chain, readgrad3 (one gather pass), paint3 (one scatter pass), real-space divergence + "
+                               "one transform pair on the potential chain, paint adjoint; 2LPT source VJP, P(k) adjoint"},
         "gpu_launches": _lib.launch_count() - l0, "loss": loss, "grad_rms": float(grad.square().mean().sqrt()),
         "grad_finite": bool(torch.isfinite(grad).all()), "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9,
     }))
@@ -516,7 +517,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--e2e-steps", type=int, default=20)
     ap.add_argument("--force-mode", default="auto", choices=["spectral", "potential", "auto"],
                     help="force path of the resident step (include/jaxpm_b200.h): three inverse transforms, one + "
                          "difference stencil, or per step by the measured fp32 error bound")

@@ -139,6 +139,21 @@ int32_t jpm_cic_paintgrad_f32(void* stream, float* mesh, const float* pos_or_dis
                               const float* weight, float weight_scalar, int64_t np, int32_t nx, int32_t ny,
                               int32_t nz, int32_t hx, int32_t hy, int32_t relative);
 
+/* The reverse-mode building blocks of pm_forces (jaxpm/pm.py:12-58) fused per pass over the particles - what
+ * jax.grad of the force loop transposes to (tests/test_gradients.py:30-80), three launches + three axpys each before:
+ *   jpm_cic_readgrad3_f32: grad[p] (+)= scale * sum_d u[p][d] * d read(m_d)(x_p) / d x_p   (m1 = m2 = NULL, cotangent =
+ *                          NULL: one mesh, grad[p] (+)= scale * d read(m0)(x_p) / d x_p - the paint adjoint);
+ *   jpm_cic_paint3_f32:    mesh3[d] += paint(x; weight = scale * u[:, d]) for d = 0..2 (mesh3: 3 contiguous meshes);
+ *   jpm_fd_divergence3_f32: out = sum_d D_d g3[d], D = the 4th-order central difference the reference's gradient
+ *                          kernel is the symbol of, so that sum_d L_d^T G_d = -jpm_density_to_potential_fused(out):
+ *                          one transform pair on the fused chain instead of three forward transforms + a k-space pass. */
+int32_t jpm_cic_readgrad3_f32(void* stream, float* grad, const float* m0, const float* m1, const float* m2,
+                              const float* pos_or_disp, const float* cotangent, float scale, int64_t np, int32_t nx,
+                              int32_t ny, int32_t nz, int32_t hx, int32_t hy, int32_t relative, int32_t accumulate);
+int32_t jpm_cic_paint3_f32(void* stream, float* mesh3, const float* pos_or_disp, const float* weights3, float scale,
+                           int64_t np, int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy, int32_t relative);
+int32_t jpm_fd_divergence3_f32(void* stream, float* out, const float* g3, int32_t nx, int32_t ny, int32_t nz);
+
 /* 2-D CIC paint of projected particles (light-cone density planes): mesh[nx][ny] += paint(pos2[np][2]) * weight[np]
  * (weight may be NULL = 1).  Replaces jaxpm/painting.py:131-158 (cic_paint_2d), same index / weight rule. */
 int32_t jpm_cic_paint_2d_f32(void* stream, float* mesh, const float* pos2, const float* weight, int64_t np,

@@ -82,6 +82,9 @@ SIGNATURES = {
     "jpm_sim_stats_host": ([vp, vp, C.POINTER(i64)], i32),
     "jpm_sim_set_force_mode": ([vp, i32], i32),
     "jpm_sim_force_info": ([vp, vp, C.POINTER(C.c_double)], i32),
+    "jpm_cic_readgrad3_f32": ([vp, vp, vp, vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32, i32], i32),
+    "jpm_cic_paint3_f32": ([vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
+    "jpm_fd_divergence3_f32": ([vp, vp, vp, i32, i32, i32], i32),
     "jpm_kernel_launch_count": ([], i64),
     "jpm_normal_field_f32": ([vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint32], i32),
     "jpm_linear_field_f32": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),

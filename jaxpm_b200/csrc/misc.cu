@@ -197,6 +197,43 @@ extern "C" int32_t jpm_axpby_f32(void* stream, float* out, float a, const float*
   return JPM_OK;
 }
 
+// 4th-order central-difference divergence of three periodic meshes, out = sum_d D_d g_d with
+// D f(x) = [8 (f(x+1) - f(x-1)) - (f(x+2) - f(x-2))] / 12 - the operator the reference's gradient kernel
+// i (8 sin w - sin 2w) / 6 (kernels.py:62-66) is the symbol of.  The adjoint of pm_forces needs
+// sum_d L_d^T G_d = -Phi (sum_d D_d G_d) (D_d antisymmetric, Phi = IFFT 1/k^2 FFT symmetric): forming the divergence
+// here leaves ONE transform pair (the potential chain) instead of three forward transforms + a k-space pass.
+__global__ void __launch_bounds__(256)
+fd_div3_kernel(float* __restrict__ out, const float* __restrict__ g0, const float* __restrict__ g1,
+               const float* __restrict__ g2, int nx, int ny, int nz) {
+  const long long n = (long long)nx * ny * nz;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  constexpr float c8 = 2.0f / 3.0f, c1 = 1.0f / 12.0f;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += stride) {
+    const int k = (int)(t % nz);
+    const long long r = t / nz;
+    const int j = (int)(r % ny), i = (int)(r / ny);
+    auto wrap = [](int a, int m) { return a < 0 ? a + m : (a >= m ? a - m : a); };
+    const long long sx = (long long)ny * nz;
+    const long long row = ((long long)i * ny + j) * nz, col = (long long)j * nz + k, pl = (long long)i * sx;
+    const float dx = c8 * (g0[wrap(i + 1, nx) * sx + col] - g0[wrap(i - 1, nx) * sx + col]) -
+                     c1 * (g0[wrap(i + 2, nx) * sx + col] - g0[wrap(i - 2, nx) * sx + col]);
+    const float dy = c8 * (g1[pl + (long long)wrap(j + 1, ny) * nz + k] - g1[pl + (long long)wrap(j - 1, ny) * nz + k]) -
+                     c1 * (g1[pl + (long long)wrap(j + 2, ny) * nz + k] - g1[pl + (long long)wrap(j - 2, ny) * nz + k]);
+    const float dz = c8 * (g2[row + wrap(k + 1, nz)] - g2[row + wrap(k - 1, nz)]) -
+                     c1 * (g2[row + wrap(k + 2, nz)] - g2[row + wrap(k - 2, nz)]);
+    out[t] = (dx + dy) + dz;
+  }
+}
+
+extern "C" int32_t jpm_fd_divergence3_f32(void* stream, float* out, const float* g3, int32_t nx, int32_t ny,
+                                          int32_t nz) {
+  JPM_CHECK_ARG(out && g3 && nx >= 4 && ny >= 4 && nz >= 4, "bad arguments (every axis needs >= 4 cells)");
+  const long long n = (long long)nx * ny * nz;
+  fd_div3_kernel<<<ew_grid(n), 256, 0, (cudaStream_t)stream>>>(out, g3, g3 + n, g3 + 2 * n, nx, ny, nz);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
 extern "C" int32_t jpm_grid_plus_disp_f32(void* stream, float* out, const float* disp, int32_t nx,
                                           int32_t ny, int32_t nz, int32_t ox, int32_t oy) {
   JPM_CHECK_ARG(out && disp && nx > 0 && ny > 0 && nz > 0, "bad arguments");

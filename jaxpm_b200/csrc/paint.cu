@@ -46,6 +46,47 @@ paint_direct_kernel(float* __restrict__ mesh, const float* __restrict__ pos,
   }
 }
 
+// Three weighted paints in one pass over the particles (the read adjoint of pm.py:54-56: G_d = paint(weight = u_d)):
+// mesh3[d][c] += u[p][d] * K(x_p, c), stencil and weights computed once, 24 REDG.E.ADD.F32.
+template <bool REL>
+__global__ void __launch_bounds__(256)
+paint3_kernel(float* __restrict__ mesh3, long long mstride, const float* __restrict__ pos, const float* __restrict__ u,
+              float scale, long long np, int nx, int ny, int nz, int pny, int pnz, int hx, int hy) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+    const float px = ld_stream(pos + 3 * p + 0);
+    const float py = ld_stream(pos + 3 * p + 1);
+    const float pz = ld_stream(pos + 3 * p + 2);
+    const float u0 = scale * ld_stream(u + 3 * p + 0), u1 = scale * ld_stream(u + 3 * p + 1),
+                u2 = scale * ld_stream(u + 3 * p + 2);
+    int bi = 0, bj = 0, bk = 0;
+    if (REL) {
+      bk = (int)(p % pnz);
+      const long long t = p / pnz;
+      bj = (int)(t % pny) + hy;
+      bi = (int)(t / pny) + hx;
+    }
+    const Cic1 cx = cic_1d<REL, false>(bi, px, nx);
+    const Cic1 cy = cic_1d<REL, false>(bj, py, ny);
+    const Cic1 cz = cic_1d<REL, false>(bk, pz, nz);
+    const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
+    const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
+          const float k = (wx[a] * wy[b]) * wz[c];
+          float* m = mesh3 + ((long long)ix[a] * ny + iy[b]) * nz + iz[c];
+          atomicAdd(m, u0 * k);
+          atomicAdd(m + mstride, u1 * k);
+          atomicAdd(m + 2 * mstride, u2 * k);
+        }
+  }
+}
+
 // Forward mode of the paint with respect to the positions (what jax.jvp / jacfwd of painting.py:15-45 produces,
 // the transpose of readgrad_kernel): mesh[c] += w_p * sum_d v_{p,d} * dK/dx_d(p, c), dK/dx_d = -sign(x_d - c_d)
 // prod_{e != d} (1 - |x_e - c_e|), sign(0) = 0.  One particle per thread, 8 REDG.E.ADD.F32.
@@ -262,6 +303,28 @@ extern "C" int32_t jpm_density_plane_f32(void* stream, float* plane, const float
   const float lo = (float)(center - width / 2), hi = (float)(center + width / 2);
   jpm::density_plane_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(plane, pos3, np, box_nx, lo, hi,
                                                                           plane_resolution);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_cic_paint3_f32(void* stream, float* mesh3, const float* pos_or_disp, const float* weights3,
+                                      float scale, int64_t np, int32_t nx, int32_t ny, int32_t nz, int32_t hx,
+                                      int32_t hy, int32_t relative) {
+  JPM_CHECK_ARG(mesh3 && pos_or_disp && weights3 && np >= 0, "null pointer");
+  JPM_CHECK_ARG(nx > 0 && ny > 0 && nz > 0 && (int64_t)nx * ny * nz < (1ll << 31), "bad mesh shape");
+  if (relative)
+    JPM_CHECK_ARG((int64_t)(nx - 2 * hx) * (ny - 2 * hy) * nz == np, "np != particle grid");
+  if (np == 0) return JPM_OK;
+  long long blocks = (np + 255) / 256;
+  const long long cap = (long long)jpm::kNumSMs * 32;
+  if (blocks > cap) blocks = cap;
+  const long long ms = (long long)nx * ny * nz;
+  if (relative)
+    jpm::paint3_kernel<true><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mesh3, ms, pos_or_disp, weights3, scale, np, nx,
+                                                                       ny, nz, ny - 2 * hy, nz, hx, hy);
+  else
+    jpm::paint3_kernel<false><<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(mesh3, ms, pos_or_disp, weights3, scale, np, nx,
+                                                                        ny, nz, ny - 2 * hy, nz, hx, hy);
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }

@@ -1077,7 +1077,9 @@ __global__ void slab_barrier_kernel(const __grid_constant__ Slab sl, unsigned ep
       const int* mine = reinterpret_cast<const int*>(sl.flags[sl.rank]);
       const int xmin = mine[kFlagXmin], xmax = mine[kFlagXmax];
       int need = max(sl.gx, sl.gy);
-      if (xmin <= xmax && reach_extra < 1000) {      // reach_extra >= 1000 (JPM_SLAB_FULL_GHOST=1): always exchange every ghost plane
+      if (reach_extra <= -1000) {                    // JPM_SLAB_GHOST_OVERRIDE=n (timing experiments only): exchange n planes
+        need = min(need, -reach_extra - 1000);
+      } else if (xmin <= xmax && reach_extra < 1000) {   // reach_extra >= 1000 (JPM_SLAB_FULL_GHOST=1): every ghost plane
         const int raw = max(0, max(sl.gx - xmin, xmax - (sl.gx + sl.Lx - 1)));
         need = min(sl.gx, raw);
         // the outermost ghost plane was touched: some particle is at (or wrapped past) the reach of the halo
@@ -1372,6 +1374,8 @@ int32_t slab_barrier(jpm_plan* p, cudaStream_t st, bool exchange_ghost_width, in
   static const long long timeout_cycles =
       (long long)((getenv("JPM_SLAB_TIMEOUT_S") ? std::max(0.1, atof(getenv("JPM_SLAB_TIMEOUT_S"))) : 4.0) * 2.0e9);
   static const bool full_ghost = getenv("JPM_SLAB_FULL_GHOST") && getenv("JPM_SLAB_FULL_GHOST")[0] == '1';
+  static const int ghost_override = getenv("JPM_SLAB_GHOST_OVERRIDE") ? atoi(getenv("JPM_SLAB_GHOST_OVERRIDE")) : -1;
+  if (ghost_override >= 0) reach_extra = -1000 - ghost_override;
   if (exchange_ghost_width)
     fft::slab_barrier_kernel<true><<<1, 32, 0, st>>>(p->slab, ++p->epoch, full_ghost ? 1000 : reach_extra, timeout_cycles);
   else

@@ -119,6 +119,54 @@ readgrad_kernel(float* __restrict__ value, float* __restrict__ grad, const float
   }
 }
 
+// The adjoint of the three reads of pm.py:54-56 with respect to the positions, in ONE pass over the particles:
+//   grad[p] (+)= sum_d u[p][d] * d read(F_d)(x_p) / d x_p      (NM == 3, cotangent u[np][3])
+//   grad[p] (+)= d read(mesh)(x_p) / d x_p                      (NM == 1, the paint adjoint: u == nullptr)
+// (three readgrad_kernel launches + three axpby before).  ACC: accumulate into grad.
+template <bool REL, int NM, bool ACC>
+__global__ void __launch_bounds__(256)
+readgradn_kernel(float* __restrict__ grad, const float* __restrict__ m0, const float* __restrict__ m1,
+                 const float* __restrict__ m2, const float* __restrict__ pos, const float* __restrict__ u, float scale,
+                 long long np, int nx, int ny, int nz, int pny, int pnz, int hx, int hy) {
+  const float* mm[3] = {m0, m1, m2};
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x; p < np; p += stride) {
+    const float px = ld_stream(pos + 3 * p + 0);
+    const float py = ld_stream(pos + 3 * p + 1);
+    const float pz = ld_stream(pos + 3 * p + 2);
+    float w[NM];
+#pragma unroll
+    for (int d = 0; d < NM; ++d) w[d] = u ? scale * ld_stream(u + NM * p + d) : scale;
+    Cic1 cx, cy, cz;
+    make_stencil<REL, true>(p, px, py, pz, nx, ny, nz, pny, pnz, hx, hy, cx, cy, cz);
+    const int ix[2] = {cx.i0, cx.i1}, iy[2] = {cy.i0, cy.i1}, iz[2] = {cz.i0, cz.i1};
+    const float wx[2] = {cx.w0, cx.w1}, wy[2] = {cy.w0, cy.w1}, wz[2] = {cz.w0, cz.w1};
+    const float sx[2] = {cx.s0, cx.s1}, sy[2] = {cy.s0, cy.s1}, sz[2] = {cz.s0, cz.s1};
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a)
+#pragma unroll
+      for (int b = 0; b < 2; ++b)
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (REL && (ix[a] < 0 || iy[b] < 0 || iz[c] < 0)) continue;
+          const long long o = ((long long)ix[a] * ny + iy[b]) * nz + iz[c];
+          float m = 0.f;
+#pragma unroll
+          for (int d = 0; d < NM; ++d) m = fmaf(w[d], __ldg(mm[d] + o), m);
+          gx = fmaf(m, (sx[a] * wy[b]) * wz[c], gx);
+          gy = fmaf(m, (wx[a] * sy[b]) * wz[c], gy);
+          gz = fmaf(m, (wx[a] * wy[b]) * sz[c], gz);
+        }
+    if (ACC) {
+      gx += grad[3 * p + 0]; gy += grad[3 * p + 1]; gz += grad[3 * p + 2];
+    }
+    st_stream(grad + 3 * p + 0, gx);
+    st_stream(grad + 3 * p + 1, gy);
+    st_stream(grad + 3 * p + 2, gz);
+  }
+}
+
 static int grid_for(long long np) {
   long long blocks = (np + 255) / 256;
   const long long cap = (long long)kNumSMs * 32;
@@ -224,6 +272,35 @@ extern "C" int32_t jpm_cic_readgrad_f32(void* stream, float* value, float* grad,
   else
     readgrad_kernel<false><<<grid_for(np), 256, 0, s>>>(value, grad, mesh, pos_or_disp, grad_scale,
                                                         grad_scale_scalar, np, nx, ny, nz, pny, nz, hx, hy);
+  JPM_LAUNCH_CHECK();
+  return JPM_OK;
+}
+
+extern "C" int32_t jpm_cic_readgrad3_f32(void* stream, float* grad, const float* m0, const float* m1, const float* m2,
+                                         const float* pos_or_disp, const float* cotangent, float scale, int64_t np,
+                                         int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy, int32_t relative,
+                                         int32_t accumulate) {
+  JPM_CHECK_ARG(grad && m0 && pos_or_disp && np >= 0, "null pointer");
+  JPM_CHECK_ARG((m1 != nullptr) == (m2 != nullptr), "pass one mesh or three");
+  JPM_CHECK_ARG(!(m1 && !cotangent), "three meshes need the cotangent u[np][3]");
+  JPM_CHECK_ARG(!(!m1 && cotangent), "one mesh takes no per-particle cotangent (use jpm_cic_readgrad_f32)");
+  JPM_CHECK_MESH(nx, ny, nz);
+  if (relative)
+    JPM_CHECK_ARG((int64_t)(nx - 2 * hx) * (ny - 2 * hy) * nz == np, "np != particle grid");
+  if (np == 0) return JPM_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int pny = ny - 2 * hy;
+#define RG(REL_, NM_, ACC_)                                                                                  \
+  readgradn_kernel<REL_, NM_, ACC_><<<grid_for(np), 256, 0, s>>>(grad, m0, m1, m2, pos_or_disp, cotangent, scale, np, \
+                                                                 nx, ny, nz, pny, nz, hx, hy)
+  if (m1) {
+    if (relative) { if (accumulate) RG(true, 3, true); else RG(true, 3, false); }
+    else { if (accumulate) RG(false, 3, true); else RG(false, 3, false); }
+  } else {
+    if (relative) { if (accumulate) RG(true, 1, true); else RG(true, 1, false); }
+    else { if (accumulate) RG(false, 1, true); else RG(false, 1, false); }
+  }
+#undef RG
   JPM_LAUNCH_CHECK();
   return JPM_OK;
 }

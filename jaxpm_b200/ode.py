@@ -216,10 +216,15 @@ class _DriftKickStep(torch.autograd.Function):
         (pos1,) = ctx.saved_tensors
         d, k, mesh_shape, relative = ctx.cfg
         g_vel1 = g_vel1.contiguous()
-        with torch.enable_grad():
-            x = pos1.detach().requires_grad_(True)
-            F = pm_forces(x, mesh_shape=mesh_shape, paint_absolute_pos=not relative)
-            (gx,) = torch.autograd.grad(F, x, ops.axpby(k, g_vel1))
+        from . import pm as _pm
+        if _pm._FAST_API and _pm._FUSED_VJP and ops.fast_path_shape(mesh_shape):
+            # the force value is not needed here, only its vector-Jacobian product: straight to the fused adjoint passes
+            gx = _pm._pm_forces_vjp_fused(pos1, ops.axpby(k, g_vel1), mesh_shape, relative, 0.0, None)
+        else:
+            with torch.enable_grad():
+                x = pos1.detach().requires_grad_(True)
+                F = pm_forces(x, mesh_shape=mesh_shape, paint_absolute_pos=not relative)
+                (gx,) = torch.autograd.grad(F, x, ops.axpby(k, g_vel1))
         g_pos = ops.axpby(1.0, gx, 1.0, g_pos1.contiguous()) if g_pos1 is not None else gx
         g_vel = ops.axpby(1.0, g_vel1, d, g_pos)
         return g_pos, g_vel, None, None, None, None

@@ -155,6 +155,43 @@ def cic_readgrad(mesh, pos_or_disp, relative=False, halo=(0, 0), want_value=True
             grad.reshape(p.shape) if want_grad else None)
 
 
+def cic_readgrad3(mesh3, pos_or_disp, cotangent, relative=False, halo=(0, 0), scale=1.0, out=None):
+    """sum_d cotangent[..., d] * d read(mesh3[d]) / d x in one pass (the read half of the pm_forces adjoint)."""
+    m = as_f32(mesh3)
+    p = as_f32(pos_or_disp, m.device).reshape(-1, 3)
+    u = as_f32(cotangent, m.device).reshape(-1, 3)
+    acc = out is not None
+    g = out if acc else torch.empty_like(p)
+    call("jpm_cic_readgrad3_f32", stream(), ptr(g, torch.float32), ptr(m[0]), ptr(m[1]), ptr(m[2]), ptr(p), ptr(u),
+         float(scale), p.shape[0], *m.shape[1:], halo[0], halo[1], int(relative), int(acc))
+    return g
+
+
+def cic_readgrad1_(grad, mesh, pos_or_disp, relative=False, halo=(0, 0), scale=1.0):
+    """grad += scale * d read(mesh) / d x (the paint adjoint), accumulated in place."""
+    m = as_f32(mesh)
+    p = as_f32(pos_or_disp, m.device).reshape(-1, 3)
+    call("jpm_cic_readgrad3_f32", stream(), ptr(grad, torch.float32), ptr(m), None, None, ptr(p), None, float(scale),
+         p.shape[0], *m.shape, halo[0], halo[1], int(relative), 1)
+    return grad
+
+
+def cic_paint3_(mesh3, pos_or_disp, weights3, relative=False, halo=(0, 0), scale=1.0):
+    """mesh3[d] += paint(x; weight = scale * weights3[..., d]) for the three components in one pass."""
+    p = as_f32(pos_or_disp, mesh3.device).reshape(-1, 3)
+    w = as_f32(weights3, mesh3.device).reshape(-1, 3)
+    call("jpm_cic_paint3_f32", stream(), ptr(mesh3, torch.float32), ptr(p), ptr(w), float(scale), p.shape[0],
+         *mesh3.shape[1:], halo[0], halo[1], int(relative))
+    return mesh3
+
+
+def fd_divergence3(g3):
+    """sum_d D_d g3[d] with the 4th-order central difference (the real-space form of the gradient kernel)."""
+    out = torch.empty(g3.shape[1:], dtype=torch.float32, device=g3.device)
+    call("jpm_fd_divergence3_f32", stream(), ptr(out), ptr(g3, torch.float32), *g3.shape[1:])
+    return out
+
+
 def read3_kick_drift_(force3, pos, vel, kick, drift, relative=False, halo=(0, 0), pos_prev=None,
                       vel_prev=None, use_new_vel=True, forces_out=None):
     """Fused read3 + kick + drift.  Kick-drift form is in place on (pos, vel); with

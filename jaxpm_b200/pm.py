@@ -21,10 +21,38 @@ from .growth import dGf2a, dGfa, growth_factor, growth_factor_second, growth_rat
 import os as _os
 
 _FAST_API = _os.environ.get("JPM_FAST_API", "1") != "0"   # JPM_FAST_API=0: order-preserving kernels + cuFFT everywhere
+_FUSED_VJP = _os.environ.get("JPM_FUSED_VJP", "1") != "0"  # 0: the unfused adjoint (3 gathers + 3 paints + cuFFT)
 
 
 def _filter_key(ft):
     return None if ft is None else (ft[0], float(ft[1]))
+
+
+def _pm_forces_vjp_fused(positions, u, mesh_shape, relative, r_split, filter_tab):
+    """Cotangent u[..., 3] of the forces -> gradient with respect to the positions, on the fused passes (power-of-two
+    meshes): recompute the force meshes through the fused FFT chain, ONE pass over the particles for the read adjoint
+    (readgrad3), ONE for the three weighted paints (paint3), the real-space divergence of those meshes
+    (sum_d L_d^T G_d = -Phi sum_d D_d G_d, D_d = the difference stencil the gradient kernel is the symbol of), ONE
+    transform pair on the potential chain, and the paint adjoint accumulated in place.  Before: 4 gathers, 3 paints,
+    6 axpys and 5 cuFFT transforms + a k-space pass per force evaluation."""
+    plan = ops.get_plan(mesh_shape, positions.device)
+    rho = torch.zeros(plan.shape, dtype=torch.float32, device=positions.device)
+    if relative:
+        ops.cic_paint_dx_(rho, positions)
+    else:
+        ops.cic_paint_(rho, positions)
+    f3 = ops.force_meshes_from_density_fused(rho, plan, r_split, filter_tab)
+    del rho
+    g = ops.cic_readgrad3(f3, positions, u, relative)
+    del f3
+    G = torch.zeros((3, *plan.shape), dtype=torch.float32, device=positions.device)
+    ops.cic_paint3_(G, positions, u, relative)
+    S = ops.fd_divergence3(G)
+    del G
+    psi = ops.potential_from_density_fused(S, plan, r_split, filter_tab)
+    del S
+    ops.cic_readgrad1_(g, psi, positions, relative, scale=-1.0)
+    return g.reshape(positions.shape)
 
 
 class _PMForces(torch.autograd.Function):
@@ -32,6 +60,12 @@ class _PMForces(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, positions, mesh_shape, relative, r_split, filter_tab):
+        if _FAST_API and _FUSED_VJP and ops.fast_path_shape(mesh_shape) and positions.numel() > 0:
+            # value on the tile kernels; the backward pass recomputes what it needs (nothing but the positions is kept)
+            ctx.save_for_backward(positions)
+            ctx.cfg = (None, relative, r_split, filter_tab)
+            ctx.mesh_shape = tuple(mesh_shape)
+            return ops.pm_forces_tiles(positions, mesh_shape, relative, float(r_split), filter_tab)
         plan = ops.get_plan(mesh_shape, positions.device)
         rho = torch.zeros(plan.shape, dtype=torch.float32, device=positions.device)
         if relative:
@@ -46,6 +80,11 @@ class _PMForces(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, u):
+        if ctx.cfg[0] is None:
+            (positions,) = ctx.saved_tensors
+            _, relative, r_split, filter_tab = ctx.cfg
+            return _pm_forces_vjp_fused(positions, u.contiguous(), ctx.mesh_shape, relative, r_split, filter_tab), \
+                None, None, None, None
         positions, f3 = ctx.saved_tensors
         plan, relative, r_split, filter_tab = ctx.cfg
         u = u.contiguous().reshape(-1, 3)

@@ -95,3 +95,57 @@ def test_recompute_driver_equals_plain_autograd(cuda):
         grads.append((x.grad.cpu().numpy(), v.grad.cpu().numpy()))
     for a, b in zip(grads[0], grads[1]):
         assert np.abs(a - b).max() < 1e-5 * np.abs(b).max()
+
+
+@pytest.mark.parametrize("relative", [True, False])
+def test_fused_adjoint_passes(cuda, relative):
+    """The fused reverse-mode passes of pm_forces (readgrad3, paint3, the real-space divergence + one transform pair on
+    the potential chain) against the unfused adjoint (three gathers, three paints, cuFFT + the transposed k-space pass)
+    and their building blocks against plain compositions."""
+    from jaxpm_b200 import ops
+    from jaxpm_b200 import pm as jpm_pm
+    shape = (32, 16, 64)
+    rng = np.random.default_rng(5)
+    grid = np.stack(np.meshgrid(*[np.arange(s) for s in shape], indexing="ij"), -1).astype(np.float32)
+    disp = (1.5 * rng.standard_normal((*shape, 3))).astype(np.float32)
+    x = T(disp if relative else grid + disp, cuda)
+    u = T(rng.standard_normal((*shape, 3)).astype(np.float32), cuda)
+    m3 = T(rng.standard_normal((3, *shape)).astype(np.float32), cuda)
+    # readgrad3 == sum of three scaled readgrads; accumulate form of the one-mesh variant
+    ref = torch.zeros_like(x).reshape(-1, 3)
+    for d in range(3):
+        _, gd = ops.cic_readgrad(m3[d], x, relative, want_value=False, grad_scale=u[..., d].contiguous().reshape(-1))
+        ref += gd.reshape(-1, 3)
+    got = ops.cic_readgrad3(m3, x, u, relative)
+    assert float((got - ref).abs().max() / ref.abs().max()) < 1e-5
+    _, g1 = ops.cic_readgrad(m3[0], x, relative, want_value=False)
+    acc = got.clone()
+    ops.cic_readgrad1_(acc, m3[0], x, relative, scale=-2.0)
+    assert float((acc - (got - 2.0 * g1.reshape(-1, 3))).abs().max() / ref.abs().max()) < 1e-5
+    # paint3 == three weighted paints
+    G = torch.zeros((3, *shape), device=cuda)
+    ops.cic_paint3_(G, x, u, relative)
+    for d in range(3):
+        one = torch.zeros(shape, device=cuda)
+        w = u[..., d].contiguous()
+        (ops.cic_paint_dx_ if relative else ops.cic_paint_)(one, x, w)
+        assert float((G[d] - one).abs().max() / one.abs().max()) < 1e-5
+    # divergence == the 4th-order central differences, periodic
+    D = lambda f, ax: (8 * (torch.roll(f, -1, ax) - torch.roll(f, 1, ax)) - (torch.roll(f, -2, ax) - torch.roll(f, 2, ax))) / 12
+    ref_div = D(m3[0], 0) + D(m3[1], 1) + D(m3[2], 2)
+    assert float((ops.fd_divergence3(m3) - ref_div).abs().max() / ref_div.abs().max()) < 1e-5
+    # the whole vector-Jacobian product, with and without the long-range split
+    for r_split in (0.0, 1.3):
+        outs = {}
+        for fused in (True, False):
+            jpm_pm._FUSED_VJP = fused
+            try:
+                xx = x.clone().requires_grad_(True)
+                F = jpm_pm.pm_forces(xx, mesh_shape=shape, paint_absolute_pos=not relative, r_split=r_split)
+                (g,) = torch.autograd.grad(F, xx, u)
+                outs[fused] = (F.detach(), g)
+            finally:
+                jpm_pm._FUSED_VJP = True
+        assert float((outs[True][0] - outs[False][0]).abs().max() / outs[False][0].abs().max()) < 1e-5
+        err = float((outs[True][1] - outs[False][1]).abs().max() / outs[False][1].abs().max())
+        assert err < 2e-5, (r_split, err)
