@@ -111,7 +111,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_s = 128 if (args.steps + args.warmup) <= 12 else 64
+    n_s = 128 if (args.steps + args.warmup) <= 20 else 64     # ~10 s per 128^3 step on 16 host cores
     rate, sps, cores = cpu_step_rate(n_s, args.steps, args.warmup)
     sample = (f"{args.steps} drift-kick steps of a {n_s}^3-particle / {n_s}^3-mesh sub-box of the {args.size}^3 "
               f"workload (same 1 Mpc/h cells, Planck15 ICs, clustered 1LPT state at a = 0.775), oracle NumPy/SciPy "
