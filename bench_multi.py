@@ -20,7 +20,10 @@ def run_multi(args, world, rank, dev):
     from jaxpm_b200.pm import linear_field, lpt
 
     N = args.size
-    pdims = (world, 1)
+    # default process grid: x slabs up to 4 ranks; at 8 ranks 4x2 pencils - a 512^3 slab is then only 64 planes thick
+    # against 2 x 29 ghost planes, and the clustered state loads the slabs unevenly (paint 0.20 ... 0.38 ms over the
+    # ranks, 1.62 ms/step) where the pencils stay balanced (0.21 ... 0.25 ms, 1.41 ms/step; profiles/r02m8c_*)
+    pdims = (4, 2) if world == 8 else (world, 1)
     if getattr(args, "pdims", None):
         pdims = tuple(int(v) for v in args.pdims.lower().split("x"))
         assert pdims[0] * pdims[1] == world, f"--pdims {args.pdims} needs {pdims[0] * pdims[1]} ranks"
@@ -140,8 +143,11 @@ def run_multi(args, world, rank, dev):
                 acc[name] = acc.get(name, 0.0) + ms / reps
         names = list(acc)
         tt = torch.tensor([acc[n] for n in names], device=dev)
+        tmin = tt.clone()
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
         timing = {"stage_ms_max_over_ranks": {n: round(float(v), 4) for n, v in zip(names, tt)},
+                  "stage_ms_min_over_ranks": {n: round(float(v), 4) for n, v in zip(names, tmin)},
                   "ghost_planes_used": stepper.plan.ghost_width(), "ghost_planes_allocated": h}
     # NVLink bytes this rank sends + receives per step on the slab path (remote stores of the two FFT transposes,
     # ghost planes read for the halo reduce, ghost planes written for the halo fill), against the measured
