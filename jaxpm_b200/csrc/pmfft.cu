@@ -987,8 +987,14 @@ zinv_kernel(const __grid_constant__ Slab sl, const float2* __restrict__ twh, con
 // in y and z are periodic images inside the padded array (index -/+ n), in x too when P == 1; the x planes of a
 // slab beyond what the neighbours filled hold nothing a particle within the halo reach reads.
 // HBM: 4 B/cell read + 12 B/cell written; the +-2 planes / rows are L2 / L1 hits.
-constexpr int kGradPlanes = 8;      // x planes per thread: the +-2 x neighbours slide through registers
-__global__ void __launch_bounds__(256)
+#ifndef JPM_GRAD_PLANES
+#define JPM_GRAD_PLANES 8
+#endif
+#ifndef JPM_GRAD_MINCTAS
+#define JPM_GRAD_MINCTAS 4   // register cap for 4 resident CTAs per SM (64 registers instead of 78): 0.489 -> 0.414 ms
+#endif                       // at 512^3; 5 (48 registers) 0.423, 6 (40, spills) 0.61; 16 planes per thread: no gain
+constexpr int kGradPlanes = JPM_GRAD_PLANES;      // x planes per thread: the +-2 x neighbours slide through registers
+__global__ void __launch_bounds__(256, JPM_GRAD_MINCTAS)
 fdgrad_kernel(const __grid_constant__ Slab sl, int x_lo, int x_hi, unsigned* __restrict__ fmax_bits) {
   const int nzp = sl.nzp, nyp = sl.nyp, nz4 = nzp / 4;
   const int z4 = blockIdx.x * 32 + (threadIdx.x & 31);

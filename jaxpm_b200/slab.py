@@ -42,6 +42,35 @@ def slab_supported(global_shape, pdims, halo_x, halo_y=None):
     return True
 
 
+def pencil_targets(pdims, rank, global_shape, gx, gy, xl, y0, ge, rows=16, G=4):
+    """Host restatement of the routing rule of the z passes on a pencil grid (`pencil_targets` in csrc/pmfft.cu), for
+    documentation and the CPU tests: which arrays hold plane `xl` of FFT slab `rank`, rows `y0 .. y0 + rows - 1`.
+
+    Returns [(owner_rank, plane_in_its_array, first_array_row, r0, r1)]: tile rows r0 <= r < r1 live in the array of
+    `owner_rank` at plane `plane` (0 = its first ghost plane), rows `first_array_row + r`.  The first entry is the
+    pencil that owns the rows (all of them); the others are the ghost images held by the x / y / corner neighbours
+    (`ge` ghost planes / rows per side in use).  The forward z pass SUMS the entries (halo reduce + row-group
+    transpose), the inverse z pass WRITES to all of them (halo fill)."""
+    px, py = pdims
+    nx, ny = global_shape[:2]
+    lx, Lx, Ly = nx // (px * py), nx // px, ny // py
+    a, b = divmod(rank, py)
+    xq = b * lx + xl
+    by, yl0 = divmod(y0, Ly)
+    gex, gey = min(gx, ge), min(gy, ge)
+    xs = [(a, gx + xq)]
+    if xq < gex:
+        xs.append(((a - 1) % px, gx + Lx + xq))
+    if xq >= Lx - gex:
+        xs.append(((a + 1) % px, xq - (Lx - gx)))
+    ys = [(by, G + gy + yl0, 0, rows)]
+    if yl0 < gey:
+        ys.append(((by - 1) % py, G + gy + Ly + yl0, 0, min(rows, gey - yl0)))
+    if yl0 + rows > Ly - gey:
+        ys.append(((by + 1) % py, G + gy + yl0 - Ly, max(0, Ly - gey - yl0), rows))
+    return [(xr * py + yc, xp, yr, r0, r1) for xr, xp in xs for yc, yr, r0, r1 in ys]
+
+
 class SlabPlan:
     """One rank's jpm_plan of the slab / pencil decomposition (buffers + peer mappings).  `nranks` is the rank count
     of an x-slab grid, or pass `pdims=(px, py)` (rank = a py + b) with the y ghost width `gy` for a pencil grid."""

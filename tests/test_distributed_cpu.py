@@ -212,3 +212,58 @@ def test_slab_routing_rule():
     assert not slab_supported((32, 32, 24), (2, 1), 8)            # not a power of two
     assert not slab_supported((512, 512, 512), (8, 1), 65)        # halo wider than a slab
     assert not slab_supported((64, 64, 64), (8, 1), 0)
+
+
+@pytest.mark.parametrize("pdims,shape,gx,gy,ge", [((2, 2), (32, 32), 8, 8, 5), ((2, 4), (64, 64), 8, 8, 8), ((4, 2), (64, 64), 16, 6, 9),
+                                                  ((1, 4), (32, 64), 4, 8, 3), ((1, 2), (64, 32), 8, 16, 16)])
+def test_pencil_exchange_rule(pdims, shape, gx, gy, ge):
+    """The routing rule of the fused path on pencil grids (slab.pencil_targets, the host restatement of the device
+    function the z passes use), on a 2-D model (z is local): every rank paints into its pencil + `ge` ghost planes /
+    rows; the forward pass must hand every FFT slab the periodic global sum (halo reduce of
+    jaxpm/distributed.py:61-85 + the row-group transpose), the inverse pass must fill every rank's pencil AND ghost
+    frame, corners included, with the global field (halo fill, jaxpm/painting.py:248-252)."""
+    from jaxpm_b200.slab import pencil_targets
+    px, py = pdims
+    nx, ny = shape
+    P, G, rows = px * py, 4, 16
+    lx, Lx, Ly = nx // P, nx // px, ny // py
+    rng = np.random.default_rng(3)
+    gex, gey = min(gx, ge), min(gy, ge)
+    local, truth = [], np.zeros(shape)
+    for r in range(P):
+        a, b = divmod(r, py)
+        arr = np.zeros((Lx + 2 * gx, Ly + 2 * gy + 2 * G))
+        # what a paint can touch: the pencil and ge ghost planes / rows around it
+        x0, x1, y0, y1 = gx - gex, gx + Lx + gex, G + gy - gey, G + gy + Ly + gey
+        arr[x0:x1, y0:y1] = rng.standard_normal((x1 - x0, y1 - y0))
+        local.append(arr)
+        xs = (np.arange(x0, x1) - gx + a * Lx) % nx
+        ys = (np.arange(y0, y1) - G - gy + b * Ly) % ny
+        np.add.at(truth, (xs[:, None], ys[None, :]), arr[x0:x1, y0:y1])
+    # forward: slab r, plane xl, row tile y0 = sum over the targets
+    got = np.zeros(shape)
+    for r in range(P):
+        for xl in range(lx):
+            for y0 in range(0, ny, rows):
+                acc = np.zeros(rows)
+                for owner, plane, row0, r0, r1 in pencil_targets(pdims, r, shape, gx, gy, xl, y0, ge, rows, G):
+                    acc[r0:r1] += local[owner][plane, row0 + r0:row0 + r1]
+                got[r * lx + xl, y0:y0 + rows] = acc
+    np.testing.assert_allclose(got, truth, rtol=0, atol=1e-12)
+    # inverse: every rank's pencil + ghost frame receives the global field
+    field = rng.standard_normal(shape)
+    out = [np.full_like(a_, np.nan) for a_ in local]
+    for r in range(P):
+        for xl in range(lx):
+            for y0 in range(0, ny, rows):
+                for owner, plane, row0, r0, r1 in pencil_targets(pdims, r, shape, gx, gy, xl, y0, ge, rows, G):
+                    out[owner][plane, row0 + r0:row0 + r1] = field[r * lx + xl, y0 + r0:y0 + r1]
+    for r in range(P):
+        a, b = divmod(r, py)
+        x0, x1, y0, y1 = gx - gex, gx + Lx + gex, G + gy - gey, G + gy + Ly + gey
+        xs = (np.arange(x0, x1) - gx + a * Lx) % nx
+        ys = (np.arange(y0, y1) - G - gy + b * Ly) % ny
+        np.testing.assert_array_equal(out[r][x0:x1, y0:y1], field[xs[:, None], ys[None, :]])
+        rest = out[r].copy()
+        rest[x0:x1, y0:y1] = np.nan
+        assert np.isnan(rest).all()          # nothing is written outside the frame in use
