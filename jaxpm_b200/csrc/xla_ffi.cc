@@ -230,6 +230,44 @@ XLA_FFI_DEFINE_HANDLER_SYMBOL(JpmGreensDiv, GreensDivImpl,
                                   .Attr<float>("norm")
                                   .Attr<float>("r_split"));
 
+// the whole vector-Jacobian product of pm_forces with respect to the positions on the fused passes (what the
+// custom_vjp rule of pm_forces binds: jaxpm_b200/pm.py:_pm_forces_vjp_fused).  f3 = the force meshes recomputed by
+// JpmDensityToForceMeshes; workspace: three meshes G3 + one mesh S + one mesh psi, owned by XLA (Ret buffers).
+static ffi::Error PmForcesVjpImpl(cudaStream_t s, ffi::Buffer<ffi::F32> f3, ffi::Buffer<ffi::F32> pos,
+                                  ffi::Buffer<ffi::F32> cotangent, ffi::ResultBuffer<ffi::F32> grad,
+                                  ffi::ResultBuffer<ffi::F32> g3, ffi::ResultBuffer<ffi::F32> div,
+                                  ffi::ResultBuffer<ffi::F32> psi, int64_t plan, float r_split, int32_t relative) {
+  auto d = f3.dimensions();   // [3, nx, ny, nz]
+  const int64_t nc = (int64_t)d[1] * d[2] * d[3], np = (int64_t)pos.element_count() / 3;
+  int32_t rc = jpm_cic_readgrad3_f32(s, grad->typed_data(), f3.typed_data(), f3.typed_data() + nc,
+                                     f3.typed_data() + 2 * nc, pos.typed_data(), cotangent.typed_data(), 1.0f, np, d[1],
+                                     d[2], d[3], 0, 0, relative, 0);
+  if (rc) return status(rc);
+  cudaMemsetAsync(g3->typed_data(), 0, g3->size_bytes(), s);
+  if ((rc = jpm_cic_paint3_f32(s, g3->typed_data(), pos.typed_data(), cotangent.typed_data(), 1.0f, np, d[1], d[2], d[3],
+                               0, 0, relative)))
+    return status(rc);
+  if ((rc = jpm_fd_divergence3_f32(s, div->typed_data(), g3->typed_data(), d[1], d[2], d[3]))) return status(rc);
+  if ((rc = jpm_density_to_potential_fused(reinterpret_cast<jpm_plan*>(plan), s, div->typed_data(), psi->typed_data(),
+                                           r_split, nullptr, 0, 0.f)))
+    return status(rc);
+  return status(jpm_cic_readgrad3_f32(s, grad->typed_data(), psi->typed_data(), nullptr, nullptr, pos.typed_data(),
+                                      nullptr, -1.0f, np, d[1], d[2], d[3], 0, 0, relative, 1));
+}
+XLA_FFI_DEFINE_HANDLER_SYMBOL(JpmPmForcesVjp, PmForcesVjpImpl,
+                              ffi::Ffi::Bind()
+                                  .Ctx<ffi::PlatformStream<cudaStream_t>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Arg<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Ret<ffi::Buffer<ffi::F32>>()
+                                  .Attr<int64_t>("plan")
+                                  .Attr<float>("r_split")
+                                  .Attr<int32_t>("relative"));
+
 // ---- multi-GPU slab plan under shard_map (one call per shard, collective: every shard must be launched) --------
 static ffi::Error SlabForcesImpl(cudaStream_t s, ffi::Buffer<ffi::F32> density_local, ffi::ResultBuffer<ffi::F32> force3,
                                  int64_t plan, float r_split) {

@@ -55,5 +55,5 @@ def test_xla_ffi_handlers_type_check():
     src = open(os.path.join(root, "jaxpm_b200", "csrc", "xla_ffi.cc")).read()
     for name in ("JpmCicPaint", "JpmCicRead", "JpmCicPaintDx", "JpmCicRead3", "JpmRead3KickDrift",
                  "JpmDensityToForceMeshes", "JpmSimForces", "JpmSimStep", "JpmCicReadGrad", "JpmCicPaintGrad",
-                 "JpmGreensDiv", "JpmSlabForces", "JpmNormalField"):
+                 "JpmGreensDiv", "JpmPmForcesVjp", "JpmSlabForces", "JpmNormalField"):
         assert f"XLA_FFI_DEFINE_HANDLER_SYMBOL({name}," in src, name
