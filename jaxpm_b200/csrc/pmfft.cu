@@ -11,8 +11,13 @@
 //   reference: jaxpm/pm.py:41-56 (fft3d, invlaplace * longrange, -gradient_kernel, ifft3d x3),
 //              jaxpm/kernels.py:10-23,41-115, jaxpm/distributed.py:37-42.
 //
-// HBM traffic per force evaluation (Nc cells, fp32): 4+4, 4+4, 4+12, 12+12, 12+12 = 80 B/cell against
-// 8+16+24 = 48 B/cell algorithmic and ~130 B/cell for cuFFT (3 passes per 3-D transform) + the k-space pass.
+// HBM traffic per force evaluation (Nc cells, fp32), measured with ncu at 512^3 (profiles/traffic_512.json):
+//   three-transform chain: 8 + 8 + 12 + 20 + 25 = 73 B/cell (9.8 GB) against 8 + 16 + 24 = 48 B/cell algorithmic and
+//                          ~130 B/cell for cuFFT (3 passes per 3-D transform) + the k-space pass;
+//   potential chain:       8 + 8 + 8 + 8 + 8 = 40 B/cell (5.4 GB) + the gradient pass 4 + 12 = 16 B/cell (2.2 GB):
+//                          ONE inverse transform psi = IFFT(delta_k / k^2), the three force meshes by the 4th-order
+//                          difference stencil the reference's gradient kernel is the symbol of (X-pot, Y-pot, gradient
+//                          pass below; chosen per step by the measured fp32 error bound, csrc/sim.cu).
 //
 // Each 1-D FFT is a Stockham autosort transform in shared memory, radix 8/4, twiddles from a table
 // computed in double precision.  Column passes keep a [N][C] tile (C consecutive kz = one 128-byte or
