@@ -89,6 +89,19 @@ int32_t jpm_cic_read_f32(void* stream, float* out, const float* mesh, const floa
 int32_t jpm_cic_read_dx_f32(void* stream, float* out, const float* mesh, const float* disp,
                             int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy);
 
+/* float64 forms of the four CIC primitives above (what the reference computes under jax_enable_x64, the mode of
+ * its distributed tests, tests/test_distributed_pm.py:30): positions / displacements, weights and meshes are double and
+ * the index / weight rules run in double.  Same argument meaning as the _f32 entries (paint accumulates into `mesh`;
+ * weight: per-particle array or NULL + scalar; the _dx forms take the padded local mesh [nx+2hx][ny+2hy][nz]). */
+int32_t jpm_cic_paint_f64(void* stream, double* mesh, const double* positions, const double* weight,
+                          double weight_scalar, int64_t np, int32_t nx, int32_t ny, int32_t nz);
+int32_t jpm_cic_paint_dx_f64(void* stream, double* mesh, const double* disp, const double* weight,
+                             double weight_scalar, int32_t nx, int32_t ny, int32_t nz, int32_t hx, int32_t hy);
+int32_t jpm_cic_read_f64(void* stream, double* out, const double* mesh, const double* positions, int64_t np,
+                         int32_t nx, int32_t ny, int32_t nz);
+int32_t jpm_cic_read_dx_f64(void* stream, double* out, const double* mesh, const double* disp, int32_t nx,
+                            int32_t ny, int32_t nz, int32_t hx, int32_t hy);
+
 /* The three reads + jnp.stack of jaxpm/pm.py:54-56 in one pass: out[np][3] =
  * scale * (read(fx), read(fy), read(fz)).  relative != 0 selects the
  * painting_utils rule with halo offsets (then np = nx*ny*nz of the particle grid

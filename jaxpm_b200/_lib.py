@@ -85,6 +85,10 @@ SIGNATURES = {
     "jpm_cic_readgrad3_f32": ([vp, vp, vp, vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32, i32], i32),
     "jpm_cic_paint3_f32": ([vp, vp, vp, vp, f32, i64, i32, i32, i32, i32, i32, i32], i32),
     "jpm_fd_divergence3_f32": ([vp, vp, vp, i32, i32, i32], i32),
+    "jpm_cic_paint_f64": ([vp, vp, vp, vp, C.c_double, i64, i32, i32, i32], i32),
+    "jpm_cic_paint_dx_f64": ([vp, vp, vp, vp, C.c_double, i32, i32, i32, i32, i32], i32),
+    "jpm_cic_read_f64": ([vp, vp, vp, vp, i64, i32, i32, i32], i32),
+    "jpm_cic_read_dx_f64": ([vp, vp, vp, vp, i32, i32, i32, i32, i32], i32),
     "jpm_kernel_launch_count": ([], i64),
     "jpm_normal_field_f32": ([vp, vp, i32, i32, i32, i32, i32, i32, C.c_uint64, C.c_uint32], i32),
     "jpm_linear_field_f32": ([vp, vp, vp, vp, vp, i32, f32, f32, f32, f32, f32, f32], i32),

@@ -2,7 +2,8 @@
 /root/reference/jaxpm/painting.py (cic_paint :48-75, cic_read :109-128,
 cic_paint_dx :192-215, cic_read_dx :239-260), backed by the sm_100a kernels.
 
-Arrays are float32 CUDA tensors (torch is the device-memory provider here; in a
+Arrays are float32 CUDA tensors - or float64 ones for the four primitives below, which then compute in double like
+the reference under jax_enable_x64 (no gradient rules, single device) - (torch is the device-memory provider here; in a
 JAX deployment the same C-ABI entry points are bound through XLA FFI, see
 INTEGRATION.md).  Gradients are provided the way `jax.grad` of the reference
 would produce them (paint^T = read, read^T = paint, plus the position
@@ -113,6 +114,27 @@ class _CicReadDx(torch.autograd.Function):
         return gmesh, gd, None
 
 
+def _is_f64(t):
+    return isinstance(t, torch.Tensor) and t.dtype == torch.float64
+
+
+def _f64_weight(weight, n, device):
+    """(per-particle float64 array or None, scalar) for the float64 entries."""
+    if _is_scalar(weight):
+        return None, float(weight)
+    w = weight.to(device=device, dtype=torch.float64).contiguous().reshape(-1)
+    if w.numel() != n:
+        raise ValueError("Weight shape must match particle shape")
+    return w, 1.0
+
+
+def _f64_guard(*tensors, sharding=None):
+    if sharding is not None and sharding.size > 1:
+        raise NotImplementedError("float64 painting is single-device (the sharded paths compute in float32)")
+    if any(isinstance(t, torch.Tensor) and t.requires_grad for t in tensors):
+        raise NotImplementedError("float64 painting carries no gradient rules; use float32 inputs for reverse / forward mode")
+
+
 def _prep_weight(weight, device):
     if _is_scalar(weight):
         return weight if isinstance(weight, torch.Tensor) else float(weight)
@@ -122,6 +144,15 @@ def _prep_weight(weight, device):
 def cic_paint(grid_mesh, positions, weight=1., halo_size=0, sharding=None):
     """Paints positions onto mesh (accumulating into a copy of `grid_mesh`).
     mesh: [nx, ny, nz]; positions: [..., 3] in cell units (reshaped to (nx,ny,nz,3), painting.py:57)."""
+    if _is_f64(positions):
+        # x64 mode of the reference (jax_enable_x64, tests/test_distributed_pm.py:30): rules and accumulation in double
+        from ._lib import call, ptr, stream
+        _f64_guard(grid_mesh, positions, weight, sharding=sharding)
+        out = grid_mesh.to(device=positions.device, dtype=torch.float64).clone().contiguous()
+        pos = positions.contiguous().reshape(-1, 3)
+        w, ws = _f64_weight(weight, pos.shape[0], pos.device)
+        call("jpm_cic_paint_f64", stream(), ptr(out), ptr(pos), ptr(w), ws, pos.shape[0], *out.shape)
+        return out
     grid_mesh = as_f32(grid_mesh)
     positions = as_f32(positions, grid_mesh.device)
     if sharding is not None and sharding.size > 1:
@@ -138,6 +169,14 @@ def cic_paint(grid_mesh, positions, weight=1., halo_size=0, sharding=None):
 
 def cic_read(grid_mesh, positions, halo_size=0, sharding=None):
     """Reads the mesh at `positions`; returns positions.shape[:-1] (painting.py:128)."""
+    if _is_f64(positions):
+        from ._lib import call, ptr, stream
+        _f64_guard(grid_mesh, positions, sharding=sharding)
+        mesh = grid_mesh.to(device=positions.device, dtype=torch.float64).contiguous()
+        pos = positions.contiguous().reshape(-1, 3)
+        out = torch.empty(pos.shape[0], dtype=torch.float64, device=pos.device)
+        call("jpm_cic_read_f64", stream(), ptr(out), ptr(mesh), ptr(pos), pos.shape[0], *mesh.shape)
+        return out.reshape(positions.shape[:-1])
     grid_mesh = as_f32(grid_mesh)
     positions = as_f32(positions, grid_mesh.device)
     if sharding is not None and sharding.size > 1:
@@ -150,6 +189,17 @@ def cic_paint_dx(displacements, halo_size=0, sharding=None, weight=1.0, chunk_si
     """Relative-mode paint: particle (i,j,k) sits at (i,j,k)+displacements[i,j,k].
     `chunk_size` is accepted for signature compatibility (the reference scans over
     chunks of 2**24 particles, painting_utils.py:115-131; the kernel needs no chunking)."""
+    if _is_f64(displacements):
+        from ._lib import call, ptr, stream
+        _f64_guard(displacements, weight, sharding=sharding)
+        d = displacements.contiguous()
+        nx, ny, nz = d.shape[:3]
+        if not _is_scalar(weight) and tuple(weight.shape) != tuple(d.shape[:-1]):
+            raise ValueError("Weight shape must match particle shape")
+        w, ws = _f64_weight(weight, nx * ny * nz, d.device)
+        mesh = torch.zeros((nx, ny, nz), dtype=torch.float64, device=d.device)
+        call("jpm_cic_paint_dx_f64", stream(), ptr(mesh), ptr(d), ptr(w), ws, nx, ny, nz, 0, 0)
+        return mesh
     displacements = as_f32(displacements)
     weight = _prep_weight(weight, displacements.device)
     if not _is_scalar(weight) and tuple(weight.shape) != tuple(displacements.shape[:-1]):
@@ -161,6 +211,15 @@ def cic_paint_dx(displacements, halo_size=0, sharding=None, weight=1.0, chunk_si
 
 
 def cic_read_dx(grid_mesh, disp, halo_size=0, sharding=None):
+    if _is_f64(disp):
+        from ._lib import call, ptr, stream
+        _f64_guard(grid_mesh, disp, sharding=sharding)
+        d = disp.contiguous()
+        mesh = grid_mesh.to(device=d.device, dtype=torch.float64).contiguous()
+        nx, ny, nz = d.shape[:3]
+        out = torch.empty((nx, ny, nz), dtype=torch.float64, device=d.device)
+        call("jpm_cic_read_dx_f64", stream(), ptr(out), ptr(mesh), ptr(d), nx, ny, nz, 0, 0)
+        return out
     grid_mesh = as_f32(grid_mesh)
     disp = as_f32(disp, grid_mesh.device)
     if sharding is not None and sharding.size > 1:

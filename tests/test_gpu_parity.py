@@ -563,3 +563,39 @@ def test_density_plane(cuda):
         ref = OP.density_plane(pos, box, center, width, res)
         got = density_plane(T(pos, cuda), box, center, width, res).cpu().numpy()
         assert rel_err(got, ref) < FIELD_TOL
+
+
+@pytest.mark.parametrize("shape", [(16, 16, 16), (24, 40, 18)])
+def test_float64_primitives(cuda, shape):
+    """The x64 mode of the reference (jax_enable_x64, the mode of tests/test_distributed_pm.py:30): float64 positions
+    select the double-precision kernels (index / weight rules and accumulation in double); against the oracle run in
+    float64 to 1e-12, including the dropped-corner edge case and positions outside the box."""
+    from jaxpm_b200.painting import cic_paint, cic_paint_dx, cic_read, cic_read_dx
+    rng = np.random.default_rng(12)
+    grid, disp = displaced(shape, 2.0)
+    pos = (grid + disp).astype(np.float64) + 1e-9 * rng.standard_normal((*shape, 3))
+    pos[0, 0, 0] = (-0.25, -1e-13, shape[2] + 2.5)
+    disp = disp.astype(np.float64) + 1e-9 * rng.standard_normal((*shape, 3))
+    disp[0, 0, 0] = (-1e-13, 0.3, -0.2)
+    disp[1, 1, 1, 0] = -1.0 - 1e-13
+    w = rng.uniform(0.5, 1.5, shape)
+    mesh = rng.standard_normal(shape)
+    T64 = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=cuda)
+    tol = 1e-12
+    for weight, wt in ((1.0, 1.0), (w, T64(w))):
+        ref = OP.cic_paint(np.zeros(shape), pos, weight)
+        got = cic_paint(torch.zeros(shape, dtype=torch.float64, device=cuda), T64(pos), wt)
+        assert got.dtype == torch.float64 and rel_err(got.cpu().numpy(), ref) < tol
+        ref = OP.cic_paint_dx(disp, weight)
+        got = cic_paint_dx(T64(disp), weight=wt)
+        assert got.dtype == torch.float64 and rel_err(got.cpu().numpy(), ref) < tol
+    assert rel_err(cic_read(T64(mesh), T64(pos)).cpu().numpy(), OP.cic_read(mesh, pos)) < tol
+    assert rel_err(cic_read_dx(T64(mesh), T64(disp)).cpu().numpy(), OP.cic_read_dx(mesh, disp)) < tol
+    # float64 resolves what float32 cannot: a displacement of 1e-9 cells changes the painted field
+    a = cic_paint_dx(T64(disp)).cpu().numpy()
+    d2 = disp.copy()
+    d2[2, 3, 4, 0] += 1e-9
+    b = cic_paint_dx(T64(d2)).cpu().numpy()
+    assert 1e-10 < np.abs(a - b).max() < 1e-8
+    with pytest.raises(NotImplementedError):
+        cic_paint_dx(T64(disp).requires_grad_(True))
