@@ -155,6 +155,39 @@ class _ForcesFromSpectrum(torch.autograd.Function):
         return gfield, gpos, None, None, None
 
 
+def _pm_forces_f64(positions, mesh_shape, r_split, paint_absolute_pos, sharding):
+    """The x64 mode of pm_forces (jax_enable_x64, the mode of the reference's distributed tests,
+    tests/test_distributed_pm.py:30): float64 positions -> float64 forces.  Paint and the three reads are the double
+    kernels of csrc/f64.cu; the transforms in between are library FFTs in double (torch.fft = cuFFT D2Z / Z2D) with the
+    k-space kernels of kernels.py:41-115 applied as written.  A parity / reference mode - single device, no gradient
+    rules; the float32 path is the product."""
+    from .painting import cic_paint, cic_paint_dx, cic_read, cic_read_dx
+    if not _single(sharding):
+        raise NotImplementedError("float64 pm_forces is single-device")
+    relative = not paint_absolute_pos
+    if relative:
+        mesh_shape = tuple(positions.shape[:3])
+        rho = cic_paint_dx(positions)
+    else:
+        mesh_shape = tuple(int(n) for n in mesh_shape)
+        rho = cic_paint(torch.zeros(mesh_shape, dtype=torch.float64, device=positions.device), positions)
+    dk = torch.fft.rfftn(rho)
+    dev = rho.device
+    w = [2 * np.pi * torch.fft.fftfreq(n, dtype=torch.float64, device=dev) for n in mesh_shape[:2]]
+    w.append(2 * np.pi * torch.fft.rfftfreq(mesh_shape[2], dtype=torch.float64, device=dev))
+    kx, ky, kz = w[0][:, None, None], w[1][None, :, None], w[2][None, None, :]
+    kk = kx**2 + ky**2 + kz**2
+    pot = dk * torch.where(kk == 0, torch.zeros_like(kk), -1.0 / torch.where(kk == 0, torch.ones_like(kk), kk))
+    if r_split != 0:
+        pot = pot * torch.exp(-kk * r_split**2)
+    out = []
+    for wd in (kx, ky, kz):
+        grad = 1j * (8 * torch.sin(wd) - torch.sin(2 * wd)) / 6.0
+        f = torch.fft.irfftn(-grad * pot, s=mesh_shape)
+        out.append(cic_read_dx(f, positions) if relative else cic_read(f, positions))
+    return torch.stack(out, dim=-1)
+
+
 def pm_forces(positions, mesh_shape=None, delta=None, r_split=0, paint_absolute_pos=True, halo_size=0,
               sharding=None, filter_tab=None):
     """Computes gravitational forces on particles using a PM scheme (pm.py:12-58).
@@ -164,6 +197,8 @@ def pm_forces(positions, mesh_shape=None, delta=None, r_split=0, paint_absolute_
     if mesh_shape is None:
         assert (delta is not None), "If mesh_shape is not provided, delta should be provided"
         mesh_shape = getattr(delta, "mesh_shape", None) or tuple(delta.shape)
+    if isinstance(positions, torch.Tensor) and positions.dtype == torch.float64 and delta is None:
+        return _pm_forces_f64(positions, mesh_shape, float(r_split), paint_absolute_pos, sharding)
     positions = as_f32(positions)
     relative = not paint_absolute_pos
     if not _single(sharding):

@@ -599,3 +599,23 @@ def test_float64_primitives(cuda, shape):
     assert 1e-10 < np.abs(a - b).max() < 1e-8
     with pytest.raises(NotImplementedError):
         cic_paint_dx(T64(disp).requires_grad_(True))
+
+
+@pytest.mark.parametrize("absolute", [False, True])
+def test_float64_pm_forces(cuda, absolute):
+    """pm_forces in the reference's x64 mode: float64 in, float64 out, against the oracle run in float64 (where the
+    float32 product path agrees with it only to ~1e-6)."""
+    from jaxpm_b200.pm import pm_forces
+    shape = (16, 24, 32)
+    grid, disp = displaced(shape, 1.5)
+    x = (grid + disp if absolute else disp).astype(np.float64)
+    ref = OPM.pm_forces(x, mesh_shape=shape, paint_absolute_pos=absolute, r_split=0.0)
+    got = pm_forces(torch.as_tensor(x, device=cuda), mesh_shape=shape, paint_absolute_pos=absolute)
+    assert got.dtype == torch.float64 and got.shape == (*shape, 3)
+    assert rel_err(got.cpu().numpy(), ref) < 1e-10
+    got32 = pm_forces(torch.as_tensor(x.astype(np.float32), device=cuda), mesh_shape=shape, paint_absolute_pos=absolute)
+    e32 = rel_err(got32.cpu().numpy(), ref)
+    assert 1e-9 < e32 < FIELD_TOL
+    ref_s = OPM.pm_forces(x, mesh_shape=shape, paint_absolute_pos=absolute, r_split=1.3)
+    got_s = pm_forces(torch.as_tensor(x, device=cuda), mesh_shape=shape, paint_absolute_pos=absolute, r_split=1.3)
+    assert rel_err(got_s.cpu().numpy(), ref_s) < 1e-10
