@@ -137,7 +137,9 @@ def schedule(cosmo, args, kick_drift_coefficients):
     S, K, W = args.schedule_steps, args.steps, args.warmup
     n_pre = max(W, S - K)
     total = n_pre + K
-    d, k = kick_drift_coefficients(cosmo, 0.1, 0.1 + total * 0.9 / S, total, "symplectic")
+    # more steps than the schedule asked for (a large --steps): still end at a = 1, with proportionally smaller steps
+    a_end = 0.1 + min(total, S) * 0.9 / S
+    d, k = kick_drift_coefficients(cosmo, 0.1, a_end, total, "symplectic")
     return n_pre, d, k
 
 

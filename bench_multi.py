@@ -11,6 +11,23 @@ import torch
 import torch.distributed as dist
 
 
+def nvlink_counters(gpu_index):
+    """(tx_bytes, rx_bytes) summed over the NVLink links of one GPU from the driver's cumulative data counters
+    (`nvidia-smi nvlink -gt d`, KiB per link), or None when the tool does not report them."""
+    import re
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(gpu_index)], capture_output=True, text=True,
+                             timeout=20).stdout
+    except Exception:
+        return None
+    tx = [int(v) for v in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
+    rx = [int(v) for v in re.findall(r"Data Rx:\s*(\d+)\s*KiB", out)]
+    if not tx or not rx:
+        return None
+    return sum(tx) * 1024, sum(rx) * 1024
+
+
 def run_multi(args, world, rank, dev):
     from bench import METRIC, UNIT, ClockSampler, _peaks, schedule
     from jaxpm_b200 import _lib, halo, ops
@@ -56,6 +73,7 @@ def run_multi(args, world, rank, dev):
         step(n)
     dist.barrier()
     torch.cuda.synchronize()
+    nv0 = nvlink_counters(dev.index) if rank == 0 else None      # driver counters around the timed region (rank 0's GPU)
     sampler = ClockSampler(dev.index)
     sampler.start()
     l0 = _lib.launch_count()
@@ -66,6 +84,7 @@ def run_multi(args, world, rank, dev):
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
+    nv1 = nvlink_counters(dev.index) if rank == 0 else None
     launches = _lib.launch_count() - l0
     clocks = sampler.stop()
     t = torch.tensor([e0.elapsed_time(e1) * 1e-3], device=dev)
@@ -181,7 +200,12 @@ def run_multi(args, world, rank, dev):
             regroup_out = ncomp * regroup_in
         sent = transposes + ghosts_out + regroup_out
         ghosts_in = ghosts_in + regroup_in
+        measured = None
+        if nv0 is not None and nv1 is not None:
+            measured = {"tx_bytes_per_step": (nv1[0] - nv0[0]) / K, "rx_bytes_per_step": (nv1[1] - nv0[1]) / K,
+                        "source": "nvidia-smi nvlink -gt d on rank 0's GPU around the timed steps (all links, KiB counters)"}
         nvlink = {"sent_bytes_per_rank_per_step": int(sent), "read_bytes_per_rank_per_step": int(ghosts_in),
+                  "measured_rank0": measured,
                   "sent_GBps_over_whole_step": sent * K / t_dev / 1e9, "peak_GBps_per_direction": 770.0,
                   "frac_of_link_if_not_overlapped": sent / 770e9 / (t_dev / K)}
     peak, peak_kind = _peaks()
