@@ -71,9 +71,12 @@ def run_multi(args, world, rank, dev):
 
     for n in range(n_pre):
         step(n)
+    torch.cuda.synchronize()
+    # driver NVLink counters around the timed region (rank 0's GPU) - read BEFORE the barrier that starts it: the ranks
+    # spin on each other inside the step, a late rank would be timed by all the others
+    nv0 = nvlink_counters(dev.index) if rank == 0 else None
     dist.barrier()
     torch.cuda.synchronize()
-    nv0 = nvlink_counters(dev.index) if rank == 0 else None      # driver counters around the timed region (rank 0's GPU)
     sampler = ClockSampler(dev.index)
     sampler.start()
     l0 = _lib.launch_count()
