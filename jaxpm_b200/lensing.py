@@ -11,8 +11,6 @@ from ._lib import as_f32, call, ptr, stream
 
 def density_plane(positions, box_shape, center, width, plane_resolution, smoothing_sigma=None):
     """Extracts a density plane from the simulation (same arguments and normalisation as the reference)."""
-    if smoothing_sigma is not None:
-        raise NotImplementedError("gaussian smoothing of the plane (utils.gaussian_smoothing) is not on the device yet")
     nx, ny, nz = box_shape
     pos = as_f32(positions).reshape(-1, 3)
     res = int(plane_resolution)
@@ -21,4 +19,8 @@ def density_plane(positions, box_shape, center, width, plane_resolution, smoothi
          res)
     # density normalisation, lensing.py:37-38
     norm = (nx / plane_resolution) * (ny / plane_resolution) * width
-    return ops.axpby(1.0 / norm, plane, out=plane)
+    plane = ops.axpby(1.0 / norm, plane, out=plane)
+    if smoothing_sigma is not None:          # lensing.py:41-42
+        from .utils import gaussian_smoothing
+        plane = gaussian_smoothing(plane, smoothing_sigma)
+    return plane

@@ -159,3 +159,18 @@ def pktranscoh(mesh0, mesh1, box_shape, kedges=None):
     ks, pk0 = power_spectrum(mesh0, box_shape=box_shape, kedges=kedges)
     ks, pk1 = power_spectrum(mesh1, box_shape=box_shape, kedges=kedges)
     return ks, pk0, pk1, (pk1 / pk0)**.5, pk01 / (pk0 * pk1)**.5
+
+
+def gaussian_smoothing(im, sigma):
+    """Gaussian smoothing of a 2-D image with scale `sigma` in pixels - jaxpm/utils.py:208-222: the image spectrum times
+    norm.pdf(|k|, 0, 1 / (2 pi sigma)) / norm.pdf(0, ...) = exp(-2 pi^2 sigma^2 |k|^2), k in cycles per pixel, real
+    part of the inverse transform.  A small library-FFT image operation (light-cone planes), not part of the force loop;
+    works on CPU or CUDA tensors."""
+    im = torch.as_tensor(im)
+    kx = torch.fft.fftfreq(im.shape[0], device=im.device, dtype=torch.float64)
+    ky = torch.fft.fftfreq(im.shape[1], device=im.device, dtype=torch.float64)
+    k2 = kx[:, None]**2 + ky[None, :]**2
+    filt = torch.exp(-2.0 * np.pi**2 * float(sigma)**2 * k2)
+    out = torch.fft.ifft2(torch.fft.fft2(im.to(torch.float64)) * filt).real
+    return out.to(im.dtype if im.dtype.is_floating_point else torch.float32)
+

@@ -36,3 +36,22 @@ def test_host_kernels_against_reference_fixture():
     ref = K.PGD_kernel(kvec, 0.4, 2.5).numpy()
     got = np.interp(kk, np.linspace(0, kmax, tab.size), tab)
     np.testing.assert_allclose(got, ref, atol=2e-5)
+
+
+def test_gaussian_smoothing_matches_the_reference_formula():
+    """jaxpm/utils.py:208-222 restated in NumPy (scipy.stats.norm.pdf filter normalised at k = 0) on a square image."""
+    from scipy.stats import norm
+
+    from jaxpm_b200.utils import gaussian_smoothing
+    rng = np.random.default_rng(4)
+    im = rng.standard_normal((24, 24)).astype(np.float32)
+    for sigma in (0.7, 2.5):
+        kvec = np.stack(np.meshgrid(np.fft.fftfreq(im.shape[0]), np.fft.fftfreq(im.shape[1])), axis=-1)
+        k = np.linalg.norm(kvec, axis=-1)
+        filt = norm.pdf(k, 0, 1.0 / (2.0 * np.pi * sigma))
+        filt /= filt[0, 0]
+        ref = np.fft.ifft2(np.fft.fft2(im) * filt).real
+        got = gaussian_smoothing(torch.as_tensor(im), sigma).numpy()
+        assert got.dtype == np.float32
+        np.testing.assert_allclose(got, ref, atol=2e-6)
+        assert abs(got.mean() - im.mean()) < 1e-6          # the k = 0 mode is untouched
