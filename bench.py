@@ -1,17 +1,24 @@
 #!/usr/bin/env python
 """bench.py — PM particle-steps/s of the B200-native force loop (BASELINE.json metric).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--size 512] [--impl reference] [--grad] [--pdims PXxPY]
 
-A "step" is one pass of the hot path over the resident particle set: zero mesh -> CIC paint ->
-R2C FFT -> fused Green's x gradient pass -> 3x C2R FFT -> fused read3 + kick + drift
-(jaxpm/ode.py:100-117 around jaxpm/pm.py:12-58).  Workload: SIZE^3 particles on a SIZE^3 mesh
-(default 512^3, the size the metric is quoted on), Planck15 Gaussian ICs (L = SIZE Mpc/h), 1LPT at
-a = 0.1, then W untimed + K timed drift-kick steps towards a = 1 (relative/displacement mode, the
-mode of the reference's published runs).
+A "step" is one pass of the hot path over the resident particle set: zero mesh -> CIC paint -> fused FFT chain with the
+k-space kernels inside (three inverse transforms, or one + the 4th-order difference pass where the measured fp32 error
+bound allows) -> fused read3 + kick + drift (jaxpm/ode.py:100-117 around jaxpm/pm.py:12-58).  Workload: SIZE^3 particles
+on a SIZE^3 mesh (default 512^3, the size the metric is quoted on), Planck15 Gaussian ICs from the device generator
+(L = SIZE Mpc/h), 2LPT at a = 0.1, then the 40 drift-kick steps to a = 1 of BASELINE.json's configs (relative /
+displacement mode, the mode of the reference's published runs); the LAST K steps are timed (the most clustered
+state), at least W run untimed before.
 
-Prints ONE JSON line (rank 0).  `--impl reference` times the CPU restatement of the reference
-(oracle/, NumPy/SciPy; JAX is not installable here) on a bounded sub-box of the same workload.
+Prints ONE JSON line (rank 0): `value` (device-timed), `roofline` (per-kernel table from CUDA events at the stage
+boundaries, chain against 48 B/cell, ncu DRAM traffic), `e2e` (a stream of pinned host states through the pipelined
+host entry), `e2e_run` (host ICs -> LPT -> 40 steps -> host state), `api` (pm_forces through the reference's
+signature), `lpt`, `parity` (final P(k) against the order-preserving path / the one-GPU run), `cpu_baseline`.
+N > 1 (bench_multi.py): strong scaling of the same problem on the fused peer-memory path - x slabs up to 4 ranks,
+4x2 pencils at 8 - with min / max stage times over the ranks.  `--grad`: BASELINE.json config 5 (reverse-mode
+gradient of the final P(k) w.r.t. the ICs).  `--impl reference` times the CPU restatement of the reference (oracle/,
+NumPy/SciPy; JAX is not installable here) on a bounded sub-box of the same workload.
 """
 import argparse
 import json
